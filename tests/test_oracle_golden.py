@@ -1,0 +1,109 @@
+"""CPU: pin oracle/gp_kl_oracle.py against fixtures produced by the REFERENCE'S OWN functions
+(oracle/gen_golden.py executes /root/reference/src/Models/*.py unmodified under a TF1 stub)."""
+import numpy as np
+import pytest
+import torch
+
+import gp_kl_oracle as orc
+from conftest import load_golden, rel_err
+
+V1_CASES = ["g1_v1_regular", "g3_v1_ragged_s2", "g5_v1_toy_shape", "g4_v1_fixed_prior_grad"]
+
+
+def _run(g, formulation="reference", **kw):
+    aux = g.get("logvar")
+    return orc.gp_prior_kl_grads(g["mean"], g["times"], g["lengths"], g["ell_q"], g["ell_p"], g["eps"],
+                                 g.get("g_z"), aux=aux, kernel=g["kernel"], posterior=g["posterior"],
+                                 noise=g["noise"], S=g["S"], formulation=formulation, **kw)
+
+
+@pytest.mark.parametrize("name", V1_CASES)
+@pytest.mark.parametrize("formulation", ["reference", "chol"])
+def test_v1_matches_reference_run(name, formulation):
+    g = load_golden(name)
+    out, grads = _run(g, formulation)
+    # KL: 1e-9 relative (both float64 on the same float32-built K)
+    assert rel_err(out["kl_pairs"], g["kl_pairs"]) < 1e-9
+    assert abs(float(out["kl_sum"]) - float(g["kl_sum"])) < 1e-9 * abs(float(g["kl_sum"]))
+    # the reference samples with a float32 Cholesky (Full_GP_VAE_dynamic_time.py:165-168); the oracle
+    # factors in float64, so z agrees to float32 rounding x cond(K_q) (<= ~5e3 here): 1e-5
+    assert rel_err(out["z"], g["z"]) < 1e-5
+    assert rel_err(grads["mean"], g["g_mean"]) < 2e-6
+    assert rel_err(grads["ell_q"], g["g_ell_q"]) < 2e-5
+    if "g_ell_p" in g:
+        assert rel_err(grads["ell_p"], g["g_ell_p"]) < 2e-5
+
+
+def test_g1_known_answer_digits():
+    """KL sum 47.277540134328625, d/d l_q = [-40.395, ~0, 10.218, 5.2501]."""
+    g = load_golden("g1_v1_regular")
+    assert abs(float(g["kl_sum"]) - 47.277540134328625) < 1e-9
+    assert np.allclose(g["kl_pairs"].reshape(3, 4)[0].numpy(), [4.7383, 0.7809, 4.3603, 6.7722], atol=5e-5)
+    g0 = dict(g)
+    g0["g_z"] = None
+    _, grads = _run(g0)
+    assert np.allclose(grads["ell_q"].numpy(), [-40.395, 0.0, 10.218, 5.2501], atol=2e-3)
+
+
+def test_v2_matches_reference_run():
+    g = load_golden("g2_v2_diag")
+    g = dict(g)
+    g["g_z"] = None
+    out, grads = _run(g)
+    # reference takes det(K) in float32 before the log (VAE_GPprior_diag_cov.py:84,:107): 1.8e-7 gap
+    assert abs(float(out["kl_sum"]) - float(g["kl_sum"])) < 1e-6 * abs(float(g["kl_sum"]))
+    assert abs(float(g["kl_sum"]) - 10564.26834299677) < 1e-6
+    assert rel_err(out["kl_pairs"], g["kl_pairs"]) < 1e-6
+    assert rel_err(out["z"], g["z"]) < 1e-6
+    assert rel_err(grads["mean"], g["g_mean"]) < 1e-6
+    assert rel_err(grads["aux"], g["g_logvar"]) < 1e-6
+    # the numpy kernel_matrix(20, 1.0) the reference feeds in is our noise=0 kernel
+    K = orc.kernel_matrix(g["times"][0], torch.tensor(1.0), "rbf", 0.0)
+    assert rel_err(K, g["K"]) < 1e-7
+
+
+def test_numpy_second_opinion():
+    g = load_golden("g3_v1_ragged_s2")
+    lengths = g["lengths"].tolist()
+    D = g["mean"].shape[1]
+    off = 0
+    p = 0
+    for b, T in enumerate(lengths):
+        t = g["times"][b, :T]
+        for d in range(D):
+            Kq = orc.kernel_matrix(t, g["ell_q"][d]).numpy()
+            Kp = orc.kernel_matrix(t, g["ell_p"][d]).numpy()
+            kl = orc.gp_kl_div_numpy(g["mean"][off:off + T, d].numpy(), Kq, Kp)
+            assert abs(kl - float(g["kl_pairs"][p])) < 1e-9 * max(1.0, abs(kl))
+            p += 1
+        off += T
+
+
+@pytest.mark.parametrize("posterior", ["gp", "diag", "bidiag"])
+@pytest.mark.parametrize("kernel", ["rbf", "cauchy"])
+def test_oracle_gradcheck_fd(posterior, kernel):
+    """Finite differences in float64 on the oracle itself (covers Cauchy / V3, unpinned by the reference)."""
+    s = orc.synthetic_batch(2, 2, 5, S=2, ragged=True, seed=3, posterior=posterior)
+    kw = dict(kernel=kernel, posterior=posterior, S=2, build_dtype=torch.float64)
+    out, grads = orc.gp_prior_kl_grads(s["mean"].double(), s["times"].double(), s["lengths"], s["ell_q"].double(),
+                                       s["ell_p"].double(), s["eps"].double(), s["g_z"],
+                                       aux=None if s["aux"] is None else s["aux"].double(), **kw)
+
+    def loss(ell_q, ell_p, mean, aux):
+        o = orc.gp_prior_kl(mean, s["times"].double(), s["lengths"], ell_q, ell_p, s["eps"].double(), aux=aux, **kw)
+        return float(o["kl_sum"] + (s["g_z"].double() * o["z"]).sum())
+    h = 1e-6
+    base = [s["ell_q"].double(), s["ell_p"].double(), s["mean"].double(), None if s["aux"] is None else s["aux"].double()]
+    for idx, key in ((0, "ell_q"), (1, "ell_p"), (2, "mean"), (3, "aux")):
+        if base[idx] is None:
+            continue
+        x = base[idx]
+        flat = x.reshape(-1)
+        for j in range(min(3, flat.numel())):
+            xp = flat.clone(); xp[j] += h
+            xm = flat.clone(); xm[j] -= h
+            args_p = list(base); args_p[idx] = xp.reshape(x.shape)
+            args_m = list(base); args_m[idx] = xm.reshape(x.shape)
+            fd = (loss(*args_p) - loss(*args_m)) / (2 * h)
+            an = float(grads[key].reshape(-1)[j])
+            assert abs(fd - an) < 1e-5 * max(1.0, abs(an)), (key, j, fd, an)
