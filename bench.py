@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- GP-prior KL hot path (forward + backward) throughput on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl ours|reference]
+
+A "step" is one forward+backward pass of the hot path (kernel build, Cholesky, sample, KL, and the
+hand-written adjoints) over one batch of synthetic input of the named BASELINE.json config; at N>1 each
+rank owns its own batch of that size (weak scaling) and the lengthscale gradients are all-reduced over
+NCCL inside the step.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "gp-vae_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+# BASELINE.json configs (per-GPU batch).  c3 is the 8-GPU config: 512 sequences sharded 64 per GPU.
+WORKLOADS = {
+    "c1": dict(T=10, D=256, B=64, kernel="cauchy", desc="HMNIST-shape T=10 D=256 B=64 Cauchy"),
+    "c2": dict(T=48, D=35, B=256, kernel="rbf", desc="Physionet-shape T=48 D=35 B=256 RBF"),
+    "c3": dict(T=8, D=256, B=64, kernel="rbf", desc="Sprites-shape T=8 D=256 B=64/GPU (512 over 8) RBF"),
+    "c4": dict(T=512, D=64, B=1024, kernel="cauchy", desc="long-sequence T=512 D=64 B=1024 Cauchy"),
+}
+for _t in (16, 32, 64, 96, 128, 160, 192, 256, 384, 512, 768, 1024):
+    WORKLOADS["t%d" % _t] = dict(T=_t, D=64, B=max(4, min(1024, (1 << 22) // (_t * _t))), kernel="rbf",
+                                 desc="sweep T=%d D=64" % _t)
+
+
+def model_flops_pair(T, posterior="gp"):
+    """V1 forward T^3 (2 Cholesky + 1 triangular solve, T^3/3 each), backward 2 T^3."""
+    f = float(T) ** 3
+    return (f, 2.0 * f) if posterior == "gp" else (2.0 / 3.0 * f, 4.0 / 3.0 * f)
+
+
+def algo_bytes_pair(T, S=1):
+    """fwd read m, eps, write z (12T) + KL (4); bwd read m, eps, g_z (12T), write g_m (4T): 28T+16 (S=1)."""
+    return 28.0 * T + 16.0
+
+
+def make_case(w, seed, S=1):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gp_kl_oracle as orc  # input generator only (shared with the tests); no oracle compute here
+    return orc.synthetic_batch(w["B"], w["D"], w["T"], S, ragged=False, seed=seed)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.stop_flag = False
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.h = h
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def sample(self):
+        if not self.ok:
+            return
+        try:
+            self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            try:
+                r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                r = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self.stop_flag:
+            self.sample()
+            time.sleep(0.002)
+
+    def result(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_port_throughput(w, budget_s, threads, seed=1234):
+    """Oracle (float64 port of the reference's algorithm) forward+backward on a bounded sample of the
+    workload, on the host cores.  Returns (seq/s, description of the sample)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gp_kl_oracle as orc
+    torch.set_num_threads(threads)
+    T, D = w["T"], w["D"]
+    # size the sample from a quick probe so the whole measurement stays near budget_s
+    Bs = max(1, min(w["B"], 8))
+    case = orc.synthetic_batch(Bs, D, T, 1, seed=seed)
+    t0 = time.perf_counter()
+    orc.gp_prior_kl_grads(case["mean"], case["times"], case["lengths"], case["ell_q"], case["ell_p"], case["eps"],
+                          case["g_z"], kernel=w["kernel"])
+    probe = max(time.perf_counter() - t0, 1e-4)
+    per_seq = probe / Bs
+    Bs = int(max(1, min(w["B"], (budget_s / 4.0) / per_seq)))
+    case = orc.synthetic_batch(Bs, D, T, 1, seed=seed)
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(5):
+        t0 = time.perf_counter()
+        orc.gp_prior_kl_grads(case["mean"], case["times"], case["lengths"], case["ell_q"], case["ell_p"], case["eps"],
+                              case["g_z"], kernel=w["kernel"])
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 2:
+            break
+    times.sort()
+    med = times[len(times) // 2]
+    return Bs / med, "%d of %d sequences (T=%d, D=%d), %d reps, median" % (Bs, w["B"], T, D, len(times)), Bs, med
+
+
+def run_reference(args, w, rank, world):
+    """--impl reference: the reference's CPU algorithm (float64 oracle port: the reference is TF1 Python and
+    cannot travel) on all host threads; each step is a bounded sample of the workload."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gp_kl_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    T, D = w["T"], w["D"]
+    case = orc.synthetic_batch(min(w["B"], 4), D, T, 1, seed=1234)
+    t0 = time.perf_counter()
+    orc.gp_prior_kl_grads(case["mean"], case["times"], case["lengths"], case["ell_q"], case["ell_p"], case["eps"],
+                          case["g_z"], kernel=w["kernel"])
+    per_seq = max(time.perf_counter() - t0, 1e-4) / min(w["B"], 4)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    Bs = int(max(1, min(w["B"], budget / per_seq)))
+    case = orc.synthetic_batch(Bs, D, T, 1, seed=1234)
+
+    def step():
+        orc.gp_prior_kl_grads(case["mean"], case["times"], case["lengths"], case["ell_q"], case["ell_p"], case["eps"],
+                              case["g_z"], kernel=w["kernel"])
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = Bs / dt
+    sample = "%d of %d sequences per step" % (Bs, w["B"])
+    print(json.dumps({
+        "impl": "reference", "metric": "GP-prior KL fwd+bwd sequences/s", "value": val, "unit": "sequences/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + w["desc"], "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--tier", default="auto")
+    ap.add_argument("--grad-ell-p", action="store_true", help="also produce d/d ell_p (fixed-T model)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+
+    import torch.distributed as dist
+    import gpkl
+    from gpkl.parallel import GradBucket
+    import ctypes
+    L = gpkl._lib.lib()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+
+    T, D, B = w["T"], w["D"], w["B"]
+    case = make_case(w, 1234 + rank)
+    host = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
+    c = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
+    cfg = dict(kernel=w["kernel"], posterior="gp", noise=1e-3, S=1, tier=args.tier)
+    bucket = GradBucket(D, dev)
+    one = torch.ones((), dtype=torch.float64, device=dev)
+    g_mean = torch.empty_like(c["mean"])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 256 MiB > 126 MB L2
+
+    def step():
+        f = gpkl.gp_prior_kl_forward(c["mean"], c["times"], c["lengths"], c["ell_q"], c["ell_p"], c["eps"], **cfg)
+        out = bucket.out_views()
+        out["g_mean"] = g_mean
+        gpkl.gp_prior_kl_backward(c["mean"], c["times"], c["lengths"], c["ell_q"], c["ell_p"], c["eps"], c["g_z"],
+                                  one, None, grad_ell_p=args.grad_ell_p, out=out, **cfg)
+        bucket.kl.copy_(f["kl_sum"].to(torch.float32).reshape(1))
+        bucket.all_reduce()
+        return f
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- FP32 CUDA-core peak (FFMA microbenchmark, timed alone) --------------------------------------
+    sink = torch.empty(148 * 8 * 256, dtype=torch.float32, device=dev)
+    flops = ctypes.c_double(0.0)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    best_peak = 0.0
+    for i in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.gpkl_fp32_peak_launch(ctypes.c_void_p(sink.data_ptr()), 20000, ctypes.byref(flops), st)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best_peak = max(best_peak, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+
+    # ---- device-resident timed region ----------------------------------------------------------------
+    for _ in range(warmup):
+        step()
+        flush.zero_()
+    L.gpkl_profile_enable(1)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = L.gpkl_launch_count()
+    sampler.sample()
+    sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+        flush.zero_()   # evict the step's inputs from L2 between timed iterations (outside the events)
+    barrier()
+    sampler.stop_flag = True
+    sampler.sample()
+    launches = (L.gpkl_launch_count() - launches0) + (args.steps if world > 1 else 0) + args.steps
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    fwd_ms, bwd_ms = ctypes.c_double(0), ctypes.c_double(0)
+    nf, nb = ctypes.c_int32(0), ctypes.c_int32(0)
+    L.gpkl_profile_read(ctypes.byref(fwd_ms), ctypes.byref(nf), ctypes.byref(bwd_ms), ctypes.byref(nb))
+    L.gpkl_profile_enable(0)
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tmax) / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # ---- end-to-end: host (pinned) buffers in, results out, copies inside the timed region ------------
+    total_T = case["mean"].shape[0]
+    if world == 1:
+        hs = gpkl.HostStep(B, D, T, 1, total_T, kernel=w["kernel"], grad_ell_p=args.grad_ell_p, tier=args.tier,
+                           device=dev)
+
+        def e2e_step():
+            hs(host["mean"], host["times"], host["lengths"], host["ell_q"], host["ell_p"], host["eps"], host["g_z"],
+               full_outputs=False)
+            return hs.h2d_bytes, hs.d2h_bytes
+    else:
+        res_host = torch.empty(2 * D + 1, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            cc = {k: host[k].to(dev, non_blocking=True) for k in ("mean", "times", "lengths", "ell_q", "ell_p", "eps", "g_z")}
+            f = gpkl.gp_prior_kl_forward(cc["mean"], cc["times"], cc["lengths"], cc["ell_q"], cc["ell_p"], cc["eps"], **cfg)
+            out = bucket.out_views()
+            out["g_mean"] = g_mean
+            gpkl.gp_prior_kl_backward(cc["mean"], cc["times"], cc["lengths"], cc["ell_q"], cc["ell_p"], cc["eps"],
+                                      cc["g_z"], one, None, grad_ell_p=args.grad_ell_p, out=out, **cfg)
+            bucket.kl.copy_(f["kl_sum"].to(torch.float32).reshape(1))
+            bucket.all_reduce()
+            res_host.copy_(bucket.flat, non_blocking=True)
+            h2d = sum(host[k].numel() * host[k].element_size() for k in ("mean", "times", "lengths", "ell_q", "ell_p", "eps", "g_z"))
+            return h2d, res_host.numel() * 4
+    for _ in range(3):
+        h2d_b, d2h_b = e2e_step()
+        torch.cuda.synchronize()
+    barrier()
+    e2e_ms = 0.0
+    n_e2e = max(10, min(args.steps, 200))
+    for _ in range(n_e2e):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        h2d_b, d2h_b = e2e_step()
+        e1.record()
+        e1.synchronize()   # the caller reads the step's result (KL, lengthscale grads) every step
+        e2e_ms += e0.elapsed_time(e1)
+    barrier()
+    t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_val = B * world / (float(t2) / n_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (backward) -------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"
+    f_fwd, f_bwd = model_flops_pair(T)
+    npairs = B * D
+    bwd_avg_ms = bwd_ms.value / max(nb.value, 1)
+    fwd_avg_ms = fwd_ms.value / max(nf.value, 1)
+    ach_bwd = npairs * f_bwd / (bwd_avg_ms * 1e-3) / 1e12
+    ach_fwd = npairs * f_fwd / (fwd_avg_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get(args.workload, {}).get("bwd_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "fp32", "kernel": "backward (Cholesky/trisolve adjoints)", "achieved": ach_bwd, "peak": best_peak,
+        "unit": "TFLOP/s", "frac": ach_bwd / best_peak if best_peak > 0 else None, "traffic": traffic,
+        "peak_source": "FFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry; "
+                       "nominal 148x128x2x1.965GHz = 74.4)",
+        "algorithmic": "%d pairs x 2*T^3 flops" % npairs, "launch_ms": bwd_avg_ms,
+        "hbm_frac": npairs * algo_bytes_pair(T) / ((fwd_avg_ms + bwd_avg_ms) * 1e-3) / 1e9 / hbm_peak,
+        "hbm_peak_source": hbm_src,
+        "forward": {"achieved": ach_fwd, "frac": ach_fwd / best_peak if best_peak > 0 else None,
+                    "launch_ms": fwd_avg_ms, "algorithmic": "%d pairs x T^3 flops" % npairs},
+        "kernel_share_of_step": (fwd_avg_ms + bwd_avg_ms) / (total_ms / args.steps),
+    }
+
+    out = {
+        "metric": "GP-prior KL fwd+bwd sequences/s", "value": value, "unit": "sequences/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + w["desc"], "per_gpu_batch": B, "global_batch": B * world,
+                   "parallelism": "dp%d (sequences sharded, all-reduce of lengthscale grads)" % world,
+                   "l2": "256 MiB flush between timed iterations", "tier": args.tier,
+                   "grad_ell_p": bool(args.grad_ell_p)},
+        "clocks": sampler.result(),
+        "e2e": {"value": e2e_val, "unit": "sequences/s", "h2d_bytes_per_step": int(h2d_b),
+                "d2h_bytes_per_step": int(d2h_b), "ms_per_step": float(t2) / n_e2e},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, sample, _, _ = cpu_port_throughput(w, args.cpu_budget, os.cpu_count() or 1)
+        out["cpu_baseline"] = {"value": val, "unit": "sequences/s", "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": sample}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,25 @@
+// Host-side launch interface between the C ABI (gpkl_api.cu) and the kernel tiers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "gpkl_common.cuh"
+
+namespace gpkl {
+
+constexpr size_t kMaxDynSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100a
+constexpr int kNumSMs = 148;
+
+// measurement hooks (gpkl_api.cu): every kernel launch goes through note_launch(); the dominant kernel of
+// forward/backward is bracketed by prof_begin/prof_end (no-ops unless gpkl_profile_enable(1)).
+void note_launch(int n = 1);
+void prof_begin(bool backward, cudaStream_t st);
+void prof_end(bool backward, cudaStream_t st);
+
+// generic tier (gpkl_generic.cu)
+size_t generic_smem_bytes(int T, int S, bool mats_in_smem);
+size_t generic_slot_floats(int T);
+int generic_slots(const GpklDesc& d);  // 0 when the matrices fit shared memory
+cudaError_t launch_generic(const Params& P, bool backward, cudaStream_t st);
+
+}  // namespace gpkl

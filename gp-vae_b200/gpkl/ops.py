@@ -1,0 +1,213 @@
+"""PyTorch-facing operator for the GP-prior KL path.
+
+One fused op replaces the reference's four calls -- prior_kernels, approx_kernels, gp_vae_sample,
+calc_gp_kl (src/Models/Full_GP_VAE_dynamic_time.py:332-340; V2: vae_sample/calc_gp_kl,
+src/Models/VAE_GPprior_diag_cov.py:203-204) -- because they share the Cholesky factor of K_q, and a
+hand-written backward replaces TF autodiff through them (:361).  PyTorch is plumbing here (device
+memory, streams, autograd bookkeeping); all arithmetic happens in libgpkl.so.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GpklDesc, KERNELS, POSTERIORS, TIERS, FLAG_GRAD_ELL_P
+
+_WS = {}
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _make_desc(B, D, T_max, S, total_T, kernel, posterior, noise, flags=0, tier="auto"):
+    return GpklDesc(int(B), int(D), int(T_max), int(S), int(total_T), KERNELS[kernel], POSTERIORS[posterior],
+                    float(noise), int(flags), TIERS[tier], 0)
+
+
+def workspace_bytes(desc):
+    n = _lib.lib().gpkl_workspace_bytes(ctypes.byref(desc))
+    if n == 0:
+        _lib.check(_lib.lib().gpkl_forward(ctypes.byref(desc), *([None] * 12), None, 0, None))  # raises the descriptor error
+    return n
+
+
+def _workspace(desc, device):
+    n = workspace_bytes(desc)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws, n
+
+
+def _check_inputs(mean, times, lengths, ell_q, ell_p, eps, aux, posterior, S):
+    if not mean.is_cuda:
+        raise RuntimeError("gpkl: tensors must live on a CUDA device (there is no CPU implementation)")
+    B, T_max = times.shape
+    total_T, D = mean.shape
+    assert lengths.shape == (B,) and lengths.dtype == torch.int32, "lengths must be int32 [B]"
+    assert eps.shape == (B, D, S, T_max), "eps must be [B, D, S, T_max]"
+    assert ell_p.shape == (D,)
+    if posterior == "gp":
+        assert ell_q is not None and ell_q.shape == (D,)
+    else:
+        assert aux is not None and aux.shape[:2] == (total_T, D)
+    for t in (mean, times, ell_q, ell_p, eps, aux):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous()), "float32 contiguous tensors required"
+    return B, D, T_max, total_T
+
+
+def gp_prior_kl_forward(mean, times, lengths, ell_q, ell_p, eps, *, aux=None, kernel="rbf", posterior="gp",
+                        noise=1e-3, S=1, tier="auto", want_logdets=False, want_status=False):
+    """Raw forward through the C ABI (gpkl_forward).  Returns dict(z, kl_sum, kl_pairs[, logdets, status])."""
+    B, D, T_max, total_T = _check_inputs(mean, times, lengths, ell_q, ell_p, eps, aux, posterior, S)
+    dev = mean.device
+    desc = _make_desc(B, D, T_max, S, total_T, kernel, posterior, noise, 0, tier)
+    ws, n = _workspace(desc, dev)
+    z = torch.empty(S * total_T, D, dtype=torch.float32, device=dev)
+    kl_pairs = torch.empty(B * D, dtype=torch.float32, device=dev)
+    kl_sum = torch.empty((), dtype=torch.float64, device=dev)
+    logdets = torch.empty(B * D, 2, dtype=torch.float32, device=dev) if want_logdets else None
+    status = torch.zeros((), dtype=torch.int32, device=dev) if want_status else None
+    rc = _lib.lib().gpkl_forward(ctypes.byref(desc), _ptr(mean), _ptr(times), _ptr(lengths), _ptr(ell_q), _ptr(ell_p),
+                                 _ptr(aux), _ptr(eps), _ptr(z), _ptr(kl_pairs), _ptr(kl_sum), _ptr(logdets),
+                                 _ptr(status), _ptr(ws), n, _stream(dev))
+    _lib.check(rc)
+    out = {"z": z, "kl_sum": kl_sum, "kl_pairs": kl_pairs}
+    if want_logdets:
+        out["logdets"] = logdets
+    if want_status:
+        out["status"] = status
+    return out
+
+
+def gp_prior_kl_backward(mean, times, lengths, ell_q, ell_p, eps, g_z, g_kl_sum=None, g_kl_pairs=None, *, aux=None,
+                         kernel="rbf", posterior="gp", noise=1e-3, S=1, tier="auto", grad_ell_p=False,
+                         out=None):
+    """Raw backward through the C ABI (gpkl_backward).  g_kl_sum: 0-d float64 CUDA tensor or None (== 1).
+    `out` may carry preallocated g_mean / g_ell_q / g_ell_p / g_aux (e.g. views into a gradient bucket)."""
+    B, D, T_max, total_T = _check_inputs(mean, times, lengths, ell_q, ell_p, eps, aux, posterior, S)
+    dev = mean.device
+    desc = _make_desc(B, D, T_max, S, total_T, kernel, posterior, noise, FLAG_GRAD_ELL_P if grad_ell_p else 0, tier)
+    ws, n = _workspace(desc, dev)
+    out = dict(out or {})
+    g_mean = out.get("g_mean")
+    if g_mean is None:
+        g_mean = torch.empty_like(mean)
+    g_ell_q = out.get("g_ell_q")
+    if g_ell_q is None:
+        g_ell_q = torch.empty(D, dtype=torch.float32, device=dev)
+    g_ell_p = out.get("g_ell_p")
+    if g_ell_p is None and grad_ell_p:
+        g_ell_p = torch.empty(D, dtype=torch.float32, device=dev)
+    g_aux = out.get("g_aux")
+    if g_aux is None and aux is not None:
+        g_aux = torch.empty_like(aux)
+    if g_z is not None:
+        assert g_z.shape == (S * total_T, D) and g_z.dtype == torch.float32 and g_z.is_contiguous()
+    if g_kl_sum is not None:
+        assert g_kl_sum.dtype == torch.float64 and g_kl_sum.numel() == 1 and g_kl_sum.is_cuda
+    if g_kl_pairs is not None:
+        assert g_kl_pairs.shape == (B * D,) and g_kl_pairs.dtype == torch.float32 and g_kl_pairs.is_contiguous()
+    rc = _lib.lib().gpkl_backward(ctypes.byref(desc), _ptr(mean), _ptr(times), _ptr(lengths), _ptr(ell_q),
+                                  _ptr(ell_p), _ptr(aux), _ptr(eps), _ptr(g_z), _ptr(g_kl_sum), _ptr(g_kl_pairs),
+                                  _ptr(g_mean), _ptr(g_ell_q), _ptr(g_ell_p), _ptr(g_aux), None, _ptr(ws), n,
+                                  _stream(dev))
+    _lib.check(rc)
+    return {"g_mean": g_mean, "g_ell_q": g_ell_q if posterior == "gp" else None, "g_ell_p": g_ell_p, "g_aux": g_aux}
+
+
+class GpPriorKL(torch.autograd.Function):
+    """(mean, times, lengths, ell_q, ell_p, eps, aux) -> (z, kl_sum, kl_pairs), differentiable in
+    mean, ell_q, ell_p and aux.  Factors are recomputed on chip in backward (nothing T x T is saved)."""
+
+    @staticmethod
+    def forward(ctx, mean, times, lengths, ell_q, ell_p, eps, aux, kernel, posterior, noise, S, tier):
+        o = gp_prior_kl_forward(mean, times, lengths, ell_q, ell_p, eps, aux=aux, kernel=kernel, posterior=posterior,
+                                noise=noise, S=S, tier=tier)
+        ctx.save_for_backward(mean, times, lengths, ell_q, ell_p, eps, aux)
+        ctx.cfg = (kernel, posterior, noise, S, tier)
+        ctx.mark_non_differentiable()
+        return o["z"], o["kl_sum"], o["kl_pairs"]
+
+    @staticmethod
+    def backward(ctx, g_z, g_kl_sum, g_kl_pairs):
+        mean, times, lengths, ell_q, ell_p, eps, aux = ctx.saved_tensors
+        kernel, posterior, noise, S, tier = ctx.cfg
+        grad_ell_p = ctx.needs_input_grad[4]
+        if g_kl_sum is None:
+            g_kl_sum = torch.zeros((), dtype=torch.float64, device=mean.device)
+        g = gp_prior_kl_backward(mean, times, lengths, ell_q, ell_p, eps,
+                                 None if g_z is None else g_z.contiguous(), g_kl_sum.to(torch.float64).reshape(()),
+                                 None if g_kl_pairs is None else g_kl_pairs.contiguous(), aux=aux, kernel=kernel,
+                                 posterior=posterior, noise=noise, S=S, tier=tier, grad_ell_p=grad_ell_p)
+        return (g["g_mean"], None, None, g["g_ell_q"] if ctx.needs_input_grad[3] else None,
+                g["g_ell_p"] if grad_ell_p else None, None, g["g_aux"] if aux is not None else None,
+                None, None, None, None, None)
+
+
+def gp_prior_kl(mean, times, lengths, ell_q, ell_p, eps=None, *, aux=None, kernel="rbf", posterior="gp", noise=1e-3,
+                S=1, tier="auto", generator=None):
+    """Fused GP-prior path.  Returns (z [S*sum_T, D] f32, kl_sum f64 scalar, kl_pairs [B*D] f32).
+
+    eps=None draws the N(0,1) noise on the device (the reference's tf.random_normal inside tf_kernel,
+    Full_GP_VAE_dynamic_time.py:166); pass eps [B, D, S, T_max] explicitly for reproducible parity runs."""
+    if eps is None:
+        B, T_max = times.shape
+        eps = torch.randn(B, mean.shape[1], S, T_max, device=mean.device, dtype=torch.float32, generator=generator)
+    if posterior != "gp" and ell_q is None:
+        ell_q = ell_p
+    return GpPriorKL.apply(mean, times, lengths, ell_q, ell_p, eps, aux, kernel, posterior, float(noise), int(S), tier)
+
+
+class HostStep:
+    """Forward+backward with HOST (pinned) buffers through gpkl_step_host: the end-to-end call a caller
+    holding CPU tensors makes.  Owns the device staging area and pinned result buffers."""
+
+    def __init__(self, B, D, T_max, S, total_T, *, kernel="rbf", posterior="gp", noise=1e-3, grad_ell_p=False,
+                 tier="auto", device="cuda:0"):
+        self.device = torch.device(device)
+        self.desc = _make_desc(B, D, T_max, S, total_T, kernel, posterior, noise,
+                               FLAG_GRAD_ELL_P if grad_ell_p else 0, tier)
+        n = _lib.lib().gpkl_step_host_bytes(ctypes.byref(self.desc))
+        if n == 0:
+            raise RuntimeError("gpkl: bad descriptor")
+        self.nbytes = n
+        self.staging = torch.empty(n, dtype=torch.uint8, device=self.device)
+        pin = dict(pin_memory=True)
+        self.z = torch.empty(S * total_T, D, dtype=torch.float32, **pin)
+        self.kl_pairs = torch.empty(B * D, dtype=torch.float32, **pin)
+        self.kl_sum = torch.empty((), dtype=torch.float64, **pin)
+        self.g_mean = torch.empty(total_T, D, dtype=torch.float32, **pin)
+        self.g_ell_q = torch.empty(D, dtype=torch.float32, **pin)
+        self.g_ell_p = torch.empty(D, dtype=torch.float32, **pin) if grad_ell_p else None
+        self.g_aux = torch.empty(total_T, D, dtype=torch.float32, **pin) if posterior == "diag" else None
+        self.posterior = posterior
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def __call__(self, mean, times, lengths, ell_q, ell_p, eps, g_z=None, aux=None, *, full_outputs=True):
+        """All arguments are CPU tensors (pinned for async copies).  Results land in self.* (pinned) once the
+        current stream is synchronised.  full_outputs=False reads back only kl_sum and the lengthscale grads."""
+        for t in (mean, times, lengths, ell_q, ell_p, eps, g_z, aux):
+            assert t is None or (not t.is_cuda and t.is_contiguous())
+        z = self.z if full_outputs else None
+        klp = self.kl_pairs if full_outputs else None
+        gm = self.g_mean if full_outputs else None
+        ga = self.g_aux if full_outputs else None
+        rc = _lib.lib().gpkl_step_host(ctypes.byref(self.desc), _ptr(mean), _ptr(times), _ptr(lengths), _ptr(ell_q),
+                                       _ptr(ell_p), _ptr(aux), _ptr(eps), _ptr(g_z), _ptr(z), _ptr(klp),
+                                       _ptr(self.kl_sum), _ptr(gm), _ptr(self.g_ell_q), _ptr(self.g_ell_p), _ptr(ga),
+                                       _ptr(self.staging), self.nbytes, _stream(self.device))
+        _lib.check(rc)
+        ins = [mean, times, lengths, ell_q, ell_p, eps, g_z, aux]
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in ins if t is not None)
+        outs = [z, klp, self.kl_sum, gm, self.g_ell_q if self.posterior == "gp" else None, self.g_ell_p, ga]
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in outs if t is not None)
+        return self

@@ -1,0 +1,76 @@
+"""The reference's four call sites, by name, over the fused op.
+
+In the reference main() (src/Models/Full_GP_VAE_dynamic_time.py:332-340)
+
+    prior_kernel, prior_time_chars         = prior_kernels(sequences, sizes, latent_size, batch_size)
+    approx_kernel, chol_noise, approx_chars = approx_kernels(sequences, sizes, latent_size, batch_size, S)
+    latent_sample                           = gp_vae_sample(latent_mean, chol_noise, sizes, batch_size, S, latent_size)
+    sum_gp_kl, gp_kl                        = calc_gp_kl(latent_mean, sizes, approx_kernel, prior_kernel, batch_size, latent_size)
+
+materialise [B*D, T_max^2] kernel tensors in memory.  Here the two *_kernels calls only record WHAT
+to build (times, lengths, lengthscales) in light handles -- no T x T matrix is ever formed in HBM --
+and the first of gp_vae_sample / calc_gp_kl that runs launches the fused CUDA op once; the other
+returns the cached half.  Same argument order and meaning as the reference functions.
+"""
+import torch
+
+from .ops import gp_prior_kl
+
+
+class KernelHandle:
+    """What prior_kernels / approx_kernels return in place of the [B*D, T_max^2] tensor."""
+
+    def __init__(self, path, role, time_chars):
+        self.path, self.role, self.time_chars = path, role, time_chars
+
+
+class GPPriorPath:
+    def __init__(self, latent_size, *, kernel="rbf", noise=1e-3, prior_lengthscale=1.0, approx_lengthscale=1.0,
+                 train_prior=False, device="cuda:0", tier="auto"):
+        dev = torch.device(device)
+        # tf.Variable(tf.constant(1.0, shape=[latent_size,1]), name='approx_time_chars')   (:72)
+        self.approx_time_chars = torch.nn.Parameter(torch.full((latent_size,), float(approx_lengthscale), device=dev))
+        # tf.constant(1.0, ...) (:114) -- a tf.Variable in Full_GP_VAE_fixed_for_MovMnist.py:96
+        p = torch.full((latent_size,), float(prior_lengthscale), device=dev)
+        self.prior_time_chars = torch.nn.Parameter(p) if train_prior else p
+        self.latent_size, self.kernel, self.noise, self.tier = latent_size, kernel, noise, tier
+        self._seq = None
+        self._cache = None
+
+    def parameters(self):
+        ps = [self.approx_time_chars]
+        if isinstance(self.prior_time_chars, torch.nn.Parameter):
+            ps.append(self.prior_time_chars)
+        return ps
+
+    def _note(self, sequences, sequence_sizes, latent_size, batch_size):
+        assert latent_size == self.latent_size and sequences.shape[0] == batch_size
+        self._seq = (sequences.contiguous().float(), sequence_sizes.to(torch.int32).contiguous())
+        self._cache = None
+
+    def prior_kernels(self, sequences, sequence_sizes, latent_size, batch_size):
+        self._note(sequences, sequence_sizes, latent_size, batch_size)
+        return KernelHandle(self, "prior", self.prior_time_chars), self.prior_time_chars
+
+    def approx_kernels(self, sequences, sequence_sizes, latent_size, batch_size, number_samples, eps=None):
+        self._note(sequences, sequence_sizes, latent_size, batch_size)
+        self.number_samples, self._eps = number_samples, eps
+        h = KernelHandle(self, "approx", self.approx_time_chars)
+        return h, h, self.approx_time_chars  # (approx_kernel, chol_noise, time_chars)
+
+    def _run(self, mean):
+        if self._cache is None or self._cache[0] is not mean:
+            times, lengths = self._seq
+            out = gp_prior_kl(mean.contiguous(), times, lengths, self.approx_time_chars, self.prior_time_chars,
+                              self._eps, kernel=self.kernel, noise=self.noise, S=self.number_samples, tier=self.tier)
+            self._cache = (mean, out)
+        return self._cache[1]
+
+    def gp_vae_sample(self, mean, noise_chol_full_time, sequence_sizes, batch_size, number_samples, latent_size):
+        assert isinstance(noise_chol_full_time, KernelHandle) and number_samples == self.number_samples
+        return self._run(mean)[0]
+
+    def calc_gp_kl(self, mean, sequence_sizes, approx_linear_kernel, prior_kernel, batch_size, latent_size):
+        assert isinstance(approx_linear_kernel, KernelHandle) and isinstance(prior_kernel, KernelHandle)
+        _, kl_sum, kl_pairs = self._run(mean)
+        return kl_sum, kl_pairs

@@ -1,0 +1,131 @@
+/* gpkl.h -- C ABI of the B200-native GP-prior KL path for GP-VAE (libgpkl.so).
+ *
+ * Drop-in boundary for ONE path of ethanev/GP-VAE: the GP-prior term of the ELBO.  The reference has
+ * no plugin/FFI layer; the boundary is the four Python call sites in its main()
+ *   prior_kernels(...)    src/Models/Full_GP_VAE_dynamic_time.py:332  (def :100-130)
+ *   approx_kernels(...)   src/Models/Full_GP_VAE_dynamic_time.py:335  (def :60-98)
+ *   gp_vae_sample(...)    src/Models/Full_GP_VAE_dynamic_time.py:339  (def :174-195)
+ *   calc_gp_kl(...)       src/Models/Full_GP_VAE_dynamic_time.py:340  (def :197-260)
+ * (V2, diagonal posterior: vae_sample / calc_gp_kl, src/Models/VAE_GPprior_diag_cov.py:203-204,
+ *  defs :64-71, :73-119) and TensorFlow's autodiff through them (:361).  Because all four share the
+ * Cholesky factor of K_q they are ONE fused forward entry point here, plus one backward entry point.
+ *
+ * Conventions
+ *   - plain C: POD descriptor, raw pointers, sizes; no C++/torch types, no exceptions.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all buffers,
+ *     including the workspace; the library allocates nothing and keeps no global state.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation, no
+ *     allocation => CUDA-graph capturable and re-entrant.
+ *   - outputs are fully overwritten (no caller zero-fill needed); reductions are deterministic.
+ *   - layouts are the reference's:
+ *       mean   [total_T, D] f32   rows sequence-major then time (encoder output, :329)
+ *       times  [B, T_max]   f32   zero padded on the right (DataHandler.py:151)
+ *       lengths[B]          i32   T_b, 0 <= T_b <= T_max            (:322)
+ *       ell_q, ell_p [D]    f32   posterior / prior lengthscales    (:72, :114)
+ *       eps    [B, D, S, T_max] f32  N(0,1) draws (tf.random_normal at :166, made explicit)
+ *       aux    posterior DIAG: logvar [total_T, D]; BIDIAG: [total_T, D, 2]; GP: unused (NULL)
+ *       z      [S*total_T, D] f32  per sequence S blocks of [T_b, D]  (:186-194)
+ *       kl_pairs [B*D] f32  pair index p = b*D + d (:216-217, :239);  kl_sum f64 scalar (:228)
+ *   - return value: 0 on success, a GPKL_ERR_* code otherwise (see gpkl_strerror).  A non-positive-
+ *     definite pivot yields NaN in that pair's outputs and increments *status (if non-NULL) on the
+ *     device -- the analogue of TF's "Cholesky decomposition was not successful".
+ */
+#ifndef GPKL_H_
+#define GPKL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPKL_VERSION 1
+
+enum { GPKL_KERNEL_RBF = 0, GPKL_KERNEL_CAUCHY = 1 };
+enum { GPKL_POST_GP = 0, GPKL_POST_DIAG = 1, GPKL_POST_BIDIAG = 2 };
+enum { GPKL_TIER_AUTO = 0, GPKL_TIER_GENERIC = 1, GPKL_TIER_WARP = 2, GPKL_TIER_BLOCK = 3 };
+enum { GPKL_FLAG_GRAD_ELL_P = 1 };   /* backward also produces d/d ell_p (Full_GP_VAE_fixed_for_MovMnist.py:96) */
+
+enum {
+  GPKL_OK = 0,
+  GPKL_ERR_NULL = 1,         /* a required pointer is NULL */
+  GPKL_ERR_DESC = 2,         /* inconsistent descriptor (negative sizes, unknown enum) */
+  GPKL_ERR_UNSUPPORTED = 3,  /* combination not implemented (e.g. tier cannot hold this T) */
+  GPKL_ERR_WORKSPACE = 4,    /* ws_bytes < gpkl_workspace_bytes(desc) */
+  GPKL_ERR_CUDA = 5          /* a CUDA runtime call failed (launch error) */
+};
+
+typedef struct GpklDesc {
+  int32_t B;         /* sequences in the batch (batch_size, :312) */
+  int32_t D;         /* latent dimensions (latent_size, :317) */
+  int32_t T_max;     /* row stride of times and innermost stride of eps */
+  int32_t S;         /* samples per pair (number_samples, :318) */
+  int64_t total_T;   /* sum of lengths = rows of mean */
+  int32_t kernel;    /* GPKL_KERNEL_* ; RBF == tf_kernel :162 */
+  int32_t posterior; /* GPKL_POST_*   */
+  float noise;       /* jitter, 1e-3 in tf_kernel :154 ; 0 reproduces the numpy kernel_matrix of V2 */
+  int32_t flags;     /* GPKL_FLAG_* */
+  int32_t tier;      /* GPKL_TIER_* ; AUTO picks by T_max */
+  int32_t reserved;
+} GpklDesc;
+
+int gpkl_version(void);
+const char* gpkl_strerror(int code);
+
+/* Bytes of device workspace forward/backward need for this descriptor (max of both). */
+size_t gpkl_workspace_bytes(const GpklDesc* desc);
+
+/* Fused forward: kernel build + Cholesky + sample + KL.
+ * Replaces prior_kernels + approx_kernels + gp_vae_sample + calc_gp_kl (see header comment).
+ * logdets [B*D, 2] = (log|K_p|, log|K_q|) per pair, may be NULL.  status may be NULL. */
+int gpkl_forward(const GpklDesc* desc, const float* mean, const float* times, const int32_t* lengths,
+                 const float* ell_q, const float* ell_p, const float* aux, const float* eps,
+                 float* z, float* kl_pairs, double* kl_sum, float* logdets, int32_t* status,
+                 void* workspace, size_t ws_bytes, void* stream);
+
+/* Backward of  Loss = g_kl_sum*kl_sum + <g_kl_pairs, kl_pairs> + <g_z, z>  (replaces TF autodiff, :361).
+ * g_z [S*total_T, D] may be NULL (== 0); g_kl_sum is a DEVICE f64 scalar, NULL == 1.0;
+ * g_kl_pairs [B*D] may be NULL (== 0).  Outputs: g_mean [total_T, D]; g_ell_q [D] (GP posterior only,
+ * may be NULL otherwise); g_ell_p [D] only written when GPKL_FLAG_GRAD_ELL_P (else may be NULL);
+ * g_aux like aux (DIAG/BIDIAG only).  The factors are recomputed on chip: nothing T x T is read
+ * from or written to HBM between forward and backward. */
+int gpkl_backward(const GpklDesc* desc, const float* mean, const float* times, const int32_t* lengths,
+                  const float* ell_q, const float* ell_p, const float* aux, const float* eps,
+                  const float* g_z, const double* g_kl_sum, const float* g_kl_pairs,
+                  float* g_mean, float* g_ell_q, float* g_ell_p, float* g_aux, int32_t* status,
+                  void* workspace, size_t ws_bytes, void* stream);
+
+/* Device staging area a host-buffer step needs (inputs + outputs + workspace), in bytes. */
+size_t gpkl_step_host_bytes(const GpklDesc* desc);
+
+/* One forward+backward step with HOST buffers (pinned memory recommended): copies the inputs to the
+ * device staging area, runs gpkl_forward + gpkl_backward with g_kl_sum = 1, copies z, kl_pairs, kl_sum,
+ * g_mean, g_ell_q, g_ell_p back, all on `stream` (asynchronous; synchronise the stream before reading).
+ * g_z_host / aux_host / g_aux_host / g_ell_p_host may be NULL as for the device entry points. */
+int gpkl_step_host(const GpklDesc* desc, const float* mean_host, const float* times_host,
+                   const int32_t* lengths_host, const float* ell_q_host, const float* ell_p_host,
+                   const float* aux_host, const float* eps_host, const float* g_z_host,
+                   float* z_host, float* kl_pairs_host, double* kl_sum_host, float* g_mean_host,
+                   float* g_ell_q_host, float* g_ell_p_host, float* g_aux_host,
+                   void* staging, size_t staging_bytes, void* stream);
+
+/* ---- measurement hooks (bench.py; not part of the data path) ------------------------------------
+ * These are the only process-global state in the library and are not thread safe.
+ * gpkl_launch_count: kernels this library has launched since load (bench.py's gpu_launches).
+ * gpkl_profile_enable(1): forward/backward additionally record CUDA events on `stream` immediately
+ *   around their dominant kernel launch (ring of 1024 pairs each); gpkl_profile_read synchronises
+ *   those events and returns summed milliseconds and launch counts since the last read. */
+int64_t gpkl_launch_count(void);
+int gpkl_profile_enable(int on);
+int gpkl_profile_read(double* fwd_ms, int32_t* fwd_launches, double* bwd_ms, int32_t* bwd_launches);
+
+/* FP32 CUDA-core peak microbenchmark: launches one kernel of independent FFMA chains on `stream`
+ * (148*8 CTAs x 256 threads x iters x 16 FMAs) and stores the flop count of that launch in *flops.
+ * The caller times it with CUDA events; sink (device, >= 148*8*256 floats) keeps the work alive. */
+int gpkl_fp32_peak_launch(float* sink, int32_t iters, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPKL_H_ */

@@ -1,0 +1,189 @@
+"""GPU parity: the CUDA path, called through the C ABI (libgpkl.so), against (a) the golden fixtures
+produced by the reference's own functions and (b) the float64 oracle on seeded inputs.
+Tolerances are BASELINE.json's: log-det / KL 1e-5 relative, gradients 1e-4 (scale-relative, max norm)."""
+import pytest
+import torch
+
+import gp_kl_oracle as orc
+from conftest import load_golden, rel_err
+from gpu_util import TOL_GRAD, TOL_KL, TOL_Z, assert_parity, compare, run_cuda
+
+pytestmark = pytest.mark.gpu
+
+TIERS = ["generic", "auto"]
+
+
+@pytest.mark.parametrize("tier", TIERS)
+@pytest.mark.parametrize("name", ["g1_v1_regular", "g3_v1_ragged_s2", "g5_v1_toy_shape", "g4_v1_fixed_prior_grad"])
+def test_golden_v1(cuda_device, name, tier):
+    """Fixtures = outputs of Full_GP_VAE_dynamic_time / Full_GP_VAE_fixed_for_MovMnist run verbatim."""
+    g = load_golden(name)
+    fwd, bwd = run_cuda(g, cuda_device, S=g["S"], noise=g["noise"], tier=tier, grad_ell_p=True)
+    assert int(fwd["status"]) == 0
+    assert rel_err(fwd["kl_pairs"], g["kl_pairs"]) < TOL_KL
+    assert abs(float(fwd["kl_sum"]) - float(g["kl_sum"])) < TOL_KL * abs(float(g["kl_sum"]))
+    assert rel_err(fwd["z"], g["z"]) < TOL_Z
+    assert rel_err(bwd["g_mean"], g["g_mean"]) < TOL_GRAD
+    assert rel_err(bwd["g_ell_q"], g["g_ell_q"]) < TOL_GRAD
+    if "g_ell_p" in g:
+        assert rel_err(bwd["g_ell_p"], g["g_ell_p"]) < TOL_GRAD
+
+
+@pytest.mark.parametrize("tier", TIERS)
+def test_golden_v2(cuda_device, tier):
+    """Fixture = VAE_GPprior_diag_cov.calc_gp_kl / vae_sample run verbatim (numpy kernel == noise 0)."""
+    g = load_golden("g2_v2_diag")
+    fwd, bwd = run_cuda(g, cuda_device, posterior="diag", noise=0.0, tier=tier, grad_ell_p=False)
+    assert rel_err(fwd["kl_pairs"], g["kl_pairs"]) < TOL_KL
+    assert abs(float(fwd["kl_sum"]) - float(g["kl_sum"])) < TOL_KL * abs(float(g["kl_sum"]))
+    assert rel_err(fwd["z"], g["z"]) < TOL_Z
+    # fixture gradients are of kl_sum alone (no g_z): rerun backward without g_z
+    g2 = dict(g)
+    g2.pop("g_z", None)
+    _, bwd = run_cuda(g2, cuda_device, posterior="diag", noise=0.0, tier=tier, grad_ell_p=False)
+    assert rel_err(bwd["g_mean"], g["g_mean"]) < TOL_GRAD
+    assert rel_err(bwd["g_aux"], g["g_logvar"]) < TOL_GRAD
+
+
+GRID = [
+    # (B, D, T, S, ragged)
+    (3, 4, 1, 1, False),
+    (3, 4, 2, 2, False),
+    (4, 5, 7, 1, True),
+    (2, 3, 8, 1, False),
+    (5, 6, 10, 1, False),
+    (3, 5, 16, 2, True),
+    (2, 7, 20, 1, False),
+    (3, 3, 31, 1, True),
+    (2, 4, 32, 1, False),
+    (2, 3, 33, 3, True),
+    (4, 35, 48, 1, False),
+    (2, 2, 64, 1, True),
+    (2, 2, 65, 1, False),
+    (1, 3, 100, 2, True),
+    (1, 2, 128, 1, False),
+    (1, 2, 160, 1, False),
+]
+
+
+@pytest.mark.parametrize("tier", TIERS)
+@pytest.mark.parametrize("kernel", ["rbf", "cauchy"])
+@pytest.mark.parametrize("B,D,T,S,ragged", GRID)
+def test_v1_vs_oracle(cuda_device, B, D, T, S, ragged, kernel, tier):
+    case = orc.synthetic_batch(B, D, T, S, ragged=ragged, seed=100 + T)
+    errs = compare(case, cuda_device, kernel=kernel, S=S, tier=tier, grad_ell_p=True)
+    assert_parity(errs, "V1 %s T=%d" % (kernel, T))
+
+
+@pytest.mark.parametrize("tier", TIERS)
+@pytest.mark.parametrize("kernel", ["rbf", "cauchy"])
+@pytest.mark.parametrize("B,D,T,S,ragged", [g for g in GRID if g[2] in (1, 7, 10, 20, 33, 48, 100, 160)])
+def test_v2_vs_oracle(cuda_device, B, D, T, S, ragged, kernel, tier):
+    case = orc.synthetic_batch(B, D, T, S, ragged=ragged, seed=200 + T, posterior="diag")
+    errs = compare(case, cuda_device, kernel=kernel, posterior="diag", S=S, tier=tier, grad_ell_p=True)
+    assert_parity(errs, "V2 %s T=%d" % (kernel, T))
+
+
+@pytest.mark.parametrize("T", [200, 300])
+def test_large_T_workspace_path(cuda_device, T):
+    """T too large for shared-memory-resident factors: matrices live in the caller's workspace (L2)."""
+    case = orc.synthetic_batch(1, 3, T, 1, ragged=False, seed=T)
+    errs = compare(case, cuda_device, kernel="cauchy", grad_ell_p=True)
+    assert_parity(errs, "large T=%d" % T)
+
+
+def test_upstream_weights(cuda_device):
+    """Non-trivial upstream gradients on every output (g_kl_sum != 1, per-pair weights, g_z)."""
+    case = orc.synthetic_batch(3, 4, 12, 2, ragged=True, seed=9)
+    gkp = torch.randn(12, generator=torch.Generator().manual_seed(1))
+    errs = compare(case, cuda_device, S=2, g_kl_pairs=gkp, g_kl_sum=0.37, grad_ell_p=True)
+    assert_parity(errs, "upstream")
+
+
+def test_empty_sequences_and_batch(cuda_device):
+    """lengths may contain zeros (a fully masked sequence); B may be 0."""
+    import gpkl
+    case = orc.synthetic_batch(4, 3, 6, 1, ragged=False, seed=4)
+    lengths = torch.tensor([6, 0, 3, 0], dtype=torch.int32)
+    keep = torch.cat([torch.arange(0, 6), torch.arange(12, 15)])
+    case["mean"] = case["mean"][keep].contiguous()
+    case["g_z"] = case["g_z"][keep].contiguous()
+    case["lengths"] = lengths
+    case["times"][1] = 0
+    case["times"][3] = 0
+    case["times"][2, 3:] = 0
+    errs = compare(case, cuda_device, grad_ell_p=True)
+    assert_parity(errs, "zeros")
+    dev = cuda_device
+    z = torch.zeros
+    o = gpkl.gp_prior_kl_forward(z(0, 3, device=dev), z(0, 5, device=dev), z(0, dtype=torch.int32, device=dev),
+                                 torch.ones(3, device=dev), torch.ones(3, device=dev), z(0, 3, 1, 5, device=dev))
+    assert float(o["kl_sum"]) == 0.0 and o["z"].shape == (0, 3)
+
+
+def test_not_positive_definite_is_reported(cuda_device):
+    """Duplicate time stamps with zero jitter make K singular: TF raises InvalidArgumentError; here the
+    pair's outputs are NaN/inf and the device status counter is non-zero."""
+    import gpkl
+    dev = cuda_device
+    times = torch.tensor([[0.0, 1.0, 1.0, 2.0]], device=dev)
+    o = gpkl.gp_prior_kl_forward(torch.zeros(4, 1, device=dev), times, torch.tensor([4], dtype=torch.int32, device=dev),
+                                 torch.ones(1, device=dev), torch.ones(1, device=dev), torch.zeros(1, 1, 1, 4, device=dev),
+                                 noise=0.0, want_status=True)
+    torch.cuda.synchronize()
+    assert int(o["status"]) > 0 or not torch.isfinite(o["kl_pairs"]).all()
+
+
+def test_autograd_function_matches_raw(cuda_device):
+    import gpkl
+    dev = cuda_device
+    case = orc.synthetic_batch(3, 4, 9, 2, ragged=True, seed=21)
+    c = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
+    mean = c["mean"].clone().requires_grad_(True)
+    lq = c["ell_q"].clone().requires_grad_(True)
+    lp = c["ell_p"].clone().requires_grad_(True)
+    z, kl_sum, kl_pairs = gpkl.gp_prior_kl(mean, c["times"], c["lengths"], lq, lp, c["eps"], S=2)
+    loss = 0.5 * kl_sum + (c["g_z"].double() * z.double()).sum()
+    loss.backward()
+    out, grads = orc.gp_prior_kl_grads(case["mean"], case["times"], case["lengths"], case["ell_q"], case["ell_p"],
+                                       case["eps"], case["g_z"], 0.5, S=2)
+    assert rel_err(mean.grad, grads["mean"]) < TOL_GRAD
+    assert rel_err(lq.grad, grads["ell_q"]) < TOL_GRAD
+    assert rel_err(lp.grad, grads["ell_p"]) < TOL_GRAD
+    assert rel_err(kl_pairs, out["kl_pairs"]) < TOL_KL
+
+
+def test_reference_named_api(cuda_device):
+    """The four reference call sites by name (reference_api.GPPriorPath) reproduce golden G3."""
+    import gpkl
+    dev = cuda_device
+    g = load_golden("g3_v1_ragged_s2")
+    B, D = g["times"].shape[0], g["mean"].shape[1]
+    path = gpkl.GPPriorPath(D, device=dev)
+    with torch.no_grad():
+        path.approx_time_chars.copy_(g["ell_q"].to(dev))
+    seqs, sizes = g["times"].to(dev), g["lengths"].to(dev)
+    mean = g["mean"].to(dev).requires_grad_(True)
+    prior_kernel, _ = path.prior_kernels(seqs, sizes, D, B)
+    approx_kernel, chol_noise, chars = path.approx_kernels(seqs, sizes, D, B, g["S"], eps=g["eps"].to(dev))
+    z = path.gp_vae_sample(mean, chol_noise, sizes, B, g["S"], D)
+    kl_sum, kl = path.calc_gp_kl(mean, sizes, approx_kernel, prior_kernel, B, D)
+    (kl_sum + (g["g_z"].to(dev).double() * z.double()).sum()).backward()
+    assert rel_err(kl, g["kl_pairs"]) < TOL_KL and rel_err(z, g["z"]) < TOL_Z
+    assert rel_err(mean.grad, g["g_mean"]) < TOL_GRAD
+    assert rel_err(path.approx_time_chars.grad, g["g_ell_q"]) < TOL_GRAD
+
+
+def test_host_step_matches_device_path(cuda_device):
+    import gpkl
+    case = orc.synthetic_batch(6, 5, 14, 1, ragged=True, seed=33)
+    fwd, bwd = run_cuda(case, cuda_device, grad_ell_p=True)
+    hs = gpkl.HostStep(6, 5, 14, 1, case["mean"].shape[0], grad_ell_p=True, device=cuda_device)
+    pin = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
+    hs(pin["mean"], pin["times"], pin["lengths"], pin["ell_q"], pin["ell_p"], pin["eps"], pin["g_z"])
+    torch.cuda.synchronize()
+    assert torch.equal(hs.z, fwd["z"].cpu()) and torch.equal(hs.kl_pairs, fwd["kl_pairs"].cpu())
+    assert float(hs.kl_sum) == float(fwd["kl_sum"])
+    assert torch.equal(hs.g_mean, bwd["g_mean"].cpu()) and torch.equal(hs.g_ell_q, bwd["g_ell_q"].cpu())
+    assert torch.equal(hs.g_ell_p, bwd["g_ell_p"].cpu())
+    assert hs.h2d_bytes > 0 and hs.d2h_bytes > 0
