@@ -187,6 +187,12 @@ extern "C" int gpkl_forward(const GpklDesc* desc, const float* mean, const float
   int rc = check_desc(desc);
   if (rc != GPKL_OK) return rc;
   const GpklDesc& d = *desc;
+  if (d.B == 0) {  // empty batch: only the scalar is defined
+    if (!kl_sum) return GPKL_ERR_NULL;
+    cudaMemsetAsync(kl_sum, 0, sizeof(double), static_cast<cudaStream_t>(stream));
+    if (status) cudaMemsetAsync(status, 0, sizeof(int32_t), static_cast<cudaStream_t>(stream));
+    return GPKL_OK;
+  }
   if (!mean || !times || !lengths || !ell_p || !eps || !z || !kl_pairs || !kl_sum || !workspace) return GPKL_ERR_NULL;
   if (d.posterior == GPKL_POST_GP && !ell_q) return GPKL_ERR_NULL;
   if (d.posterior != GPKL_POST_GP && !aux) return GPKL_ERR_NULL;
@@ -224,6 +230,13 @@ extern "C" int gpkl_backward(const GpklDesc* desc, const float* mean, const floa
   if (rc != GPKL_OK) return rc;
   const GpklDesc& d = *desc;
   const bool want_lp = (d.flags & GPKL_FLAG_GRAD_ELL_P) != 0;
+  if (d.B == 0) {
+    cudaStream_t st0 = static_cast<cudaStream_t>(stream);
+    if (g_ell_q) cudaMemsetAsync(g_ell_q, 0, sizeof(float) * d.D, st0);
+    if (want_lp && g_ell_p) cudaMemsetAsync(g_ell_p, 0, sizeof(float) * d.D, st0);
+    if (status) cudaMemsetAsync(status, 0, sizeof(int32_t), st0);
+    return GPKL_OK;
+  }
   if (!mean || !times || !lengths || !ell_p || !eps || !g_mean || !workspace) return GPKL_ERR_NULL;
   if (d.posterior == GPKL_POST_GP && (!ell_q || !g_ell_q)) return GPKL_ERR_NULL;
   if (d.posterior != GPKL_POST_GP && (!aux || !g_aux)) return GPKL_ERR_NULL;

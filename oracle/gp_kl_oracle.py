@@ -233,9 +233,10 @@ def gp_kl_div_numpy(m, Kq, Kp):
     return 0.5 * (p1 - T + (ldp - ldq) + p3)
 
 
-def synthetic_batch(B, D, T, S=1, *, ragged=False, seed=1234, posterior="gp", ell_p_value=1.0):
+def synthetic_batch(B, D, T, S=1, *, ragged=False, seed=1234, posterior="gp", ell_p_value=1.0, grid=False):
     """Seeded synthetic inputs of SURVEY.md S8(d): irregular times cumsum(U(0.5,1.5)), mean/eps~N(0,1),
-    l_p = ell_p_value, l_q = l_p*exp(N(0,0.1^2)); ragged: T_b ~ U{ceil(T/2)..T}."""
+    l_p = ell_p_value, l_q = l_p*exp(N(0,0.1^2)); ragged: T_b ~ U{ceil(T/2)..T}.
+    grid=True uses the reference's own time stamps 0,1,..,T-1 (DataHandler.py:42; cond(K) <= 68 at l=1)."""
     g = torch.Generator().manual_seed(seed)
     if ragged:
         lengths = torch.randint((T + 1) // 2, T + 1, (B,), generator=g, dtype=torch.int32)
@@ -243,6 +244,8 @@ def synthetic_batch(B, D, T, S=1, *, ragged=False, seed=1234, posterior="gp", el
     else:
         lengths = torch.full((B,), T, dtype=torch.int32)
     times = torch.cumsum(torch.rand(B, T, generator=g) + 0.5, dim=1).to(torch.float32)
+    if grid:
+        times = torch.arange(T, dtype=torch.float32).repeat(B, 1)
     for b in range(B):
         times[b, int(lengths[b]):] = 0.0
     total = int(lengths.sum())

@@ -42,8 +42,29 @@ def run_oracle(case, *, kernel="rbf", posterior="gp", noise=1e-3, S=1, g_kl_pair
                                  posterior=posterior, noise=noise, S=S)
 
 
-def compare(case, dev, **cfg):
-    """Returns dict of scale-relative errors CUDA vs oracle."""
+def reference_rounding_floor(case, **ocfg):
+    """How far the REFERENCE'S OWN result moves when its float32-built K (tf_kernel builds K in float32,
+    Full_GP_VAE_dynamic_time.py:156-164) is replaced by the exactly evaluated K: the sensitivity of the
+    reference to the last bit of its kernel entries, ~eps32*cond(K).  Any implementation whose float32 exp
+    differs from TF's/torch's in the last ulp sits at this distance from the reference, so stress inputs
+    (irregular times, cond ~1e3) are judged against 1e-5 + 4x this floor; reference-like grids are judged
+    against the plain 1e-5 / 1e-4."""
+    aux = case.get("aux")
+    if aux is None:
+        aux = case.get("logvar")
+    args = (case["mean"], case["times"], case["lengths"], case["ell_q"], case["ell_p"], case["eps"], case.get("g_z"))
+    kw = {k: v for k, v in ocfg.items() if k not in ("g_kl_sum", "g_kl_pairs")}
+    gs, gp = ocfg.get("g_kl_sum", 1.0), ocfg.get("g_kl_pairs")
+    o32, g32 = orc.gp_prior_kl_grads(*args, gs, gp, aux=aux, **kw)
+    o64, g64 = orc.gp_prior_kl_grads(*args, gs, gp, aux=aux, build_dtype=torch.float64, **kw)
+    floor = {"kl": rel_err(o32["kl_pairs"], o64["kl_pairs"])}
+    floor["grad"] = max(rel_err(g32[k], g64[k]) for k in ("mean", "ell_q", "ell_p", "aux") if g32[k] is not None
+                        and float(g64[k].abs().max()) > 0)
+    return floor
+
+
+def compare(case, dev, floor=False, **cfg):
+    """Returns dict of scale-relative errors CUDA vs oracle (plus the reference rounding floor on request)."""
     fwd, bwd = run_cuda(case, dev, **cfg)
     ocfg = {k: v for k, v in cfg.items() if k not in ("tier", "grad_ell_p")}
     out, grads = run_oracle(case, **ocfg)
@@ -62,17 +83,29 @@ def compare(case, dev, **cfg):
         errs["g_aux"] = rel_err(bwd["g_aux"], grads["aux"])
     if cfg.get("grad_ell_p", True):
         errs["g_ell_p"] = rel_err(bwd["g_ell_p"], grads["ell_p"])
+    if floor:
+        errs["floor"] = reference_rounding_floor(case, **ocfg)
     return errs
 
 
 def assert_parity(errs, tag=""):
+    """Strict (1e-5 KL/log-det/z, 1e-4 gradients) unless errs carries a reference rounding floor, in which
+    case KL and gradient tolerances are widened by 4x that floor (see reference_rounding_floor)."""
+    floor = errs.get("floor", {"kl": 0.0, "grad": 0.0})
     bad = {}
     for k, v in errs.items():
+        if k == "floor":
+            continue
         if k == "status":
             if v != 0:
                 bad[k] = v
             continue
-        tol = TOL_GRAD if k.startswith("g_") else (TOL_Z if k == "z" else TOL_KL)
+        if k.startswith("g_"):
+            tol = TOL_GRAD + 4.0 * floor["grad"]
+        elif k in ("kl_pairs", "kl_sum"):
+            tol = TOL_KL + 4.0 * floor["kl"]
+        else:
+            tol = TOL_Z if k == "z" else TOL_KL
         if not (v < tol):
             bad[k] = v
     assert not bad, "%s parity failures %s (all: %s)" % (tag, bad, errs)
