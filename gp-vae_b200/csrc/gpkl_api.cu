@@ -150,9 +150,19 @@ int check_desc(const GpklDesc* d) {
 }
 
 int dispatch(const Params& P, bool backward, cudaStream_t st) {
-  // tier selection: only the generic tier exists so far; explicit requests for others are refused
-  if (P.d.tier == GPKL_TIER_WARP || P.d.tier == GPKL_TIER_BLOCK) return GPKL_ERR_UNSUPPORTED;
-  const cudaError_t e = launch_generic(P, backward, st);
+  // tier selection (GPKL_TIER_AUTO): register-resident warp tier for T <= 64, generic tier otherwise and
+  // for the combinations the specialised tiers do not implement (d/d ell_p).  Explicit requests are honoured
+  // or refused, never silently rerouted.
+  if (P.d.tier == GPKL_TIER_BLOCK) return GPKL_ERR_UNSUPPORTED;
+  cudaError_t e;
+  if (P.d.tier == GPKL_TIER_WARP) {
+    if (!warp_tier_supports(P.d)) return GPKL_ERR_UNSUPPORTED;
+    e = launch_warp(P, backward, st);
+  } else if (P.d.tier == GPKL_TIER_AUTO && warp_tier_supports(P.d)) {
+    e = launch_warp(P, backward, st);
+  } else {
+    e = launch_generic(P, backward, st);
+  }
   return e == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
 }
 

@@ -22,4 +22,8 @@ size_t generic_slot_floats(int T);
 int generic_slots(const GpklDesc& d);  // 0 when the matrices fit shared memory
 cudaError_t launch_generic(const Params& P, bool backward, cudaStream_t st);
 
+// warp tier (gpkl_warp.cu): register-resident, T <= 64
+bool warp_tier_supports(const GpklDesc& d);
+cudaError_t launch_warp(const Params& P, bool backward, cudaStream_t st);
+
 }  // namespace gpkl

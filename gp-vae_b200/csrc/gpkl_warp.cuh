@@ -1,0 +1,668 @@
+// Warp tier: T <= 64.  A group of LP lanes owns one (sequence, latent-dim) pair; each lane keeps R rows
+// (or columns) of the T x T matrix in REGISTERS (TM = LP*R >= T), so the O(T^3) work is FFMA on
+// registers and the only shared-memory traffic is one 128-bit broadcast load per 4*R FMAs.
+//
+//   (LP,R) = (8,1) T<=8 [4 pairs/warp], (16,1) T<=16 [2 pairs/warp], (32,1) T<=32, (16,3) T<=48
+//   [2 pairs/warp], (32,2) T<=64.   Lane `lig` of a group owns rows/columns lig + LP*j, j < R.
+//
+// Forward (V1):   rows of K_p built in registers -> right-looking Cholesky (column broadcast through a
+//   double-buffered shared vector, one __syncwarp per column) -> a = L_p^-1 m by a shuffle column sweep
+//   -> L_p rows parked in shared memory (packed lower, 16 B aligned rows) -> same for K_q, z = m + L_q eps
+//   from the register rows -> L_q transposed through shared memory so each lane owns COLUMNS -> forward
+//   substitution A = L_p^-1 L_q with L_p as 128-bit broadcast operand -> KL = 1/2[sum_offdiag A^2 +
+//   sum f(A_ii) + |a|^2] with the cancelling diagonal part in float64.
+// Backward (V1):  recompute the factors the same way; X_p = L_p^-1 and X_q = L_q^-1 as register columns;
+//   alpha = X_p^T a; C' = (Phi(w eps^T) - g/2 I) X_q by a running prefix sum down each register column;
+//   d/d ell_q = sum_{k != l} dK_q(k,l) [ g/2 (X_p^T X_p)_kl + (X_q^T C')_kl ]  with the second operand's
+//   columns broadcast from shared memory.  Nothing T x T touches HBM.
+//
+// Reference replaced: tf_kernel / gp_vae_sample / gp_kl_div (src/Models/Full_GP_VAE_dynamic_time.py:
+// 149-172, :174-195, :242-260), V2 gp_kl_div / vae_sample (src/Models/VAE_GPprior_diag_cov.py:64-71,
+// :100-119) and TF autodiff through them (:361).
+#pragma once
+#include "gpkl_common.cuh"
+#include "gpkl_launch.h"
+
+namespace gpkl {
+namespace {
+
+constexpr int WPC = 4;  // warps per CTA
+
+// Packed lower-triangular storage with 16-byte aligned rows: row i has capacity 4*(i/4+1) floats.
+__host__ __device__ constexpr int poff(int i) { return 8 * (i >> 2) * ((i >> 2) + 1) + (i & 3) * 4 * ((i >> 2) + 1); }
+
+template <int LP, int R>
+struct Geo {
+  static constexpr int TM = LP * R;
+  static constexpr int PK = poff(TM);
+  static constexpr int G = 32 / LP;  // groups (pairs) per warp
+  // per-group shared floats: 2 packed buffers, 2 column buffers, ts, dgp, dgq, dinv, as, pd + 3*S*TM
+  static constexpr int fixed_floats() { return 2 * PK + 2 * TM + 6 * TM; }
+};
+
+template <int LP>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = LP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LP, int R>
+struct Smem {
+  static constexpr int TM = LP * R;
+  float *bufA, *bufB, *col, *ts, *dgp, *dgq, *dinv, *as, *pd, *vS, *uS, *wS;
+  __device__ Smem(float* base, int S) {
+    bufA = base; base += Geo<LP, R>::PK;
+    bufB = base; base += Geo<LP, R>::PK;
+    col = base; base += 2 * TM;
+    ts = base; base += TM;
+    dgp = base; base += TM;
+    dgq = base; base += TM;
+    dinv = base; base += TM;
+    as = base; base += TM;
+    pd = base; base += TM;
+    vS = base; base += S * TM;
+    uS = base; base += S * TM;
+    wS = base;
+  }
+};
+
+// Rows of K(t, ell) (lower triangle incl. diagonal, zeros above; identity on padded rows/cols).
+template <int LP, int R, int KERNEL>
+__device__ __forceinline__ void build_rows(float (&a)[R][LP * R], const float (&trow)[R], const float* __restrict__ ts,
+                                           int lig, int T, int Tw, float ell, float sig, float noise) {
+  constexpr int TM = LP * R;
+#pragma unroll
+  for (int k4 = 0; k4 < TM; k4 += 4) {
+    if (k4 < Tw) {
+      const float4 t4 = *reinterpret_cast<const float4*>(ts + k4);
+      const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k4 + e;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int r = lig + LP * j;
+          float v = kern_val<KERNEL>(trow[j] - tv[e], ell, sig);
+          if (k == r) v += noise;
+          a[j][k] = (k <= r && r < T) ? v : ((k == r) ? 1.0f : 0.0f);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int j = 0; j < R; ++j) a[j][k4 + e] = (k4 + e == lig + LP * j) ? 1.0f : 0.0f;
+    }
+  }
+}
+
+// Right-looking Cholesky on register rows.  col: 2*TM floats of shared memory (double buffered).
+template <int LP, int R>
+__device__ __forceinline__ void chol_rows(float (&a)[R][LP * R], int lig, int T, int Tw, float* __restrict__ col,
+                                          float* __restrict__ dg, int& bad) {
+  constexpr int TM = LP * R;
+#pragma unroll
+  for (int j = 0; j < TM; ++j) {
+    if (j < Tw) {
+      float* cb = col + (j & 1) * TM;
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) cb[lig + LP * jj] = a[jj][j];
+      __syncwarp();
+      const float d = cb[j];
+      const float sd = sqrtf(d);
+      const float rs = 1.0f / sd;
+      const float rd = rs * rs;
+      if (j < T && !(d > 0.0f)) bad = 1;
+      float s[R];
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) s[jj] = (lig + LP * jj > j) ? a[jj][j] * rd : 0.0f;
+#pragma unroll
+      for (int k4 = (j + 1) & ~3; k4 < TM; k4 += 4) {
+        if (k4 < Tw) {
+          const float4 c4 = *reinterpret_cast<const float4*>(cb + k4);
+          const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (k4 + e > j) {
+#pragma unroll
+              for (int jj = 0; jj < R; ++jj) a[jj][k4 + e] = fmaf(-s[jj], cv[e], a[jj][k4 + e]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) a[jj][j] *= rs;
+      if (lig == (j % LP)) {
+        a[j / LP][j] = sd;
+        dg[j] = sd;
+      }
+    } else if (lig == (j % LP)) {
+      dg[j] = 1.0f;  // identity padding beyond the longest sequence of this warp
+    }
+  }
+}
+
+// b <- L^-1 b by a column sweep over register rows; solution also written to out[] (shared).
+template <int LP, int R>
+__device__ __forceinline__ void sweep_vec(const float (&a)[R][LP * R], float (&b)[R], int lig, int Tw,
+                                          const float* __restrict__ dinv, float* __restrict__ out) {
+  constexpr int TM = LP * R;
+#pragma unroll
+  for (int k = 0; k < TM; ++k) {
+    if (k < Tw) {
+      const float cand = b[k / LP] * dinv[k];
+      const float xk = __shfl_sync(0xffffffffu, cand, k % LP, LP);
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) b[jj] = fmaf(-a[jj][k], xk, b[jj]);
+      if (lig == (k % LP)) out[k] = xk;
+    }
+  }
+}
+
+// Park register rows in shared memory, packed lower (padding in the last 4-group of a row is zero).
+template <int LP, int R>
+__device__ __forceinline__ void store_rows(const float (&a)[R][LP * R], int lig, float* __restrict__ buf) {
+  constexpr int TM = LP * R;
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) {
+    const int r = lig + LP * jj;
+    float* row = buf + poff(r);
+#pragma unroll
+    for (int g = 0; g < TM / 4; ++g) {
+      if (4 * g <= r)
+        *reinterpret_cast<float4*>(row + 4 * g) = make_float4(a[jj][4 * g], a[jj][4 * g + 1], a[jj][4 * g + 2], a[jj][4 * g + 3]);
+    }
+  }
+}
+
+// x[jj][i] <- element (i, c_jj) of the packed lower matrix in buf (0 above the diagonal).
+template <int LP, int R>
+__device__ __forceinline__ void load_cols(float (&x)[R][LP * R], int lig, const float* __restrict__ buf) {
+  constexpr int TM = LP * R;
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      const int c = lig + LP * jj;
+      x[jj][i] = (i >= c) ? buf[poff(i) + c] : 0.0f;
+    }
+}
+
+// In place forward substitution on register columns: x <- L^-1 x, L packed lower in shared memory.
+template <int LP, int R>
+__device__ __forceinline__ void solve_cols(float (&x)[R][LP * R], const float* __restrict__ Lpk,
+                                           const float* __restrict__ dinv, int Tw) {
+  constexpr int TM = LP * R;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    if (i < Tw) {
+      const float* row = Lpk + poff(i);
+      float acc[R][2];
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) acc[jj][0] = acc[jj][1] = 0.0f;
+#pragma unroll
+      for (int k4 = 0; k4 < i; k4 += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(row + k4);
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (k4 + e < i) {
+#pragma unroll
+            for (int jj = 0; jj < R; ++jj) acc[jj][e & 1] = fmaf(lv[e], x[jj][k4 + e], acc[jj][e & 1]);
+          }
+        }
+      }
+      const float di = dinv[i];
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) x[jj][i] = (x[jj][i] - (acc[jj][0] + acc[jj][1])) * di;
+    }
+  }
+}
+
+// Column c of a lower-triangular matrix (zeros for i < c) -> packed row TM-1-c, reversed in i, so that
+// other lanes can stream it back with aligned 128-bit broadcast loads at static register positions.
+__device__ __forceinline__ int poff_dyn(int i) {
+  const int q = i >> 2, r = i & 3;
+  return 8 * q * (q + 1) + 4 * r * (q + 1);
+}
+
+template <int LP, int R>
+__device__ __forceinline__ void store_cols_rev(const float (&x)[R][LP * R], int lig, float* __restrict__ buf) {
+  constexpr int TM = LP * R;
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) {
+    const int ip = TM - 1 - (lig + LP * jj);
+    float* row = buf + poff_dyn(ip);
+#pragma unroll
+    for (int g = 0; g < TM / 4; ++g) {
+      if (4 * g <= ip)
+        *reinterpret_cast<float4*>(row + 4 * g) =
+            make_float4(x[jj][TM - 1 - 4 * g], x[jj][TM - 2 - 4 * g], x[jj][TM - 3 - 4 * g], x[jj][TM - 4 - 4 * g]);
+    }
+  }
+}
+
+// sum_{l != c} dK(c,l)/d ell * <x_c, M_l>  for each register column c; M columns in reversed-packed shared.
+template <int LP, int R, int KERNEL>
+__device__ __forceinline__ float contract_cols(const float (&x)[R][LP * R], const float* __restrict__ M,
+                                               const float* __restrict__ ts, const float (&tcol)[R], int lig, int T,
+                                               float ell, float sig) {
+  constexpr int TM = LP * R;
+  const float inv_sig = 1.0f / sig, il3 = 1.0f / (ell * ell * ell);
+  float acc = 0.0f;
+  for (int l = 0; l < T; ++l) {
+    const int ip = TM - 1 - l;
+    const float* row = M + poff_dyn(ip);
+    float dot[R];
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) dot[jj] = 0.0f;
+#pragma unroll
+    for (int g = 0; g < TM / 4; ++g) {
+      if (4 * g <= ip) {
+        const float4 q = *reinterpret_cast<const float4*>(row + 4 * g);
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+          dot[jj] = fmaf(q.x, x[jj][TM - 1 - 4 * g], dot[jj]);
+          dot[jj] = fmaf(q.y, x[jj][TM - 2 - 4 * g], dot[jj]);
+          dot[jj] = fmaf(q.z, x[jj][TM - 3 - 4 * g], dot[jj]);
+          dot[jj] = fmaf(q.w, x[jj][TM - 4 - 4 * g], dot[jj]);
+        }
+      }
+    }
+    const float tl = ts[l];
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      const int c = lig + LP * jj;
+      const float dt = tcol[jj] - tl;
+      const float kv = kern_val<KERNEL>(dt, ell, sig);
+      const float dk = kern_dell<KERNEL>(dt, kv, il3, inv_sig);
+      if (c != l && c < T) acc = fmaf(dot[jj], dk, acc);
+    }
+  }
+  return acc;
+}
+
+struct PairInfo {
+  int p, b, d, T, lig;
+  long long r0;
+  bool active;
+};
+
+template <int LP>
+__device__ __forceinline__ PairInfo pair_info(const Params& P) {
+  PairInfo pi;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int G = 32 / LP;
+  pi.lig = lane % LP;
+  pi.p = (blockIdx.x * WPC + warp) * G + lane / LP;
+  pi.active = pi.p < P.d.B * P.d.D;
+  pi.b = pi.active ? pi.p / P.d.D : 0;
+  pi.d = pi.active ? pi.p - pi.b * P.d.D : 0;
+  pi.T = pi.active ? P.lengths[pi.b] : 0;
+  pi.r0 = pi.active ? P.offsets[pi.b] : 0;
+  return pi;
+}
+
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <int LP, int R, int KERNEL, int POST>
+__global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats) {
+  constexpr int TM = LP * R;
+  extern __shared__ __align__(16) float smem_f[];
+  const GpklDesc& d = P.d;
+  const int S = d.S;
+  const PairInfo pi = pair_info<LP>(P);
+  const int gslot = (threadIdx.x >> 5) * (32 / LP) + (threadIdx.x & 31) / LP;
+  Smem<LP, R> sm(smem_f + (size_t)gslot * group_floats, S);
+  const int T = pi.T, lig = pi.lig;
+  const int Tw = warp_max(T);
+  if (Tw == 0) {
+    if (pi.active && lig == 0) {
+      P.kl_pairs[pi.p] = 0.0f;
+      if (P.logdets) { P.logdets[2 * pi.p] = 0.0f; P.logdets[2 * pi.p + 1] = 0.0f; }
+    }
+    return;
+  }
+  const float noise = d.noise, sig = (float)(1.0 - (double)noise);
+  float trow[R], mrow[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int r = lig + LP * j;
+    const bool ok = r < T;
+    trow[j] = ok ? P.times[(size_t)pi.b * d.T_max + r] : 0.0f;
+    mrow[j] = ok ? P.mean[(size_t)(pi.r0 + r) * d.D + pi.d] : 0.0f;
+    sm.ts[r] = trow[j];
+    for (int s = 0; s < S; ++s) sm.vS[s * TM + r] = ok ? P.eps[((size_t)pi.p * S + s) * d.T_max + r] : 0.0f;
+  }
+  __syncwarp();
+  int bad = 0;
+  float a[R][TM];
+  const float lp = pi.active ? P.ell_p[pi.d] : 1.0f;
+  build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise);
+  chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
+  __syncwarp();
+  float bvec[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) bvec[j] = mrow[j];
+  sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as);
+  store_rows<LP, R>(a, lig, sm.bufA);
+  __syncwarp();
+  double part = 0.0, ldp = 0.0, ldq = 0.0;
+  if (POST == GPKL_POST_GP) {
+    const float lq = pi.active ? P.ell_q[pi.d] : 1.0f;
+    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise);
+    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad);
+    // z_s = m + L_q eps_s from the register rows
+    for (int s = 0; s < S; ++s) {
+      float zz[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) zz[j] = mrow[j];
+#pragma unroll
+      for (int k4 = 0; k4 < TM; k4 += 4) {
+        if (k4 < Tw) {
+          const float4 e4 = *reinterpret_cast<const float4*>(sm.vS + s * TM + k4);
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            zz[j] = fmaf(a[j][k4], e4.x, zz[j]);
+            zz[j] = fmaf(a[j][k4 + 1], e4.y, zz[j]);
+            zz[j] = fmaf(a[j][k4 + 2], e4.z, zz[j]);
+            zz[j] = fmaf(a[j][k4 + 3], e4.w, zz[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int r = lig + LP * j;
+        if (r < T) P.z[((size_t)S * pi.r0 + (size_t)s * T + r) * d.D + pi.d] = zz[j];
+      }
+    }
+    store_rows<LP, R>(a, lig, sm.bufB);
+    __syncwarp();
+    float (&x)[R][TM] = a;  // reuse the registers: columns of L_q
+    load_cols<LP, R>(x, lig, sm.bufB);
+    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
+    float ssq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) {
+        const float v = (i == lig + LP * jj) ? 0.0f : x[jj][i];
+        ssq = fmaf(v, v, ssq);
+      }
+    part = (double)ssq;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int r = lig + LP * j;
+      if (r < T) {
+        const double lpd = (double)sm.dgp[r], lqd = (double)sm.dgq[r];
+        const double av = (double)sm.as[r];
+        part += diag_term(lqd / lpd) + av * av;
+        ldp += 2.0 * log(lpd);
+        ldq += 2.0 * log(lqd);
+      }
+    }
+  } else {  // diagonal posterior: X = L_p^-1 columns, h_c = |X[:,c]|^2
+    float (&x)[R][TM] = a;
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
+    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      const int c = lig + LP * jj;
+      float h = 0.0f;
+#pragma unroll
+      for (int i = 0; i < TM; ++i) h = fmaf(x[jj][i], x[jj][i], h);
+      if (c < T) {
+        const float lv = P.aux[(size_t)(pi.r0 + c) * d.D + pi.d];
+        const float vv = expf(lv), sd = expf(0.5f * lv);
+        const double lpd = (double)sm.dgp[c], av = (double)sm.as[c];
+        part += (double)h * (double)vv - 1.0 - (double)lv + av * av + 2.0 * log(lpd);
+        ldp += 2.0 * log(lpd);
+        ldq += (double)lv;
+        for (int s = 0; s < S; ++s)
+          P.z[((size_t)S * pi.r0 + (size_t)s * T + c) * d.D + pi.d] = mrow[jj] + sd * sm.vS[s * TM + c];
+      }
+    }
+  }
+  part = group_sum<LP>(part);
+  if (P.logdets) {
+    ldp = group_sum<LP>(ldp);
+    ldq = group_sum<LP>(ldq);
+  }
+  bad = __any_sync(0xffffffffu, bad && pi.active) ? 1 : 0;
+  if (pi.active && lig == 0) {
+    P.kl_pairs[pi.p] = (float)(0.5 * part);
+    if (P.logdets) { P.logdets[2 * pi.p] = (float)ldp; P.logdets[2 * pi.p + 1] = (float)ldq; }
+  }
+  if (bad && P.status && (threadIdx.x & 31) == 0) atomicAdd(P.status, 1);
+}
+
+template <int LP, int R, int KERNEL, int POST>
+__global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats) {
+  constexpr int TM = LP * R;
+  extern __shared__ __align__(16) float smem_f[];
+  const GpklDesc& d = P.d;
+  const int S = d.S;
+  const PairInfo pi = pair_info<LP>(P);
+  const int gslot = (threadIdx.x >> 5) * (32 / LP) + (threadIdx.x & 31) / LP;
+  Smem<LP, R> sm(smem_f + (size_t)gslot * group_floats, S);
+  const int T = pi.T, lig = pi.lig;
+  const int Tw = warp_max(T);
+  if (Tw == 0) {
+    if (pi.active && lig == 0 && P.gq_pairs) P.gq_pairs[pi.p] = 0.0f;
+    return;
+  }
+  const float noise = d.noise, sig = (float)(1.0 - (double)noise);
+  const float g = pi.active ? (float)((P.g_kl_sum ? *P.g_kl_sum : 1.0) + (P.g_kl_pairs ? (double)P.g_kl_pairs[pi.p] : 0.0)) : 0.0f;
+  float trow[R], mrow[R], gzs[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int r = lig + LP * j;
+    const bool ok = r < T;
+    trow[j] = ok ? P.times[(size_t)pi.b * d.T_max + r] : 0.0f;
+    mrow[j] = ok ? P.mean[(size_t)(pi.r0 + r) * d.D + pi.d] : 0.0f;
+    sm.ts[r] = trow[j];
+    float gs = 0.0f;
+    for (int s = 0; s < S; ++s) {
+      sm.vS[s * TM + r] = ok ? P.eps[((size_t)pi.p * S + s) * d.T_max + r] : 0.0f;
+      const float gz = (ok && P.g_z) ? P.g_z[((size_t)S * pi.r0 + (size_t)s * T + r) * d.D + pi.d] : 0.0f;
+      sm.uS[s * TM + r] = gz;
+      gs += gz;
+    }
+    gzs[j] = gs;
+  }
+  __syncwarp();
+  int bad = 0;
+  float a[R][TM];
+  const float lp = pi.active ? P.ell_p[pi.d] : 1.0f;
+  build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise);
+  chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
+  __syncwarp();
+  float bvec[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) bvec[j] = mrow[j];
+  sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as);
+  store_rows<LP, R>(a, lig, sm.bufA);
+  __syncwarp();
+  // X_p = L_p^-1 as register columns
+  float (&x)[R][TM] = a;
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
+  solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
+  // alpha_c = <X_p[:,c], a> ; g_mean = g alpha + sum_s g_z
+  float hdiag[R];
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) {
+    float al = 0.0f, h = 0.0f;
+#pragma unroll
+    for (int k4 = 0; k4 < TM; k4 += 4) {
+      if (k4 < Tw) {
+        const float4 a4 = *reinterpret_cast<const float4*>(sm.as + k4);
+        al = fmaf(x[jj][k4], a4.x, al);
+        al = fmaf(x[jj][k4 + 1], a4.y, al);
+        al = fmaf(x[jj][k4 + 2], a4.z, al);
+        al = fmaf(x[jj][k4 + 3], a4.w, al);
+        if (POST == GPKL_POST_DIAG) {
+          h = fmaf(x[jj][k4], x[jj][k4], h);
+          h = fmaf(x[jj][k4 + 1], x[jj][k4 + 1], h);
+          h = fmaf(x[jj][k4 + 2], x[jj][k4 + 2], h);
+          h = fmaf(x[jj][k4 + 3], x[jj][k4 + 3], h);
+        }
+      }
+    }
+    hdiag[jj] = h;
+    const int c = lig + LP * jj;
+    if (c < T) P.g_mean[(size_t)(pi.r0 + c) * d.D + pi.d] = g * al + gzs[jj];
+  }
+  if (POST == GPKL_POST_DIAG) {
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      const int c = lig + LP * jj;
+      if (c < T) {
+        const float lv = P.aux[(size_t)(pi.r0 + c) * d.D + pi.d];
+        const float vv = expf(lv), sd = expf(0.5f * lv);
+        float ge = 0.0f;
+        for (int s = 0; s < S; ++s) ge = fmaf(sm.uS[s * TM + c], sm.vS[s * TM + c], ge);
+        P.g_aux[(size_t)(pi.r0 + c) * d.D + pi.d] = 0.5f * g * (hdiag[jj] * vv - 1.0f) + 0.5f * sd * ge;
+      }
+    }
+  } else {
+    const float lq = pi.active ? P.ell_q[pi.d] : 1.0f;
+    // t1 = sum_{k != l} dK_q(k,l) (X_p^T X_p)_kl
+    store_cols_rev<LP, R>(x, lig, sm.bufB);
+    __syncwarp();
+    float t1 = contract_cols<LP, R, KERNEL>(x, sm.bufB, sm.ts, trow, lig, T, lq, sig);
+    __syncwarp();
+    // factor K_q
+    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise);
+    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgq[lig + LP * j];
+    store_rows<LP, R>(a, lig, sm.bufA);
+    __syncwarp();
+    // w_s = L_q^T g_z,s (column reads of the packed rows) ; pd = 1/2 sum_s w_s eps_s - g/2
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      const int k = lig + LP * jj;
+      float pdk = 0.0f;
+      for (int s = 0; s < S; ++s) {
+        float wk = 0.0f;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          if (i < Tw) {
+            const float l = (i >= k) ? sm.bufA[poff(i) + k] : 0.0f;
+            wk = fmaf(l, sm.uS[s * TM + i], wk);
+          }
+        }
+        sm.wS[s * TM + k] = wk;
+        pdk = fmaf(wk, sm.vS[s * TM + k], pdk);
+      }
+      sm.pd[k] = 0.5f * pdk - 0.5f * g;
+    }
+    __syncwarp();
+    // X_q columns
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
+    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
+    // C'[:,l] = pd .* X_q[:,l] + sum_s w_s .* prefix(eps_s .* X_q[:,l]) -> reversed-packed rows of bufB
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      const int ip = TM - 1 - (lig + LP * jj);
+      float* row = sm.bufB + poff_dyn(ip);
+      float cum = 0.0f;  // sample 0 fused; further samples are added below
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        if (i < Tw) {
+          const float xi = x[jj][i];
+          float cv = fmaf(sm.pd[i], xi, sm.wS[i] * cum);
+          cum = fmaf(sm.vS[i], xi, cum);
+          if (TM - 1 - i <= (ip | 3)) row[TM - 1 - i] = cv;
+        } else {
+          if (TM - 1 - i <= (ip | 3)) row[TM - 1 - i] = 0.0f;
+        }
+      }
+      for (int s = 1; s < S; ++s) {
+        float cs = 0.0f;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          if (i < Tw) {
+            const float xi = x[jj][i];
+            if (TM - 1 - i <= (ip | 3)) row[TM - 1 - i] = fmaf(sm.wS[s * TM + i], cs, row[TM - 1 - i]);
+            cs = fmaf(sm.vS[s * TM + i], xi, cs);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const float t2 = contract_cols<LP, R, KERNEL>(x, sm.bufB, sm.ts, trow, lig, T, lq, sig);
+    const double gq = group_sum<LP>(0.5 * (double)g * (double)t1 + (double)t2);
+    if (pi.active && lig == 0) P.gq_pairs[pi.p] = (float)gq;
+  }
+  bad = __any_sync(0xffffffffu, bad && pi.active) ? 1 : 0;
+  if (bad && P.status && (threadIdx.x & 31) == 0) atomicAdd(P.status, 1);
+}
+
+template <int LP, int R>
+size_t warp_smem_bytes(int S) {
+  return (size_t)WPC * (32 / LP) * (Geo<LP, R>::fixed_floats() + 3 * S * LP * R) * sizeof(float);
+}
+
+template <int LP, int R, int KERNEL, int POST, bool BWD>
+cudaError_t launch_cfg(const Params& P, cudaStream_t st) {
+  const int S = P.d.S;
+  const int group_floats = Geo<LP, R>::fixed_floats() + 3 * S * LP * R;
+  const size_t smem = warp_smem_bytes<LP, R>(S);
+  if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
+  const int npairs = P.d.B * P.d.D;
+  const int per_cta = WPC * (32 / LP);
+  const int grid = (npairs + per_cta - 1) / per_cta;
+  cudaError_t e;
+  if constexpr (!BWD) {
+    auto kern = fwd_warp<LP, R, KERNEL, POST>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    prof_begin(false, st);
+    kern<<<grid, WPC * 32, smem, st>>>(P, group_floats);
+    prof_end(false, st);
+  } else {
+    auto kern = bwd_warp<LP, R, KERNEL, POST>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    prof_begin(true, st);
+    kern<<<grid, WPC * 32, smem, st>>>(P, group_floats);
+    prof_end(true, st);
+  }
+  note_launch();
+  return cudaGetLastError();
+}
+
+template <int LP, int R, bool BWD>
+cudaError_t launch_kp(const Params& P, cudaStream_t st) {
+  const bool rbf = P.d.kernel == GPKL_KERNEL_RBF;
+  const bool gp = P.d.posterior == GPKL_POST_GP;
+  if (rbf && gp) return launch_cfg<LP, R, GPKL_KERNEL_RBF, GPKL_POST_GP, BWD>(P, st);
+  if (rbf && !gp) return launch_cfg<LP, R, GPKL_KERNEL_RBF, GPKL_POST_DIAG, BWD>(P, st);
+  if (!rbf && gp) return launch_cfg<LP, R, GPKL_KERNEL_CAUCHY, GPKL_POST_GP, BWD>(P, st);
+  return launch_cfg<LP, R, GPKL_KERNEL_CAUCHY, GPKL_POST_DIAG, BWD>(P, st);
+}
+
+}  // namespace
+}  // namespace gpkl
