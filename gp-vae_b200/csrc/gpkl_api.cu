@@ -156,9 +156,9 @@ int dispatch(const Params& P, bool backward, cudaStream_t st) {
   if (P.d.tier == GPKL_TIER_BLOCK) return GPKL_ERR_UNSUPPORTED;
   cudaError_t e;
   if (P.d.tier == GPKL_TIER_WARP) {
-    if (!warp_tier_supports(P.d)) return GPKL_ERR_UNSUPPORTED;
+    if (!warp_tier_supports(P.d, backward)) return GPKL_ERR_UNSUPPORTED;
     e = launch_warp(P, backward, st);
-  } else if (P.d.tier == GPKL_TIER_AUTO && warp_tier_supports(P.d)) {
+  } else if (P.d.tier == GPKL_TIER_AUTO && warp_tier_supports(P.d, backward)) {
     e = launch_warp(P, backward, st);
   } else {
     e = launch_generic(P, backward, st);

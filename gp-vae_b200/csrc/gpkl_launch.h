@@ -23,7 +23,7 @@ int generic_slots(const GpklDesc& d);  // 0 when the matrices fit shared memory
 cudaError_t launch_generic(const Params& P, bool backward, cudaStream_t st);
 
 // warp tier (gpkl_warp.cu): register-resident, T <= 64
-bool warp_tier_supports(const GpklDesc& d);
+bool warp_tier_supports(const GpklDesc& d, bool backward);
 cudaError_t launch_warp(const Params& P, bool backward, cudaStream_t st);
 
 }  // namespace gpkl

@@ -7,9 +7,9 @@ namespace gpkl {
 template <int LP, int R, bool BWD>
 cudaError_t launch_warp_inst(const Params& P, cudaStream_t st);
 
-bool warp_tier_supports(const GpklDesc& d) {
+bool warp_tier_supports(const GpklDesc& d, bool backward) {
   if (d.T_max > 64 || d.T_max < 1) return false;
-  if (d.flags & GPKL_FLAG_GRAD_ELL_P) return false;  // d/d ell_p is served by the generic tier
+  if (backward && (d.flags & GPKL_FLAG_GRAD_ELL_P)) return false;  // d/d ell_p is served by the generic tier
   if (d.posterior != GPKL_POST_GP && d.posterior != GPKL_POST_DIAG) return false;
   if (d.S > 8) return false;
   return true;

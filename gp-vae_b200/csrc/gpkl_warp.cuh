@@ -371,10 +371,12 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
           const float4 e4 = *reinterpret_cast<const float4*>(sm.vS + s * TM + k4);
 #pragma unroll
           for (int j = 0; j < R; ++j) {
-            zz[j] = fmaf(a[j][k4], e4.x, zz[j]);
-            zz[j] = fmaf(a[j][k4 + 1], e4.y, zz[j]);
-            zz[j] = fmaf(a[j][k4 + 2], e4.z, zz[j]);
-            zz[j] = fmaf(a[j][k4 + 3], e4.w, zz[j]);
+            // entries above the diagonal of a register row hold update garbage (never part of L): mask them
+            const int r = lig + LP * j;
+            zz[j] = fmaf(k4 <= r ? a[j][k4] : 0.0f, e4.x, zz[j]);
+            zz[j] = fmaf(k4 + 1 <= r ? a[j][k4 + 1] : 0.0f, e4.y, zz[j]);
+            zz[j] = fmaf(k4 + 2 <= r ? a[j][k4 + 2] : 0.0f, e4.z, zz[j]);
+            zz[j] = fmaf(k4 + 3 <= r ? a[j][k4 + 3] : 0.0f, e4.w, zz[j]);
           }
         }
       }
