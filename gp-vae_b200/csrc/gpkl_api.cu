@@ -150,16 +150,20 @@ int check_desc(const GpklDesc* d) {
 }
 
 int dispatch(const Params& P, bool backward, cudaStream_t st) {
-  // tier selection (GPKL_TIER_AUTO): register-resident warp tier for T <= 64, generic tier otherwise and
-  // for the combinations the specialised tiers do not implement (d/d ell_p).  Explicit requests are honoured
-  // or refused, never silently rerouted.
-  if (P.d.tier == GPKL_TIER_BLOCK) return GPKL_ERR_UNSUPPORTED;
+  // tier selection (GPKL_TIER_AUTO): register-resident warp tier for T <= 32, shared-memory block tier up to
+  // T ~ 144, generic tier otherwise and for the combinations the specialised tiers do not implement
+  // (d/d ell_p).  Explicit requests are honoured or refused, never silently rerouted.
   cudaError_t e;
   if (P.d.tier == GPKL_TIER_WARP) {
     if (!warp_tier_supports(P.d, backward)) return GPKL_ERR_UNSUPPORTED;
     e = launch_warp(P, backward, st);
-  } else if (P.d.tier == GPKL_TIER_AUTO && warp_tier_supports(P.d, backward)) {
+  } else if (P.d.tier == GPKL_TIER_BLOCK) {
+    if (!block_tier_supports(P.d, backward)) return GPKL_ERR_UNSUPPORTED;
+    e = launch_block(P, backward, st);
+  } else if (P.d.tier == GPKL_TIER_AUTO && P.d.T_max <= 32 && warp_tier_supports(P.d, backward)) {
     e = launch_warp(P, backward, st);
+  } else if (P.d.tier == GPKL_TIER_AUTO && block_tier_supports(P.d, backward)) {
+    e = launch_block(P, backward, st);
   } else {
     e = launch_generic(P, backward, st);
   }

@@ -1,0 +1,554 @@
+// Block tier: one CTA per (sequence, latent-dim) pair, 32 < T <= ~160, matrices resident in shared memory.
+//
+// Loop-based by design (the register-resident warp tier is instruction-fetch bound beyond T ~ 32, see
+// profiles/r01_c2_warp_tier_unrolled_ncu_summary.txt): every O(T^3) phase is the same inner loop,
+//
+//     tile_update:  acc[4][4] (+/-)= sum_j  U[j*ldu + r0..r0+3] (x) V[j*ldv + c0..c0+3]
+//
+// i.e. a 4x4 register tile fed by two 128-bit shared-memory loads per 16 FMAs, over operands stored
+// "k-major" (contraction index outermost).  A buffer is (TP+1) x ld floats (TP = T rounded up to 16,
+// ld = TP+4) holding two triangles at once:
+//     LC(i,k) = B[k*ld + i]      factor L, column-major  (i >= k)   -> k-major in the column index
+//     XR(i,k) = B[(i+1)*ld + k]  inverse/solution X, row-major (i >= k) -> k-major in the row index
+// Phases
+//   Cholesky   left-looking by 16-column panels; K entries are GENERATED in the accumulator init (never
+//              stored), panel -= L[:,0:j0] L[panel,0:j0]^T via tile_update, the 16x16 diagonal block is
+//              factored and inverted by one warp in registers (shuffles), rows below are multiplied by the
+//              inverse block (tile_update again).  The mean vector rides along as an extra matrix row, so
+//              a = L_p^-1 m falls out of the factorisation.
+//   Solve      X = L^-1 B by 16-row blocks: tile_update against the already solved rows, then the stored
+//              inverse diagonal block (tile_update).  B = L_q gives A = L_p^-1 L_q, B = I gives L^-1.
+//   Contract   sum_{k != l} dK(k,l)/d ell * (X_U^T X_V)_kl : tile_update over the row index, kernel
+//              derivative evaluated in the epilogue (never stored).
+// Math: SURVEY.md Appendix A; reference replaced: src/Models/Full_GP_VAE_dynamic_time.py:149-172, :174-195,
+// :242-260 (+ TF autodiff :361); V2 src/Models/VAE_GPprior_diag_cov.py:64-71, :100-119.
+#include "gpkl_common.cuh"
+#include "gpkl_launch.h"
+
+namespace gpkl {
+namespace {
+
+constexpr int NB = 16;
+
+template <int SGN>
+__device__ __forceinline__ void tile_update(float (&acc)[4][4], const float* __restrict__ U, int ldu,
+                                            const float* __restrict__ V, int ldv, int ja, int jb) {
+  const float* up = U + (size_t)ja * ldu;
+  const float* vp = V + (size_t)ja * ldv;
+#pragma unroll 4
+  for (int j = ja; j < jb; ++j) {
+    const float4 u4 = *reinterpret_cast<const float4*>(up);
+    const float4 v4 = *reinterpret_cast<const float4*>(vp);
+    up += ldu;
+    vp += ldv;
+    const float u[4] = {SGN > 0 ? u4.x : -u4.x, SGN > 0 ? u4.y : -u4.y, SGN > 0 ? u4.z : -u4.z, SGN > 0 ? u4.w : -u4.w};
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(u[r], v[c], acc[r][c]);
+  }
+}
+
+struct Lay {  // shared-memory carve-up (floats), identical on host and device
+  int TP, ld, nP, S;
+  __host__ __device__ Lay(int Tmax, int S_) : S(S_) {
+    TP = (Tmax + NB - 1) / NB * NB;
+    if (TP < NB) TP = NB;
+    ld = TP + 4;
+    nP = TP / NB;
+  }
+  __host__ __device__ size_t buf() const { return (size_t)(TP + 1) * ld; }
+  __host__ __device__ size_t floats() const {
+    return 64 + 2 * buf() + (size_t)NB * ld + 2 * (size_t)nP * 256 + ld + 7 * (size_t)TP + 3 * (size_t)S * TP;
+  }
+};
+
+struct Sm {
+  double* red;
+  float *B1, *B2, *pan, *invp, *invq, *ts, *dgp, *dgq, *aa, *al, *pd, *gzs, *mm, *u, *v, *w;
+  __device__ Sm(float* base, const Lay& L) {
+    red = reinterpret_cast<double*>(base); base += 64;
+    B1 = base; base += L.buf();
+    B2 = base; base += L.buf();
+    pan = base; base += (size_t)NB * L.ld;
+    invp = base; base += (size_t)L.nP * 256;
+    invq = base; base += (size_t)L.nP * 256;
+    ts = base; base += L.ld;
+    dgp = base; base += L.TP;
+    dgq = base; base += L.TP;
+    aa = base; base += L.TP;
+    al = base; base += L.TP;
+    pd = base; base += L.TP;
+    gzs = base; base += L.TP;
+    mm = base; base += L.TP;
+    u = base; base += (size_t)L.S * L.TP;
+    v = base; base += (size_t)L.S * L.TP;
+    w = base;
+  }
+};
+
+// Entry (i,k) of the (optionally row-augmented) kernel matrix, identity on the padding.
+template <int KERNEL>
+__device__ __forceinline__ float k_entry(int i, int k, int T, int TP, bool extra, const float* __restrict__ ts,
+                                         const float* __restrict__ mm, float ell, float sig, float noise) {
+  if (i < T && k < T) {
+    float v = kern_val<KERNEL>(ts[i] - ts[k], ell, sig);
+    if (i == k) v += noise;
+    return v;
+  }
+  if (i == k) return 1.0f;
+  if (extra && i == TP && k < T) return mm[k];
+  return 0.0f;
+}
+
+// One warp: factor the 16x16 diagonal block held in pan (columns 0..15, rows j0..j0+15), write L_dd into
+// the LC triangle of Bm, its inverse (k-major: inv[c'*16 + i] = Linv[i][c']) and the diagonal into dg.
+__device__ __forceinline__ void diag_factor(float* __restrict__ Bm, int ld, int j0, int T, const float* __restrict__ pan,
+                                            float* __restrict__ inv, float* __restrict__ dg, int* bad) {
+  const int lane = threadIdx.x & 31, l = lane & 15;
+  float a[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) a[c] = (c <= l) ? pan[c * ld + j0 + l] : 0.0f;
+  float dgv = 1.0f;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const float d = __shfl_sync(0xffffffffu, a[c], c, 16);
+    const float sd = sqrtf(d);
+    const float rs = 1.0f / sd;
+    if (j0 + c < T && !(d > 0.0f)) *bad = 1;
+    const float lc = (l > c) ? a[c] * rs : ((l == c) ? sd : 0.0f);
+    a[c] = lc;
+    if (l == c) dgv = sd;
+#pragma unroll
+    for (int k = c + 1; k < 16; ++k) {
+      const float lk = __shfl_sync(0xffffffffu, lc, k, 16);
+      a[k] = fmaf(-lc, lk, a[k]);
+    }
+  }
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float s = (i == l) ? 1.0f : 0.0f;
+#pragma unroll
+    for (int k = 0; k < i; ++k) {
+      const float lik = __shfl_sync(0xffffffffu, a[k], i, 16);
+      s = fmaf(-lik, x[k], s);
+    }
+    const float lii = __shfl_sync(0xffffffffu, a[i], i, 16);
+    x[i] = s / lii;
+  }
+  if (lane < 16) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c <= l) Bm[(size_t)(j0 + c) * ld + j0 + l] = a[c];
+    dg[j0 + l] = dgv;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<float4*>(inv + l * 16 + 4 * g) = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+  }
+}
+
+// Left-looking panel Cholesky with fused kernel-matrix generation.  Result: LC triangle of Bm, inverse
+// diagonal blocks in inv[nP][256], diag(L) in dg.  extra: also carry row TP = m^T (gives L^-1 m).
+template <int KERNEL>
+__device__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool extra, const float* __restrict__ ts,
+                           const float* __restrict__ mm, float ell, float sig, float noise, float* __restrict__ pan,
+                           float* __restrict__ inv, float* __restrict__ dg, int* bad) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int cg = tid & 3, rg = tid >> 2, NRG = NT >> 2;
+  const int ld = L.ld, TP = L.TP;
+  // rows beyond the last real row are identity padding and decouple: only panels that contain real rows matter
+  const int Tact = (T + NB - 1) / NB * NB;
+  const int rows_end = extra ? TP + 4 : Tact;
+  for (int j0 = 0; j0 < Tact; j0 += NB) {
+    const int cb = j0 + 4 * cg;
+    for (int rb = j0 + 4 * rg; rb < rows_end; rb += 4 * NRG) {
+      if (rb >= Tact && rb < TP) continue;  // identity padding rows
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = k_entry<KERNEL>(rb + r, cb + c, T, TP, extra, ts, mm, ell, sig, noise);
+      tile_update<-1>(acc, Bm + rb, ld, Bm + cb, ld, 0, j0);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(pan + (size_t)(4 * cg + c) * ld + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+    }
+    __syncthreads();
+    if (tid < 32) diag_factor(Bm, ld, j0, T, pan, inv + (size_t)(j0 / NB) * 256, dg, bad);
+    __syncthreads();
+    const float* invJ = inv + (size_t)(j0 / NB) * 256;
+    for (int rb = j0 + NB + 4 * rg; rb < rows_end; rb += 4 * NRG) {
+      if (rb >= Tact && rb < TP) continue;
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+      tile_update<1>(acc, pan + rb, ld, invJ + 4 * cg, 16, 0, 16);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(Bm + (size_t)(cb + c) * ld + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+    }
+    __syncthreads();
+  }
+  // identity padding: diag entries for rows in [T, TP) (only dg is consulted for them)
+  for (int i = Tact + tid; i < TP; i += NT) dg[i] = 1.0f;
+  __syncthreads();
+}
+
+// X = L^-1 B by 16-row blocks into the XR triangle of Xb.  L: LC triangle of Lb with inverse diagonal
+// blocks invL.  IDENT: B = I, else B = LC triangle of Bb.  Returns this thread's partial sum of squares
+// of the strictly-lower entries of X (rows/cols < T).
+template <bool IDENT>
+__device__ float solve_block(const float* __restrict__ Lb, const float* __restrict__ invL, const float* __restrict__ Bb,
+                             float* __restrict__ Xb, const Lay& L, int T, float* __restrict__ pan) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int ld = L.ld;
+  const int Tact = (T + NB - 1) / NB * NB;
+  float ssq = 0.0f;
+  for (int i0 = 0; i0 < Tact; i0 += NB) {
+    const int ntile = 4 * (i0 / 4 + 4);
+    for (int id = tid; id < ntile; id += NT) {
+      const int rt = id & 3, ct = id >> 2;
+      const int rb = i0 + 4 * rt, cb = 4 * ct;
+      // (tiles entirely above the diagonal are staged too -- as zeros -- because the diagonal-block
+      //  multiply below reads every staged row of its column range)
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int row = rb + r, col = cb + c;
+          acc[r][c] = (col <= row) ? (IDENT ? (row == col ? 1.0f : 0.0f) : Bb[(size_t)col * ld + row]) : 0.0f;
+        }
+      // contraction over already solved rows k in [cb, i0); X[k][col] exists only for col <= k
+      int k = cb < i0 ? cb : i0;
+      const int khead = (k + 3 < i0) ? k + 3 : i0;
+      for (; k < khead; ++k) {
+        const float4 u4 = *reinterpret_cast<const float4*>(Lb + (size_t)k * ld + rb);
+        const float4 v4 = *reinterpret_cast<const float4*>(Xb + (size_t)(k + 1) * ld + cb);
+        const float u[4] = {u4.x, u4.y, u4.z, u4.w};
+        const float v[4] = {cb <= k ? v4.x : 0.0f, cb + 1 <= k ? v4.y : 0.0f, cb + 2 <= k ? v4.z : 0.0f,
+                            cb + 3 <= k ? v4.w : 0.0f};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(-u[r], v[c], acc[r][c]);
+      }
+      tile_update<-1>(acc, Lb + rb, ld, Xb + ld + cb, ld, k, i0);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        *reinterpret_cast<float4*>(pan + (size_t)(4 * rt + r) * ld + cb) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
+    __syncthreads();
+    const float* invI = invL + (size_t)(i0 / NB) * 256;
+    for (int id = tid; id < ntile; id += NT) {
+      const int rt = id & 3, ct = id >> 2;
+      const int rb = i0 + 4 * rt, cb = 4 * ct;
+      if (cb > rb + 3) continue;
+      float x[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x[r][c] = 0.0f;
+      tile_update<1>(x, invI + 4 * rt, 16, pan + cb, ld, 0, 16);
+      if (cb + 3 <= rb) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          *reinterpret_cast<float4*>(Xb + (size_t)(rb + r + 1) * ld + cb) = make_float4(x[r][0], x[r][1], x[r][2], x[r][3]);
+          if (rb + r < T) ssq = fmaf(x[r][0], x[r][0], fmaf(x[r][1], x[r][1], fmaf(x[r][2], x[r][2], fmaf(x[r][3], x[r][3], ssq))));
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int row = rb + r, col = cb + c;
+            if (col <= row) {
+              Xb[(size_t)(row + 1) * ld + col] = x[r][c];
+              if (col < row && row < T) ssq = fmaf(x[r][c], x[r][c], ssq);
+            }
+          }
+      }
+    }
+    __syncthreads();
+  }
+  return ssq;
+}
+
+// sum_{k != l, k,l < T} dK(k,l)/d ell * sum_{i} XU[i][k] XV[i][l]   (XR triangles of Ub / Vb); thread partial.
+template <int KERNEL>
+__device__ double contract_block(const float* __restrict__ Ub, const float* __restrict__ Vb, const Lay& L, int T,
+                                 const float* __restrict__ ts, float ell, float sig) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int ld = L.ld;
+  const int nk = (T + 3) / 4;
+  const float inv_sig = 1.0f / sig, il3 = 1.0f / (ell * ell * ell);
+  double total = 0.0;
+  for (int id = tid; id < nk * nk; id += NT) {
+    const int kt = id % nk, lt = id / nk;
+    const int kb = 4 * kt, lb = 4 * lt;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+    int i = kb > lb ? kb : lb;
+    const int ihead = (i + 3 < T) ? i + 3 : T;
+    for (; i < ihead; ++i) {
+      const float4 u4 = *reinterpret_cast<const float4*>(Ub + (size_t)(i + 1) * ld + kb);
+      const float4 v4 = *reinterpret_cast<const float4*>(Vb + (size_t)(i + 1) * ld + lb);
+      const float u[4] = {kb <= i ? u4.x : 0.0f, kb + 1 <= i ? u4.y : 0.0f, kb + 2 <= i ? u4.z : 0.0f, kb + 3 <= i ? u4.w : 0.0f};
+      const float v[4] = {lb <= i ? v4.x : 0.0f, lb + 1 <= i ? v4.y : 0.0f, lb + 2 <= i ? v4.z : 0.0f, lb + 3 <= i ? v4.w : 0.0f};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(u[r], v[c], acc[r][c]);
+    }
+    tile_update<1>(acc, Ub + ld + kb, ld, Vb + ld + lb, ld, i, T);
+    float part = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = kb + r, l = lb + c;
+        if (k < T && l < T && k != l) {
+          const float dt = ts[k] - ts[l];
+          const float kv = kern_val<KERNEL>(dt, ell, sig);
+          part = fmaf(acc[r][c], kern_dell<KERNEL>(dt, kv, il3, inv_sig), part);
+        }
+      }
+    total += (double)part;
+  }
+  return total;
+}
+
+__device__ __forceinline__ void load_pair(const Params& P, int p, int b, int dd, int T, long long r0, const Lay& L,
+                                          Sm& s, bool backward) {
+  const GpklDesc& d = P.d;
+  const int S = d.S, TP = L.TP;
+  for (int i = threadIdx.x; i < L.ld; i += blockDim.x) s.ts[i] = (i < T) ? P.times[(size_t)b * d.T_max + i] : 0.0f;
+  for (int i = threadIdx.x; i < TP; i += blockDim.x) {
+    s.mm[i] = (i < T) ? P.mean[(size_t)(r0 + i) * d.D + dd] : 0.0f;
+    if (backward) {
+      float gs = 0.0f;
+      for (int sx = 0; sx < S; ++sx) {
+        const float gz = (i < T && P.g_z) ? P.g_z[((size_t)S * r0 + (size_t)sx * T + i) * d.D + dd] : 0.0f;
+        s.u[(size_t)sx * TP + i] = gz;
+        gs += gz;
+      }
+      s.gzs[i] = gs;
+    }
+    for (int sx = 0; sx < S; ++sx)
+      s.v[(size_t)sx * TP + i] = (i < T) ? P.eps[((size_t)p * S + sx) * d.T_max + i] : 0.0f;
+  }
+}
+
+template <int KERNEL, int POST>
+__global__ void __launch_bounds__(256) fwd_block(Params P) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ int bad;
+  const GpklDesc& d = P.d;
+  const Lay L(d.T_max, d.S);
+  Sm s(smem_f, L);
+  const int S = d.S, TP = L.TP, ld = L.ld;
+  const float noise = d.noise, sig = (float)(1.0 - (double)noise);
+  for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
+    const int b = p / d.D, dd = p - b * d.D;
+    const int T = P.lengths[b];
+    const long long r0 = P.offsets[b];
+    __syncthreads();
+    if (T <= 0) {
+      if (threadIdx.x == 0) {
+        P.kl_pairs[p] = 0.0f;
+        if (P.logdets) { P.logdets[2 * p] = 0.0f; P.logdets[2 * p + 1] = 0.0f; }
+      }
+      continue;
+    }
+    if (threadIdx.x == 0) bad = 0;
+    load_pair(P, p, b, dd, T, r0, L, s, false);
+    __syncthreads();
+    chol_block<KERNEL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.invp, s.dgp, &bad);
+    double part = 0.0, ldp = 0.0, ldq = 0.0;
+    if (POST == GPKL_POST_GP) {
+      chol_block<KERNEL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.invq, s.dgq, &bad);
+      for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        for (int sx = 0; sx < S; ++sx) {
+          const float* ev = s.v + (size_t)sx * TP;
+          float acc = s.mm[i];
+          for (int k = 0; k <= i; ++k) acc = fmaf(s.B2[(size_t)k * ld + i], ev[k], acc);
+          P.z[((size_t)S * r0 + (size_t)sx * T + i) * d.D + dd] = acc;
+        }
+      }
+      const float ssq = solve_block<false>(s.B1, s.invp, s.B2, s.B1, L, T, s.pan);
+      part = (double)ssq;
+      for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        const double lpd = (double)s.dgp[i], lqd = (double)s.dgq[i];
+        const double av = (double)s.B1[(size_t)i * ld + TP];  // a_i = (L_p^-1 m)_i rides in the extra row
+        part += diag_term(lqd / lpd) + av * av;
+        ldp += 2.0 * log(lpd);
+        ldq += 2.0 * log(lqd);
+      }
+    } else {
+      (void)solve_block<true>(s.B1, s.invp, nullptr, s.B1, L, T, s.pan);
+      for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        float h = 0.0f;
+        for (int k = i; k < T; ++k) { const float x = s.B1[(size_t)(k + 1) * ld + i]; h = fmaf(x, x, h); }
+        const float lv = P.aux[(size_t)(r0 + i) * d.D + dd];
+        const float vv = expf(lv), sd = expf(0.5f * lv);
+        const double lpd = (double)s.dgp[i], av = (double)s.B1[(size_t)i * ld + TP];
+        part += (double)h * (double)vv - 1.0 - (double)lv + av * av + 2.0 * log(lpd);
+        ldp += 2.0 * log(lpd);
+        ldq += (double)lv;
+        for (int sx = 0; sx < S; ++sx)
+          P.z[((size_t)S * r0 + (size_t)sx * T + i) * d.D + dd] = s.mm[i] + sd * s.v[(size_t)sx * TP + i];
+      }
+    }
+    part = block_sum(part, s.red);
+    if (P.logdets) {
+      ldp = block_sum(ldp, s.red);
+      ldq = block_sum(ldq, s.red);
+    }
+    if (threadIdx.x == 0) {
+      P.kl_pairs[p] = (float)(0.5 * part);
+      if (P.logdets) { P.logdets[2 * p] = (float)ldp; P.logdets[2 * p + 1] = (float)ldq; }
+      if (bad && P.status) atomicAdd(P.status, 1);
+    }
+  }
+}
+
+template <int KERNEL, int POST>
+__global__ void __launch_bounds__(256) bwd_block(Params P) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ int bad;
+  const GpklDesc& d = P.d;
+  const Lay L(d.T_max, d.S);
+  Sm s(smem_f, L);
+  const int S = d.S, TP = L.TP, ld = L.ld;
+  const float noise = d.noise, sig = (float)(1.0 - (double)noise);
+  const double g_sum = P.g_kl_sum ? *P.g_kl_sum : 1.0;
+  for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
+    const int b = p / d.D, dd = p - b * d.D;
+    const int T = P.lengths[b];
+    const long long r0 = P.offsets[b];
+    __syncthreads();
+    if (T <= 0) {
+      if (threadIdx.x == 0 && P.gq_pairs) P.gq_pairs[p] = 0.0f;
+      continue;
+    }
+    const float g = (float)(g_sum + (P.g_kl_pairs ? (double)P.g_kl_pairs[p] : 0.0));
+    if (threadIdx.x == 0) bad = 0;
+    load_pair(P, p, b, dd, T, r0, L, s, true);
+    __syncthreads();
+    const float lp = P.ell_p[dd];
+    chol_block<KERNEL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.invp, s.dgp, &bad);
+    (void)solve_block<true>(s.B1, s.invp, nullptr, s.B1, L, T, s.pan);  // XR1 = X_p = L_p^-1
+    // alpha = X_p^T a ; g_mean = g alpha + sum_s g_z
+    for (int k = threadIdx.x; k < T; k += blockDim.x) {
+      float al = 0.0f;
+      for (int i = k; i < T; ++i) al = fmaf(s.B1[(size_t)(i + 1) * ld + k], s.B1[(size_t)i * ld + TP], al);
+      P.g_mean[(size_t)(r0 + k) * d.D + dd] = g * al + s.gzs[k];
+    }
+    if (POST == GPKL_POST_DIAG) {
+      for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        float h = 0.0f;
+        for (int k = i; k < T; ++k) { const float x = s.B1[(size_t)(k + 1) * ld + i]; h = fmaf(x, x, h); }
+        const float lv = P.aux[(size_t)(r0 + i) * d.D + dd];
+        const float vv = expf(lv), sd = expf(0.5f * lv);
+        float ge = 0.0f;
+        for (int sx = 0; sx < S; ++sx) ge = fmaf(s.u[(size_t)sx * TP + i], s.v[(size_t)sx * TP + i], ge);
+        P.g_aux[(size_t)(r0 + i) * d.D + dd] = 0.5f * g * (h * vv - 1.0f) + 0.5f * sd * ge;
+      }
+    } else {
+      const float lq = P.ell_q[dd];
+      const double t1 = contract_block<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig);
+      chol_block<KERNEL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, s.pan, s.invq, s.dgq, &bad);
+      // w_s = L_q^T g_z,s ; pd = 1/2 sum_s w_s eps_s - g/2
+      for (int k = threadIdx.x; k < T; k += blockDim.x) {
+        float pdk = 0.0f;
+        for (int sx = 0; sx < S; ++sx) {
+          const float* uu = s.u + (size_t)sx * TP;
+          float wk = 0.0f;
+          for (int i = k; i < T; ++i) wk = fmaf(s.B2[(size_t)k * ld + i], uu[i], wk);
+          s.w[(size_t)sx * TP + k] = wk;
+          pdk = fmaf(wk, s.v[(size_t)sx * TP + k], pdk);
+        }
+        s.pd[k] = 0.5f * pdk - 0.5f * g;
+      }
+      (void)solve_block<true>(s.B2, s.invq, nullptr, s.B2, L, T, s.pan);  // XR2 = X_q  (ends with a barrier)
+      // C' = (Phi(sum_s w_s eps_s^T) - g/2 I) X_q by running prefix sums down each column, into XR1
+      for (int l = threadIdx.x; l < T; l += blockDim.x) {
+        for (int i = l; i < T; ++i) s.B1[(size_t)(i + 1) * ld + l] = s.pd[i] * s.B2[(size_t)(i + 1) * ld + l];
+        for (int sx = 0; sx < S; ++sx) {
+          const float* ww = s.w + (size_t)sx * TP;
+          const float* vv = s.v + (size_t)sx * TP;
+          float cum = 0.0f;
+          for (int i = l; i < T; ++i) {
+            s.B1[(size_t)(i + 1) * ld + l] = fmaf(ww[i], cum, s.B1[(size_t)(i + 1) * ld + l]);
+            cum = fmaf(vv[i], s.B2[(size_t)(i + 1) * ld + l], cum);
+          }
+        }
+      }
+      __syncthreads();
+      const double t2 = contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig);
+      const double gq = block_sum(0.5 * (double)g * t1 + t2, s.red);
+      if (threadIdx.x == 0) P.gq_pairs[p] = (float)gq;
+    }
+    if (threadIdx.x == 0 && bad && P.status) atomicAdd(P.status, 1);
+  }
+}
+
+template <int KERNEL, int POST>
+cudaError_t launch_kp(const Params& P, bool backward, cudaStream_t st) {
+  const Lay L(P.d.T_max, P.d.S);
+  const size_t smem = L.floats() * sizeof(float);
+  if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
+  const int npairs = P.d.B * P.d.D;
+  const int nt = P.d.T_max <= 64 ? 64 : (P.d.T_max <= 112 ? 128 : 256);
+  int per_sm = (int)(kMaxDynSmem / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2048 / nt) per_sm = 2048 / nt;
+  const int cap = kNumSMs * per_sm * 4;
+  const int grid = npairs < cap ? npairs : cap;
+  cudaError_t e;
+  if (!backward) {
+    auto kern = fwd_block<KERNEL, POST>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    prof_begin(false, st);
+    kern<<<grid, nt, smem, st>>>(P);
+    prof_end(false, st);
+  } else {
+    auto kern = bwd_block<KERNEL, POST>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    prof_begin(true, st);
+    kern<<<grid, nt, smem, st>>>(P);
+    prof_end(true, st);
+  }
+  note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool block_tier_supports(const GpklDesc& d, bool backward) {
+  if (d.T_max < 1) return false;
+  if (backward && (d.flags & GPKL_FLAG_GRAD_ELL_P)) return false;  // d/d ell_p is served by the generic tier
+  if (d.posterior != GPKL_POST_GP && d.posterior != GPKL_POST_DIAG) return false;
+  const Lay L(d.T_max, d.S);
+  return L.floats() * sizeof(float) <= kMaxDynSmem;
+}
+
+cudaError_t launch_block(const Params& P, bool backward, cudaStream_t st) {
+  const bool rbf = P.d.kernel == GPKL_KERNEL_RBF;
+  const bool gp = P.d.posterior == GPKL_POST_GP;
+  if (rbf && gp) return launch_kp<GPKL_KERNEL_RBF, GPKL_POST_GP>(P, backward, st);
+  if (rbf && !gp) return launch_kp<GPKL_KERNEL_RBF, GPKL_POST_DIAG>(P, backward, st);
+  if (!rbf && gp) return launch_kp<GPKL_KERNEL_CAUCHY, GPKL_POST_GP>(P, backward, st);
+  return launch_kp<GPKL_KERNEL_CAUCHY, GPKL_POST_DIAG>(P, backward, st);
+}
+
+}  // namespace gpkl

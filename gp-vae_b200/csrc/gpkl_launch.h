@@ -26,4 +26,8 @@ cudaError_t launch_generic(const Params& P, bool backward, cudaStream_t st);
 bool warp_tier_supports(const GpklDesc& d, bool backward);
 cudaError_t launch_warp(const Params& P, bool backward, cudaStream_t st);
 
+// block tier (gpkl_block.cu): one CTA per pair, shared-memory resident, loop-based; T <= ~144
+bool block_tier_supports(const GpklDesc& d, bool backward);
+cudaError_t launch_block(const Params& P, bool backward, cudaStream_t st);
+
 }  // namespace gpkl

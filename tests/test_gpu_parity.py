@@ -10,7 +10,7 @@ from gpu_util import TOL_GRAD, TOL_KL, TOL_Z, assert_parity, compare, reference_
 
 pytestmark = pytest.mark.gpu
 
-TIERS = ["generic", "warp"]   # "warp": register-resident tier (T <= 64, no d/d ell_p); "auto" is used elsewhere
+TIERS = ["generic", "warp", "block"]   # warp: registers, T <= 64; block: shared memory, T <= 144; neither does d/d ell_p
 
 
 def _tier_cfg(tier, T):
@@ -19,6 +19,10 @@ def _tier_cfg(tier, T):
         if T > 64:
             pytest.skip("warp tier covers T <= 64")
         return dict(tier="warp", grad_ell_p=False)
+    if tier == "block":
+        if T > 144:
+            pytest.skip("block tier covers T <= 144")
+        return dict(tier="block", grad_ell_p=False)
     return dict(tier=tier, grad_ell_p=True)
 
 
@@ -27,7 +31,7 @@ def _tier_cfg(tier, T):
 def test_golden_v1(cuda_device, name, tier):
     """Fixtures = outputs of Full_GP_VAE_dynamic_time / Full_GP_VAE_fixed_for_MovMnist run verbatim."""
     g = load_golden(name)
-    want_lp = tier != "warp"
+    want_lp = tier == "generic"
     if not want_lp:
         g.pop("g_ell_p", None)
     fwd, bwd = run_cuda(g, cuda_device, S=g["S"], noise=g["noise"], tier=tier, grad_ell_p=want_lp)
@@ -78,6 +82,7 @@ GRID = [
     (2, 2, 65, 1, False),
     (1, 3, 100, 2, True),
     (1, 2, 128, 1, False),
+    (2, 2, 144, 1, True),
     (1, 2, 160, 1, False),
 ]
 
