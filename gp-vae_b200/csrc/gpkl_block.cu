@@ -60,21 +60,21 @@ struct Lay {  // shared-memory carve-up (floats), identical on host and device
   }
   __host__ __device__ size_t buf() const { return (size_t)(TP + 1) * ld; }
   __host__ __device__ size_t floats() const {
-    return 64 + 2 * buf() + (size_t)NB * ld + 2 * (size_t)nP * 256 + ld + 7 * (size_t)TP + 3 * (size_t)S * TP;
+    return 64 + 2 * buf() + (size_t)NB * ld + ld + 9 * (size_t)TP + 3 * (size_t)S * TP;
   }
 };
 
 struct Sm {
   double* red;
-  float *B1, *B2, *pan, *invp, *invq, *ts, *dgp, *dgq, *aa, *al, *pd, *gzs, *mm, *u, *v, *w;
+  float *B1, *B2, *pan, *rdp, *rdq, *ts, *dgp, *dgq, *aa, *al, *pd, *gzs, *mm, *u, *v, *w;
   __device__ Sm(float* base, const Lay& L) {
     red = reinterpret_cast<double*>(base); base += 64;
     B1 = base; base += L.buf();
     B2 = base; base += L.buf();
     pan = base; base += (size_t)NB * L.ld;
-    invp = base; base += (size_t)L.nP * 256;
-    invq = base; base += (size_t)L.nP * 256;
     ts = base; base += L.ld;
+    rdp = base; base += L.TP;
+    rdq = base; base += L.TP;
     dgp = base; base += L.TP;
     dgq = base; base += L.TP;
     aa = base; base += L.TP;
@@ -91,9 +91,9 @@ struct Sm {
 // Entry (i,k) of the (optionally row-augmented) kernel matrix, identity on the padding.
 template <int KERNEL>
 __device__ __forceinline__ float k_entry(int i, int k, int T, int TP, bool extra, const float* __restrict__ ts,
-                                         const float* __restrict__ mm, float ell, float sig, float noise) {
+                                         const float* __restrict__ mm, const KernC<KERNEL>& kc, float noise) {
   if (i < T && k < T) {
-    float v = kern_val<KERNEL>(ts[i] - ts[k], ell, sig);
+    float v = kc.val(ts[i] - ts[k]);
     if (i == k) v += noise;
     return v;
   }
@@ -102,50 +102,57 @@ __device__ __forceinline__ float k_entry(int i, int k, int T, int TP, bool extra
   return 0.0f;
 }
 
-// One warp: factor the 16x16 diagonal block held in pan (columns 0..15, rows j0..j0+15), write L_dd into
-// the LC triangle of Bm, its inverse (k-major: inv[c'*16 + i] = Linv[i][c']) and the diagonal into dg.
+// One warp: factor the 16x16 diagonal block held in pan (columns 0..15, rows j0..j0+15) in registers with
+// shuffles; writes L_dd into the LC triangle of Bm, diag(L) into dg and 1/diag(L) into rdg.
 __device__ __forceinline__ void diag_factor(float* __restrict__ Bm, int ld, int j0, int T, const float* __restrict__ pan,
-                                            float* __restrict__ inv, float* __restrict__ dg, int* bad) {
+                                            float* __restrict__ dg, float* __restrict__ rdg, int* bad) {
   const int lane = threadIdx.x & 31, l = lane & 15;
   float a[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) a[c] = (c <= l) ? pan[c * ld + j0 + l] : 0.0f;
-  float dgv = 1.0f;
+  float dgv = 1.0f, rdv = 1.0f;
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
     const float d = __shfl_sync(0xffffffffu, a[c], c, 16);
-    const float sd = sqrtf(d);
-    const float rs = 1.0f / sd;
+    float rs = rsqrtf(d);
+    rs = rs * fmaf(-0.5f * d, rs * rs, 1.5f);  // one Newton step: 1/sqrt(d) to ~1 ulp
+    const float sd = d * rs;
     if (j0 + c < T && !(d > 0.0f)) *bad = 1;
     const float lc = (l > c) ? a[c] * rs : ((l == c) ? sd : 0.0f);
     a[c] = lc;
-    if (l == c) dgv = sd;
+    if (l == c) { dgv = sd; rdv = rs; }
 #pragma unroll
     for (int k = c + 1; k < 16; ++k) {
       const float lk = __shfl_sync(0xffffffffu, lc, k, 16);
       a[k] = fmaf(-lc, lk, a[k]);
     }
   }
-  float x[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float s = (i == l) ? 1.0f : 0.0f;
-#pragma unroll
-    for (int k = 0; k < i; ++k) {
-      const float lik = __shfl_sync(0xffffffffu, a[k], i, 16);
-      s = fmaf(-lik, x[k], s);
-    }
-    const float lii = __shfl_sync(0xffffffffu, a[i], i, 16);
-    x[i] = s / lii;
-  }
   if (lane < 16) {
 #pragma unroll
     for (int c = 0; c < 16; ++c)
       if (c <= l) Bm[(size_t)(j0 + c) * ld + j0 + l] = a[c];
     dg[j0 + l] = dgv;
+    rdg[j0 + l] = rdv;
+  }
+}
+
+// x <- L_dd^-1 b for one 16-vector held in registers (right-looking substitution); L_dd is the 16x16
+// diagonal block at (d0,d0) of the LC triangle of Lb, read as 128-bit broadcasts; rdg = 1/diag(L).
+__device__ __forceinline__ void diag_solve16(float (&b)[16], const float* __restrict__ Lb, int ld, int d0,
+                                             const float* __restrict__ rdg) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      *reinterpret_cast<float4*>(inv + l * 16 + 4 * g) = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+  for (int c = 0; c < 16; ++c) {
+    const float xc = b[c] * rdg[d0 + c];
+    b[c] = xc;
+    const float* col = Lb + (size_t)(d0 + c) * ld + d0;  // L[d0.., d0+c]
+#pragma unroll
+    for (int g = (c + 1) / 4; g < 4; ++g) {
+      const float4 l4 = *reinterpret_cast<const float4*>(col + 4 * g);
+      const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (4 * g + e > c) b[4 * g + e] = fmaf(-xc, lv[e], b[4 * g + e]);
+    }
   }
 }
 
@@ -154,10 +161,11 @@ __device__ __forceinline__ void diag_factor(float* __restrict__ Bm, int ld, int 
 template <int KERNEL>
 __device__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool extra, const float* __restrict__ ts,
                            const float* __restrict__ mm, float ell, float sig, float noise, float* __restrict__ pan,
-                           float* __restrict__ inv, float* __restrict__ dg, int* bad) {
+                           float* __restrict__ dg, float* __restrict__ rdg, int* bad) {
   const int tid = threadIdx.x, NT = blockDim.x;
   const int cg = tid & 3, rg = tid >> 2, NRG = NT >> 2;
   const int ld = L.ld, TP = L.TP;
+  const KernC<KERNEL> kc(ell, sig);
   // rows beyond the last real row are identity padding and decouple: only panels that contain real rows matter
   const int Tact = (T + NB - 1) / NB * NB;
   const int rows_end = extra ? TP + 4 : Tact;
@@ -166,43 +174,56 @@ __device__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool ext
     for (int rb = j0 + 4 * rg; rb < rows_end; rb += 4 * NRG) {
       if (rb >= Tact && rb < TP) continue;  // identity padding rows
       float acc[4][4];
+      if (rb + 3 < T && cb + 3 < T) {  // all-real tile: no padding logic
+        const float4 tr4 = *reinterpret_cast<const float4*>(ts + rb);
+        const float4 tc4 = *reinterpret_cast<const float4*>(ts + cb);
+        const float tr[4] = {tr4.x, tr4.y, tr4.z, tr4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = k_entry<KERNEL>(rb + r, cb + c, T, TP, extra, ts, mm, ell, sig, noise);
+          for (int c = 0; c < 4; ++c) acc[r][c] = kc.val(tr[r] - tc[c]);
+        if (rb == cb) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[r][r] += noise;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = k_entry<KERNEL>(rb + r, cb + c, T, TP, extra, ts, mm, kc, noise);
+      }
       tile_update<-1>(acc, Bm + rb, ld, Bm + cb, ld, 0, j0);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         *reinterpret_cast<float4*>(pan + (size_t)(4 * cg + c) * ld + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
     }
     __syncthreads();
-    if (tid < 32) diag_factor(Bm, ld, j0, T, pan, inv + (size_t)(j0 / NB) * 256, dg, bad);
+    if (tid < 32) diag_factor(Bm, ld, j0, T, pan, dg, rdg, bad);
     __syncthreads();
-    const float* invJ = inv + (size_t)(j0 / NB) * 256;
-    for (int rb = j0 + NB + 4 * rg; rb < rows_end; rb += 4 * NRG) {
-      if (rb >= Tact && rb < TP) continue;
-      float acc[4][4];
+    // rows below the diagonal block: L[i, j0:j0+16] = pan[i, :] L_dd^-T, one row per thread
+    const int nbelow = Tact - j0 - NB;
+    const int nrows = nbelow + (extra ? 1 : 0);
+    for (int t = tid; t < nrows; t += NT) {
+      const int i = t < nbelow ? j0 + NB + t : TP;
+      float b[16];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 16; ++c) b[c] = pan[(size_t)c * ld + i];
+      diag_solve16(b, Bm, ld, j0, rdg);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
-      tile_update<1>(acc, pan + rb, ld, invJ + 4 * cg, 16, 0, 16);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<float4*>(Bm + (size_t)(cb + c) * ld + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+      for (int c = 0; c < 16; ++c) Bm[(size_t)(j0 + c) * ld + i] = b[c];
     }
     __syncthreads();
   }
-  // identity padding: diag entries for rows in [T, TP) (only dg is consulted for them)
-  for (int i = Tact + tid; i < TP; i += NT) dg[i] = 1.0f;
+  // identity padding: diag entries for rows in [Tact, TP) (only dg / rdg are consulted for them)
+  for (int i = Tact + tid; i < TP; i += NT) { dg[i] = 1.0f; rdg[i] = 1.0f; }
   __syncthreads();
 }
 
 // X = L^-1 B by 16-row blocks into the XR triangle of Xb.  L: LC triangle of Lb with inverse diagonal
-// blocks invL.  IDENT: B = I, else B = LC triangle of Bb.  Returns this thread's partial sum of squares
+// reciprocals rdgL.  IDENT: B = I, else B = LC triangle of Bb.  Returns this thread's partial sum of squares
 // of the strictly-lower entries of X (rows/cols < T).
 template <bool IDENT>
-__device__ float solve_block(const float* __restrict__ Lb, const float* __restrict__ invL, const float* __restrict__ Bb,
+__device__ float solve_block(const float* __restrict__ Lb, const float* __restrict__ rdgL, const float* __restrict__ Bb,
                              float* __restrict__ Xb, const Lay& L, int T, float* __restrict__ pan) {
   const int tid = threadIdx.x, NT = blockDim.x;
   const int ld = L.ld;
@@ -214,7 +235,7 @@ __device__ float solve_block(const float* __restrict__ Lb, const float* __restri
       const int rt = id & 3, ct = id >> 2;
       const int rb = i0 + 4 * rt, cb = 4 * ct;
       // (tiles entirely above the diagonal are staged too -- as zeros -- because the diagonal-block
-      //  multiply below reads every staged row of its column range)
+      //  solve below reads every staged row of its column)
       float acc[4][4];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
@@ -243,34 +264,19 @@ __device__ float solve_block(const float* __restrict__ Lb, const float* __restri
         *reinterpret_cast<float4*>(pan + (size_t)(4 * rt + r) * ld + cb) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
     }
     __syncthreads();
-    const float* invI = invL + (size_t)(i0 / NB) * 256;
-    for (int id = tid; id < ntile; id += NT) {
-      const int rt = id & 3, ct = id >> 2;
-      const int rb = i0 + 4 * rt, cb = 4 * ct;
-      if (cb > rb + 3) continue;
-      float x[4][4];
+    // diagonal block: X[i0:i0+16, col] = L_dd^-1 staged[:, col], one column per thread
+    for (int col = tid; col < i0 + NB; col += NT) {
+      float b[16];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < 16; ++r) b[r] = pan[(size_t)r * ld + col];
+      diag_solve16(b, Lb, ld, i0, rdgL);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) x[r][c] = 0.0f;
-      tile_update<1>(x, invI + 4 * rt, 16, pan + cb, ld, 0, 16);
-      if (cb + 3 <= rb) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          *reinterpret_cast<float4*>(Xb + (size_t)(rb + r + 1) * ld + cb) = make_float4(x[r][0], x[r][1], x[r][2], x[r][3]);
-          if (rb + r < T) ssq = fmaf(x[r][0], x[r][0], fmaf(x[r][1], x[r][1], fmaf(x[r][2], x[r][2], fmaf(x[r][3], x[r][3], ssq))));
+      for (int r = 0; r < 16; ++r) {
+        const int row = i0 + r;
+        if (col <= row) {
+          Xb[(size_t)(row + 1) * ld + col] = b[r];
+          if (col < row && row < T) ssq = fmaf(b[r], b[r], ssq);
         }
-      } else {
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int row = rb + r, col = cb + c;
-            if (col <= row) {
-              Xb[(size_t)(row + 1) * ld + col] = x[r][c];
-              if (col < row && row < T) ssq = fmaf(x[r][c], x[r][c], ssq);
-            }
-          }
       }
     }
     __syncthreads();
@@ -285,7 +291,7 @@ __device__ double contract_block(const float* __restrict__ Ub, const float* __re
   const int tid = threadIdx.x, NT = blockDim.x;
   const int ld = L.ld;
   const int nk = (T + 3) / 4;
-  const float inv_sig = 1.0f / sig, il3 = 1.0f / (ell * ell * ell);
+  const KernC<KERNEL> kc(ell, sig);
   double total = 0.0;
   for (int id = tid; id < nk * nk; id += NT) {
     const int kt = id % nk, lt = id / nk;
@@ -316,8 +322,7 @@ __device__ double contract_block(const float* __restrict__ Ub, const float* __re
         const int k = kb + r, l = lb + c;
         if (k < T && l < T && k != l) {
           const float dt = ts[k] - ts[l];
-          const float kv = kern_val<KERNEL>(dt, ell, sig);
-          part = fmaf(acc[r][c], kern_dell<KERNEL>(dt, kv, il3, inv_sig), part);
+          part = fmaf(acc[r][c], kc.dell(dt, kc.val(dt)), part);
         }
       }
     total += (double)part;
@@ -347,7 +352,7 @@ __device__ __forceinline__ void load_pair(const Params& P, int p, int b, int dd,
 }
 
 template <int KERNEL, int POST>
-__global__ void __launch_bounds__(256) fwd_block(Params P) {
+__global__ void __launch_bounds__(128, 4) fwd_block(Params P) {
   extern __shared__ __align__(16) float smem_f[];
   __shared__ int bad;
   const GpklDesc& d = P.d;
@@ -370,10 +375,10 @@ __global__ void __launch_bounds__(256) fwd_block(Params P) {
     if (threadIdx.x == 0) bad = 0;
     load_pair(P, p, b, dd, T, r0, L, s, false);
     __syncthreads();
-    chol_block<KERNEL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.invp, s.dgp, &bad);
+    chol_block<KERNEL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.dgp, s.rdp, &bad);
     double part = 0.0, ldp = 0.0, ldq = 0.0;
     if (POST == GPKL_POST_GP) {
-      chol_block<KERNEL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.invq, s.dgq, &bad);
+      chol_block<KERNEL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.dgq, s.rdq, &bad);
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
         for (int sx = 0; sx < S; ++sx) {
           const float* ev = s.v + (size_t)sx * TP;
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(256) fwd_block(Params P) {
           P.z[((size_t)S * r0 + (size_t)sx * T + i) * d.D + dd] = acc;
         }
       }
-      const float ssq = solve_block<false>(s.B1, s.invp, s.B2, s.B1, L, T, s.pan);
+      const float ssq = solve_block<false>(s.B1, s.rdp, s.B2, s.B1, L, T, s.pan);
       part = (double)ssq;
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
         const double lpd = (double)s.dgp[i], lqd = (double)s.dgq[i];
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(256) fwd_block(Params P) {
         ldq += 2.0 * log(lqd);
       }
     } else {
-      (void)solve_block<true>(s.B1, s.invp, nullptr, s.B1, L, T, s.pan);
+      (void)solve_block<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan);
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
         float h = 0.0f;
         for (int k = i; k < T; ++k) { const float x = s.B1[(size_t)(k + 1) * ld + i]; h = fmaf(x, x, h); }
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(256) fwd_block(Params P) {
 }
 
 template <int KERNEL, int POST>
-__global__ void __launch_bounds__(256) bwd_block(Params P) {
+__global__ void __launch_bounds__(128, 4) bwd_block(Params P) {
   extern __shared__ __align__(16) float smem_f[];
   __shared__ int bad;
   const GpklDesc& d = P.d;
@@ -443,8 +448,8 @@ __global__ void __launch_bounds__(256) bwd_block(Params P) {
     load_pair(P, p, b, dd, T, r0, L, s, true);
     __syncthreads();
     const float lp = P.ell_p[dd];
-    chol_block<KERNEL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.invp, s.dgp, &bad);
-    (void)solve_block<true>(s.B1, s.invp, nullptr, s.B1, L, T, s.pan);  // XR1 = X_p = L_p^-1
+    chol_block<KERNEL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad);
+    (void)solve_block<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan);  // XR1 = X_p = L_p^-1
     // alpha = X_p^T a ; g_mean = g alpha + sum_s g_z
     for (int k = threadIdx.x; k < T; k += blockDim.x) {
       float al = 0.0f;
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(256) bwd_block(Params P) {
     } else {
       const float lq = P.ell_q[dd];
       const double t1 = contract_block<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig);
-      chol_block<KERNEL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, s.pan, s.invq, s.dgq, &bad);
+      chol_block<KERNEL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, s.pan, s.dgq, s.rdq, &bad);
       // w_s = L_q^T g_z,s ; pd = 1/2 sum_s w_s eps_s - g/2
       for (int k = threadIdx.x; k < T; k += blockDim.x) {
         float pdk = 0.0f;
@@ -477,7 +482,7 @@ __global__ void __launch_bounds__(256) bwd_block(Params P) {
         }
         s.pd[k] = 0.5f * pdk - 0.5f * g;
       }
-      (void)solve_block<true>(s.B2, s.invq, nullptr, s.B2, L, T, s.pan);  // XR2 = X_q  (ends with a barrier)
+      (void)solve_block<true>(s.B2, s.rdq, nullptr, s.B2, L, T, s.pan);  // XR2 = X_q  (ends with a barrier)
       // C' = (Phi(sum_s w_s eps_s^T) - g/2 I) X_q by running prefix sums down each column, into XR1
       for (int l = threadIdx.x; l < T; l += blockDim.x) {
         for (int i = l; i < T; ++i) s.B1[(size_t)(i + 1) * ld + l] = s.pd[i] * s.B2[(size_t)(i + 1) * ld + l];
@@ -506,7 +511,7 @@ cudaError_t launch_kp(const Params& P, bool backward, cudaStream_t st) {
   const size_t smem = L.floats() * sizeof(float);
   if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
   const int npairs = P.d.B * P.d.D;
-  const int nt = P.d.T_max <= 64 ? 64 : (P.d.T_max <= 112 ? 128 : 256);
+  const int nt = P.d.T_max <= 64 ? 64 : 128;
   int per_sm = (int)(kMaxDynSmem / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 2048 / nt) per_sm = 2048 / nt;
