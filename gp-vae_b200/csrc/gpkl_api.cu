@@ -10,6 +10,7 @@
 namespace gpkl {
 
 // ---- measurement hooks ---------------------------------------------------------------------------
+long long* g_dbg = nullptr;  // device buffer for the phase trace (internal; set by gpkl_debug_set_trace)
 namespace {
 constexpr int kProfRing = 1024;
 struct ProfState {
@@ -129,9 +130,13 @@ Workspace plan(const GpklDesc& d, void* base) {
   off += align_up(P * sizeof(float));
   w.gp_pairs = reinterpret_cast<float*>(b + off);
   off += align_up(P * sizeof(float));
+  // per-CTA matrix slots for sizes whose work matrices do not fit shared memory; sized for whichever
+  // tier (block: kBlockSlots CTAs, generic: 148 CTAs) may serve this descriptor
   w.scratch = reinterpret_cast<float*>(b + off);
-  w.scratch_stride = generic_slot_floats(d.T_max);
-  off += align_up((size_t)generic_slots(d) * w.scratch_stride * sizeof(float));
+  const size_t gs = generic_slots(d) ? generic_slot_floats(d.T_max) : 0, bs = block_slot_floats(d);
+  w.scratch_stride = gs > bs ? gs : bs;
+  const size_t nslots = w.scratch_stride ? (size_t)(kBlockSlots > generic_slots(d) ? kBlockSlots : generic_slots(d)) : 0;
+  off += align_up(nslots * w.scratch_stride * sizeof(float));
   w.total = off;
   return w;
 }
@@ -150,9 +155,9 @@ int check_desc(const GpklDesc* d) {
 }
 
 int dispatch(const Params& P, bool backward, cudaStream_t st) {
-  // tier selection (GPKL_TIER_AUTO): register-resident warp tier for T <= 32, shared-memory block tier up to
-  // T ~ 144, generic tier otherwise and for the combinations the specialised tiers do not implement
-  // (d/d ell_p).  Explicit requests are honoured or refused, never silently rerouted.
+  // tier selection (GPKL_TIER_AUTO): register-resident warp tier for T <= 32, block tier above (matrices in
+  // shared memory up to T ~ 144, in an L2-backed workspace slot beyond), generic tier for the combinations
+  // the specialised tiers do not implement (d/d ell_p).  Explicit requests are honoured or refused, never silently rerouted.
   cudaError_t e;
   if (P.d.tier == GPKL_TIER_WARP) {
     if (!warp_tier_supports(P.d, backward)) return GPKL_ERR_UNSUPPORTED;
@@ -226,8 +231,9 @@ extern "C" int gpkl_forward(const GpklDesc* desc, const float* mean, const float
   P.mean = mean; P.times = times; P.lengths = lengths; P.ell_q = ell_q; P.ell_p = ell_p; P.aux = aux; P.eps = eps;
   P.z = z; P.kl_pairs = kl_pairs; P.logdets = logdets; P.status = status;
   P.offsets = w.offsets;
-  P.scratch = generic_slots(d) ? w.scratch : nullptr;
+  P.scratch = w.scratch_stride ? w.scratch : nullptr;
   P.scratch_stride = w.scratch_stride;
+  P.dbg = g_dbg;
   rc = dispatch(P, false, st);
   if (rc != GPKL_OK) return rc;
   sum_pairs_kernel<<<1, 1024, 0, st>>>(kl_pairs, d.B * d.D, kl_sum);
@@ -273,8 +279,9 @@ extern "C" int gpkl_backward(const GpklDesc* desc, const float* mean, const floa
   P.g_z = g_z; P.g_kl_sum = g_kl_sum; P.g_kl_pairs = g_kl_pairs;
   P.g_mean = g_mean; P.g_aux = g_aux; P.gq_pairs = w.gq_pairs; P.gp_pairs = w.gp_pairs; P.status = status;
   P.offsets = w.offsets;
-  P.scratch = generic_slots(d) ? w.scratch : nullptr;
+  P.scratch = w.scratch_stride ? w.scratch : nullptr;
   P.scratch_stride = w.scratch_stride;
+  P.dbg = g_dbg;
   rc = dispatch(P, true, st);
   if (rc != GPKL_OK) return rc;
   const int wpb = 8;
@@ -290,6 +297,9 @@ extern "C" int gpkl_backward(const GpklDesc* desc, const float* mean, const floa
   }
   return cudaGetLastError() == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
 }
+
+// internal, not declared in include/gpkl.h: device buffer (>= 64 int64) receiving CTA 0's phase clocks
+extern "C" void gpkl_debug_set_trace(void* dev_buf) { g_dbg = static_cast<long long*>(dev_buf); }
 
 extern "C" int64_t gpkl_launch_count(void) { return g_launches; }
 

@@ -59,18 +59,24 @@ struct Lay {  // shared-memory carve-up (floats), identical on host and device
     nP = TP / NB;
   }
   __host__ __device__ size_t buf() const { return (size_t)(TP + 1) * ld; }
-  __host__ __device__ size_t floats() const {
-    return 64 + 2 * buf() + (size_t)NB * ld + ld + 9 * (size_t)TP + 3 * (size_t)S * TP;
+  // shared floats; resident = the two work matrices live in shared memory (else in a workspace slot)
+  __host__ __device__ size_t floats(bool resident) const {
+    return 64 + (resident ? 2 * buf() : 0) + (size_t)NB * ld + ld + 9 * (size_t)TP + 3 * (size_t)S * TP;
   }
 };
 
 struct Sm {
   double* red;
   float *B1, *B2, *pan, *rdp, *rdq, *ts, *dgp, *dgq, *aa, *al, *pd, *gzs, *mm, *u, *v, *w;
-  __device__ Sm(float* base, const Lay& L) {
+  __device__ Sm(float* base, const Lay& L, float* slot) {
     red = reinterpret_cast<double*>(base); base += 64;
-    B1 = base; base += L.buf();
-    B2 = base; base += L.buf();
+    if (slot) {  // large T: matrices in this CTA's workspace slot (global memory, L1/L2 cached)
+      B1 = slot;
+      B2 = slot + L.buf();
+    } else {
+      B1 = base; base += L.buf();
+      B2 = base; base += L.buf();
+    }
     pan = base; base += (size_t)NB * L.ld;
     ts = base; base += L.ld;
     rdp = base; base += L.TP;
@@ -352,12 +358,12 @@ __device__ __forceinline__ void load_pair(const Params& P, int p, int b, int dd,
 }
 
 template <int KERNEL, int POST>
-__global__ void __launch_bounds__(128, 4) fwd_block(Params P) {
+__global__ void __launch_bounds__(256, 2) fwd_block(Params P, int use_slot) {
   extern __shared__ __align__(16) float smem_f[];
   __shared__ int bad;
   const GpklDesc& d = P.d;
   const Lay L(d.T_max, d.S);
-  Sm s(smem_f, L);
+  Sm s(smem_f, L, use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr);
   const int S = d.S, TP = L.TP, ld = L.ld;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
   for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
@@ -373,12 +379,16 @@ __global__ void __launch_bounds__(128, 4) fwd_block(Params P) {
       continue;
     }
     if (threadIdx.x == 0) bad = 0;
+    phase_mark(P, 0);
     load_pair(P, p, b, dd, T, r0, L, s, false);
     __syncthreads();
+    phase_mark(P, 1);
     chol_block<KERNEL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.dgp, s.rdp, &bad);
+    phase_mark(P, 2);
     double part = 0.0, ldp = 0.0, ldq = 0.0;
     if (POST == GPKL_POST_GP) {
       chol_block<KERNEL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.dgq, s.rdq, &bad);
+      phase_mark(P, 3);
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
         for (int sx = 0; sx < S; ++sx) {
           const float* ev = s.v + (size_t)sx * TP;
@@ -387,7 +397,9 @@ __global__ void __launch_bounds__(128, 4) fwd_block(Params P) {
           P.z[((size_t)S * r0 + (size_t)sx * T + i) * d.D + dd] = acc;
         }
       }
+      phase_mark(P, 4);
       const float ssq = solve_block<false>(s.B1, s.rdp, s.B2, s.B1, L, T, s.pan);
+      phase_mark(P, 5);
       part = (double)ssq;
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
         const double lpd = (double)s.dgp[i], lqd = (double)s.dgq[i];
@@ -416,6 +428,7 @@ __global__ void __launch_bounds__(128, 4) fwd_block(Params P) {
       ldp = block_sum(ldp, s.red);
       ldq = block_sum(ldq, s.red);
     }
+    phase_mark(P, 6);
     if (threadIdx.x == 0) {
       P.kl_pairs[p] = (float)(0.5 * part);
       if (P.logdets) { P.logdets[2 * p] = (float)ldp; P.logdets[2 * p + 1] = (float)ldq; }
@@ -425,12 +438,12 @@ __global__ void __launch_bounds__(128, 4) fwd_block(Params P) {
 }
 
 template <int KERNEL, int POST>
-__global__ void __launch_bounds__(128, 4) bwd_block(Params P) {
+__global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
   extern __shared__ __align__(16) float smem_f[];
   __shared__ int bad;
   const GpklDesc& d = P.d;
   const Lay L(d.T_max, d.S);
-  Sm s(smem_f, L);
+  Sm s(smem_f, L, use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr);
   const int S = d.S, TP = L.TP, ld = L.ld;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
   const double g_sum = P.g_kl_sum ? *P.g_kl_sum : 1.0;
@@ -445,11 +458,15 @@ __global__ void __launch_bounds__(128, 4) bwd_block(Params P) {
     }
     const float g = (float)(g_sum + (P.g_kl_pairs ? (double)P.g_kl_pairs[p] : 0.0));
     if (threadIdx.x == 0) bad = 0;
+    phase_mark(P, 16);
     load_pair(P, p, b, dd, T, r0, L, s, true);
     __syncthreads();
+    phase_mark(P, 17);
     const float lp = P.ell_p[dd];
     chol_block<KERNEL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad);
+    phase_mark(P, 18);
     (void)solve_block<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan);  // XR1 = X_p = L_p^-1
+    phase_mark(P, 19);
     // alpha = X_p^T a ; g_mean = g alpha + sum_s g_z
     for (int k = threadIdx.x; k < T; k += blockDim.x) {
       float al = 0.0f;
@@ -468,8 +485,11 @@ __global__ void __launch_bounds__(128, 4) bwd_block(Params P) {
       }
     } else {
       const float lq = P.ell_q[dd];
+      phase_mark(P, 20);
       const double t1 = contract_block<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig);
+      phase_mark(P, 21);
       chol_block<KERNEL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, s.pan, s.dgq, s.rdq, &bad);
+      phase_mark(P, 22);
       // w_s = L_q^T g_z,s ; pd = 1/2 sum_s w_s eps_s - g/2
       for (int k = threadIdx.x; k < T; k += blockDim.x) {
         float pdk = 0.0f;
@@ -482,7 +502,9 @@ __global__ void __launch_bounds__(128, 4) bwd_block(Params P) {
         }
         s.pd[k] = 0.5f * pdk - 0.5f * g;
       }
+      phase_mark(P, 23);
       (void)solve_block<true>(s.B2, s.rdq, nullptr, s.B2, L, T, s.pan);  // XR2 = X_q  (ends with a barrier)
+      phase_mark(P, 24);
       // C' = (Phi(sum_s w_s eps_s^T) - g/2 I) X_q by running prefix sums down each column, into XR1
       for (int l = threadIdx.x; l < T; l += blockDim.x) {
         for (int i = l; i < T; ++i) s.B1[(size_t)(i + 1) * ld + l] = s.pd[i] * s.B2[(size_t)(i + 1) * ld + l];
@@ -497,8 +519,11 @@ __global__ void __launch_bounds__(128, 4) bwd_block(Params P) {
         }
       }
       __syncthreads();
+      phase_mark(P, 25);
       const double t2 = contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig);
+      phase_mark(P, 26);
       const double gq = block_sum(0.5 * (double)g * t1 + t2, s.red);
+      phase_mark(P, 27);
       if (threadIdx.x == 0) P.gq_pairs[p] = (float)gq;
     }
     if (threadIdx.x == 0 && bad && P.status) atomicAdd(P.status, 1);
@@ -508,29 +533,36 @@ __global__ void __launch_bounds__(128, 4) bwd_block(Params P) {
 template <int KERNEL, int POST>
 cudaError_t launch_kp(const Params& P, bool backward, cudaStream_t st) {
   const Lay L(P.d.T_max, P.d.S);
-  const size_t smem = L.floats() * sizeof(float);
+  const bool resident = block_tier_resident(P.d);
+  const size_t smem = L.floats(resident) * sizeof(float);
   if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
+  if (!resident && !P.scratch) return cudaErrorInvalidValue;
   const int npairs = P.d.B * P.d.D;
-  const int nt = P.d.T_max <= 64 ? 64 : 128;
-  int per_sm = (int)(kMaxDynSmem / (smem + 1024));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2048 / nt) per_sm = 2048 / nt;
-  const int cap = kNumSMs * per_sm * 4;
-  const int grid = npairs < cap ? npairs : cap;
+  const int nt = P.d.T_max <= 64 ? 64 : (resident ? 128 : 256);
+  int grid;
+  if (resident) {
+    int per_sm = (int)(kMaxDynSmem / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2048 / nt) per_sm = 2048 / nt;
+    const int cap = kNumSMs * per_sm * 4;
+    grid = npairs < cap ? npairs : cap;
+  } else {
+    grid = npairs < kBlockSlots ? npairs : kBlockSlots;  // one workspace slot per CTA
+  }
   cudaError_t e;
   if (!backward) {
     auto kern = fwd_block<KERNEL, POST>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     prof_begin(false, st);
-    kern<<<grid, nt, smem, st>>>(P);
+    kern<<<grid, nt, smem, st>>>(P, resident ? 0 : 1);
     prof_end(false, st);
   } else {
     auto kern = bwd_block<KERNEL, POST>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     prof_begin(true, st);
-    kern<<<grid, nt, smem, st>>>(P);
+    kern<<<grid, nt, smem, st>>>(P, resident ? 0 : 1);
     prof_end(true, st);
   }
   note_launch();
@@ -539,12 +571,22 @@ cudaError_t launch_kp(const Params& P, bool backward, cudaStream_t st) {
 
 }  // namespace
 
+bool block_tier_resident(const GpklDesc& d) {
+  const Lay L(d.T_max, d.S);
+  return L.floats(true) * sizeof(float) <= kMaxDynSmem;
+}
+
+size_t block_slot_floats(const GpklDesc& d) {
+  const Lay L(d.T_max, d.S);
+  return block_tier_resident(d) ? 0 : 2 * L.buf();
+}
+
 bool block_tier_supports(const GpklDesc& d, bool backward) {
   if (d.T_max < 1) return false;
   if (backward && (d.flags & GPKL_FLAG_GRAD_ELL_P)) return false;  // d/d ell_p is served by the generic tier
   if (d.posterior != GPKL_POST_GP && d.posterior != GPKL_POST_DIAG) return false;
   const Lay L(d.T_max, d.S);
-  return L.floats() * sizeof(float) <= kMaxDynSmem;
+  return L.floats(false) * sizeof(float) <= kMaxDynSmem;
 }
 
 cudaError_t launch_block(const Params& P, bool backward, cudaStream_t st) {

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(NT) fwd_generic(Params P, int Tcap, int ld_cap
   const int S = d.S;
   const float noise = d.noise;
   const float sig = (float)(1.0 - (double)noise);
-  float* slot = P.scratch ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr;
+  float* slot = (!mats_in_smem && P.scratch) ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr;
   for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
     const int T = P.lengths[b];
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(NT) bwd_generic(Params P, int Tcap, int ld_cap
   const float noise = d.noise;
   const float sig = (float)(1.0 - (double)noise);
   const bool want_lp = (d.flags & GPKL_FLAG_GRAD_ELL_P) != 0;
-  float* slot = P.scratch ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr;
+  float* slot = (!mats_in_smem && P.scratch) ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr;
   const double g_sum = P.g_kl_sum ? *P.g_kl_sum : 1.0;
   for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;

@@ -26,8 +26,12 @@ cudaError_t launch_generic(const Params& P, bool backward, cudaStream_t st);
 bool warp_tier_supports(const GpklDesc& d, bool backward);
 cudaError_t launch_warp(const Params& P, bool backward, cudaStream_t st);
 
-// block tier (gpkl_block.cu): one CTA per pair, shared-memory resident, loop-based; T <= ~144
+// block tier (gpkl_block.cu): one CTA per pair, loop-based; matrices resident in shared memory for
+// T <= ~144, otherwise in one workspace slot per CTA (kBlockSlots CTAs, 2 per SM)
+constexpr int kBlockSlots = 2 * kNumSMs;
 bool block_tier_supports(const GpklDesc& d, bool backward);
+bool block_tier_resident(const GpklDesc& d);
+size_t block_slot_floats(const GpklDesc& d);  // 0 when resident
 cudaError_t launch_block(const Params& P, bool backward, cudaStream_t st);
 
 }  // namespace gpkl

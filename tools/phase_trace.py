@@ -1,0 +1,20 @@
+"""Per-phase cycle breakdown of CTA 0's FIRST pair in the block tier (internal debug hook)."""
+import ctypes, sys
+sys.path[:0] = ['/root/repo', '/root/repo/gp-vae_b200', '/root/repo/oracle', '/root/repo/tests']
+import torch, gpkl, gp_kl_oracle as orc
+from gpu_util import run_cuda
+dev = torch.device('cuda:0')
+L = gpkl._lib.lib()
+buf = torch.zeros(64, dtype=torch.int64, device=dev)
+for T in [int(a) for a in sys.argv[1:]] or [48, 128]:
+    case = orc.synthetic_batch(1, 1, T, 1, seed=1)
+    buf.zero_()
+    L.gpkl_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
+    run_cuda(case, dev, tier='block', grad_ell_p=False)
+    L.gpkl_debug_set_trace(None)
+    t = buf.cpu().tolist()
+    f = [t[i + 1] - t[i] for i in range(0, 6)]
+    b = [t[i + 1] - t[i] for i in range(16, 27)]
+    print('T=%d fwd cycles: load %d chol_p %d chol_q %d z %d solve %d reduce %d | total %d' % tuple([T] + f + [t[6] - t[0]]))
+    print('T=%d bwd cycles: load %d chol_p %d inv_p %d alpha %d t1 %d chol_q %d w %d inv_q %d Cprime %d t2 %d red %d | total %d'
+          % tuple([T] + b + [t[27] - t[16]]))
