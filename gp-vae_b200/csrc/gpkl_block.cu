@@ -94,20 +94,6 @@ struct Sm {
   }
 };
 
-// Entry (i,k) of the (optionally row-augmented) kernel matrix, identity on the padding.
-template <int KERNEL>
-__device__ __forceinline__ float k_entry(int i, int k, int T, int TP, bool extra, const float* __restrict__ ts,
-                                         const float* __restrict__ mm, const KernC<KERNEL>& kc, float noise) {
-  if (i < T && k < T) {
-    float v = kc.val(ts[i] - ts[k]);
-    if (i == k) v += noise;
-    return v;
-  }
-  if (i == k) return 1.0f;
-  if (extra && i == TP && k < T) return mm[k];
-  return 0.0f;
-}
-
 // One warp: factor the 16x16 diagonal block held in pan (columns 0..15, rows j0..j0+15) in registers with
 // shuffles; writes L_dd into the LC triangle of Bm, diag(L) into dg and 1/diag(L) into rdg.
 __device__ __forceinline__ void diag_factor(float* __restrict__ Bm, int ld, int j0, int T, const float* __restrict__ pan,
@@ -192,11 +178,26 @@ __device__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool ext
 #pragma unroll
           for (int r = 0; r < 4; ++r) acc[r][r] += noise;
         }
-      } else {
+      } else if (rb == TP) {  // the extra row block: row TP carries m^T, rows TP+1..TP+3 are zero
+        const float4 m4 = *reinterpret_cast<const float4*>(mm + cb);
+        const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[0][c] = (cb + c < T) ? mv[c] : 0.0f;
+          acc[1][c] = acc[2][c] = acc[3][c] = 0.0f;
+        }
+      } else {  // tile touching the identity padding: branch-free selects (divergent branches cost ~20 cycles each)
+        const float4 tr4 = *reinterpret_cast<const float4*>(ts + rb);
+        const float4 tc4 = *reinterpret_cast<const float4*>(ts + cb);
+        const float tr[4] = {tr4.x, tr4.y, tr4.z, tr4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = k_entry<KERNEL>(rb + r, cb + c, T, TP, extra, ts, mm, kc, noise);
+          for (int c = 0; c < 4; ++c) {
+            const int i = rb + r, k = cb + c;
+            const float v = kc.val(tr[r] - tc[c]) + (i == k ? noise : 0.0f);
+            acc[r][c] = (i < T && k < T) ? v : (i == k ? 1.0f : 0.0f);
+          }
       }
       tile_update<-1>(acc, Bm + rb, ld, Bm + cb, ld, 0, j0);
 #pragma unroll
@@ -320,16 +321,18 @@ __device__ double contract_block(const float* __restrict__ Ub, const float* __re
         for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(u[r], v[c], acc[r][c]);
     }
     tile_update<1>(acc, Ub + ld + kb, ld, Vb + ld + lb, ld, i, T);
+    const float4 tk4 = *reinterpret_cast<const float4*>(ts + kb);
+    const float4 tl4 = *reinterpret_cast<const float4*>(ts + lb);
+    const float tk[4] = {tk4.x, tk4.y, tk4.z, tk4.w}, tl[4] = {tl4.x, tl4.y, tl4.z, tl4.w};
     float part = 0.0f;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int k = kb + r, l = lb + c;
-        if (k < T && l < T && k != l) {
-          const float dt = ts[k] - ts[l];
-          part = fmaf(acc[r][c], kc.dell(dt, kc.val(dt)), part);
-        }
+        const float dt = tk[r] - tl[c];
+        const float dk = kc.dell(dt, kc.val(dt));
+        part = fmaf((k < T && l < T && k != l) ? acc[r][c] : 0.0f, dk, part);  // branch-free
       }
     total += (double)part;
   }
