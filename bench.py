@@ -213,20 +213,37 @@ def main():
     host = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
     c = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
     cfg = dict(kernel=w["kernel"], posterior="gp", noise=1e-3, S=1, tier=args.tier)
-    bucket = GradBucket(D, dev)
+    # two gradient buckets: step k's all-reduce (async, NCCL's own stream) overlaps step k+1's compute, the
+    # way DDP overlaps bucket reduction with the rest of backward; a bucket is waited for before it is rewritten
+    buckets = [GradBucket(D, dev), GradBucket(D, dev)]
+    pending = [None, None]
+    bucket = buckets[0]
     one = torch.ones((), dtype=torch.float64, device=dev)
     g_mean = torch.empty_like(c["mean"])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 256 MiB > 126 MB L2
+    step_no = [0]
 
     def step():
+        k = step_no[0] & 1
+        step_no[0] += 1
+        bk = buckets[k]
+        if pending[k] is not None:
+            pending[k].wait()          # stream-level wait: the reduction that last used this bucket is done
+            pending[k] = None
         f = gpkl.gp_prior_kl_forward(c["mean"], c["times"], c["lengths"], c["ell_q"], c["ell_p"], c["eps"], **cfg)
-        out = bucket.out_views()
+        out = bk.out_views()
         out["g_mean"] = g_mean
         gpkl.gp_prior_kl_backward(c["mean"], c["times"], c["lengths"], c["ell_q"], c["ell_p"], c["eps"], c["g_z"],
                                   one, None, grad_ell_p=args.grad_ell_p, out=out, **cfg)
-        bucket.kl.copy_(f["kl_sum"].to(torch.float32).reshape(1))
-        bucket.all_reduce()
+        bk.kl.copy_(f["kl_sum"].to(torch.float32).reshape(1))
+        pending[k] = bk.all_reduce(async_op=True)
         return f
+
+    def drain():
+        for k in (0, 1):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def barrier():
         if world > 1:
@@ -251,6 +268,7 @@ def main():
     for _ in range(warmup):
         step()
         flush.zero_()
+    drain()
     L.gpkl_profile_enable(1)
     sampler = ClockSampler(local_rank)
     barrier()
@@ -265,6 +283,12 @@ def main():
         e1.record()
         evs.append((e0, e1))
         flush.zero_()   # evict the step's inputs from L2 between timed iterations (outside the events)
+    # the last all-reduces must finish inside the timed region: their tail is timed as well
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    drain()
+    e1.record()
+    evs.append((e0, e1))
     barrier()
     sampler.stop_flag = True
     sampler.sample()
@@ -301,7 +325,7 @@ def main():
             gpkl.gp_prior_kl_backward(cc["mean"], cc["times"], cc["lengths"], cc["ell_q"], cc["ell_p"], cc["eps"],
                                       cc["g_z"], one, None, grad_ell_p=args.grad_ell_p, out=out, **cfg)
             bucket.kl.copy_(f["kl_sum"].to(torch.float32).reshape(1))
-            bucket.all_reduce()
+            bucket.all_reduce()      # synchronous here: the caller reads the reduced result every step
             res_host.copy_(bucket.flat, non_blocking=True)
             h2d = sum(host[k].numel() * host[k].element_size() for k in ("mean", "times", "lengths", "ell_q", "ell_p", "eps", "g_z"))
             return h2d, res_host.numel() * 4
@@ -362,7 +386,7 @@ def main():
         "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload + ": " + w["desc"], "per_gpu_batch": B, "global_batch": B * world,
-                   "parallelism": "dp%d (sequences sharded, all-reduce of lengthscale grads)" % world,
+                   "parallelism": "dp%d (sequences sharded; async all-reduce of lengthscale grads overlapped with the next step)" % world,
                    "l2": "256 MiB flush between timed iterations", "tier": args.tier,
                    "grad_ell_p": bool(args.grad_ell_p)},
         "clocks": sampler.result(),
