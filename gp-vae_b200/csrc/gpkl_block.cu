@@ -151,7 +151,7 @@ __device__ __forceinline__ void diag_solve16(float (&b)[16], const float* __rest
 // Left-looking panel Cholesky with fused kernel-matrix generation.  Result: LC triangle of Bm, inverse
 // diagonal blocks in inv[nP][256], diag(L) in dg.  extra: also carry row TP = m^T (gives L^-1 m).
 template <int KERNEL>
-__device__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool extra, const float* __restrict__ ts,
+__device__ __noinline__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool extra, const float* __restrict__ ts,
                            const float* __restrict__ mm, float ell, float sig, float noise, float* __restrict__ pan,
                            float* __restrict__ dg, float* __restrict__ rdg, int* bad) {
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -230,7 +230,7 @@ __device__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool ext
 // reciprocals rdgL.  IDENT: B = I, else B = LC triangle of Bb.  Returns this thread's partial sum of squares
 // of the strictly-lower entries of X (rows/cols < T).
 template <bool IDENT>
-__device__ float solve_block(const float* __restrict__ Lb, const float* __restrict__ rdgL, const float* __restrict__ Bb,
+__device__ __noinline__ float solve_block(const float* __restrict__ Lb, const float* __restrict__ rdgL, const float* __restrict__ Bb,
                              float* __restrict__ Xb, const Lay& L, int T, float* __restrict__ pan) {
   const int tid = threadIdx.x, NT = blockDim.x;
   const int ld = L.ld;
@@ -293,7 +293,7 @@ __device__ float solve_block(const float* __restrict__ Lb, const float* __restri
 
 // sum_{k != l, k,l < T} dK(k,l)/d ell * sum_{i} XU[i][k] XV[i][l]   (XR triangles of Ub / Vb); thread partial.
 template <int KERNEL>
-__device__ double contract_block(const float* __restrict__ Ub, const float* __restrict__ Vb, const Lay& L, int T,
+__device__ __noinline__ double contract_block(const float* __restrict__ Ub, const float* __restrict__ Vb, const Lay& L, int T,
                                  const float* __restrict__ ts, float ell, float sig) {
   const int tid = threadIdx.x, NT = blockDim.x;
   const int ld = L.ld;
