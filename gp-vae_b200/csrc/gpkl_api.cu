@@ -149,7 +149,8 @@ int check_desc(const GpklDesc* d) {
     return GPKL_ERR_DESC;
   if (d->tier < GPKL_TIER_AUTO || d->tier > GPKL_TIER_BLOCK) return GPKL_ERR_DESC;
   if (!(d->noise >= 0.0f) || !(d->noise < 1.0f)) return GPKL_ERR_DESC;
-  if (d->posterior == GPKL_POST_BIDIAG) return GPKL_ERR_UNSUPPORTED;
+  // V3 (bidiagonal-precision posterior) has no d/d ell_p path
+  if (d->posterior == GPKL_POST_BIDIAG && (d->flags & GPKL_FLAG_GRAD_ELL_P)) return GPKL_ERR_UNSUPPORTED;
   if ((int64_t)d->B * d->D > (int64_t)1 << 30) return GPKL_ERR_DESC;
   return GPKL_OK;
 }

@@ -144,6 +144,21 @@ __device__ void tri_contract(const float* __restrict__ U, const float* __restric
   o2 = a2;
 }
 
+// W = B^-1 for upper-bidiagonal B (diag b, super-diagonal c): upper triangular, W(i,j) = Wm[i*ld + j], j >= i.
+// One column per thread by back substitution: W(j,j) = 1/b_j, W(i,j) = -c_i W(i+1,j) / b_i.
+__device__ void bidiag_inverse(float* __restrict__ Wm, int ld, int T, const float* __restrict__ b,
+                               const float* __restrict__ c) {
+  for (int j = threadIdx.x; j < T; j += blockDim.x) {
+    float w = 1.0f / b[j];
+    Wm[(size_t)j * ld + j] = w;
+    for (int i = j - 1; i >= 0; --i) {
+      w = -c[i] * w / b[i];
+      Wm[(size_t)i * ld + j] = w;
+    }
+  }
+  __syncthreads();
+}
+
 struct SmemPlan {
   double* red;
   float *t, *m, *a, *al, *dgp, *dgq, *gzs, *pd, *hd, *var, *w, *v, *u, *wc;
@@ -209,6 +224,10 @@ __global__ void __launch_bounds__(NT) fwd_generic(Params P, int Tcap, int ld_cap
       s.m[i] = P.mean[(size_t)(r0 + i) * d.D + dd];
       s.a[i] = s.m[i];
       if (d.posterior == GPKL_POST_DIAG) s.var[i] = P.aux[(size_t)(r0 + i) * d.D + dd];  // logvar
+      if (d.posterior == GPKL_POST_BIDIAG) {  // diagonal b_i > 0 and super-diagonal c_i of the precision factor B
+        s.var[i] = P.aux[((size_t)(r0 + i) * d.D + dd) * 2];
+        s.hd[i] = P.aux[((size_t)(r0 + i) * d.D + dd) * 2 + 1];
+      }
     }
     for (int e = threadIdx.x; e < S * T; e += NT) {
       const int sidx = e / T, i = e - sidx * T;
@@ -247,6 +266,32 @@ __global__ void __launch_bounds__(NT) fwd_generic(Params P, int Tcap, int ld_cap
         part += (double)s.a[i] * (double)s.a[i];
         ldp += 2.0 * log((double)s.dgp[i]);
         ldq += 2.0 * log((double)s.dgq[i]);
+      }
+    } else if (d.posterior == GPKL_POST_BIDIAG) {
+      // V3 (extension): q = N(m, (B^T B)^-1), B upper bidiagonal (diag s.var, super s.hd)
+      //   KL = 1/2 [ ||L^-1 B^-1||_F^2 - T + log|K| + 2 sum log b_i + ||L^-1 m||^2 ],   z = m + B^-1 eps
+      trinv(s.Bp, ld, T, s.dgp);
+      bidiag_inverse(s.Bq, ld, T, s.var, s.hd);  // W = B^-1, upper triangular, W(i,j) = Bq[i*ld + j]
+      for (int e = threadIdx.x; e < T * T; e += NT) {
+        const int i = e / T, j = e - i * T;
+        const int kmax = min(i, j);
+        float mij = 0.0f;
+        for (int k = 0; k <= kmax; ++k) mij = fmaf(XR(s.Bp, i, k), s.Bq[(size_t)k * ld + j], mij);
+        part += (double)mij * (double)mij;
+      }
+      for (int i = threadIdx.x; i < T; i += NT) {
+        float ai = 0.0f;
+        for (int k = 0; k <= i; ++k) ai = fmaf(XR(s.Bp, i, k), s.m[k], ai);
+        const double lb = log((double)s.var[i]), lpd = log((double)s.dgp[i]);
+        part += (double)ai * (double)ai - 1.0 + 2.0 * lpd + 2.0 * lb;
+        ldp += 2.0 * lpd;
+        ldq -= 2.0 * lb;  // log|Sigma_q| = -2 sum log b
+        for (int sidx = 0; sidx < S; ++sidx) {
+          const float* ev = s.v + (size_t)sidx * T;
+          float acc = s.m[i];
+          for (int j = i; j < T; ++j) acc = fmaf(s.Bq[(size_t)i * ld + j], ev[j], acc);
+          P.z[((size_t)S * r0 + (size_t)sidx * T + i) * d.D + dd] = acc;
+        }
       }
     } else {  // GPKL_POST_DIAG
       trinv(s.Bp, ld, T, s.dgp);
@@ -308,6 +353,10 @@ __global__ void __launch_bounds__(NT) bwd_generic(Params P, int Tcap, int ld_cap
       s.t[i] = P.times[(size_t)b * d.T_max + i];
       s.m[i] = P.mean[(size_t)(r0 + i) * d.D + dd];
       if (d.posterior == GPKL_POST_DIAG) s.var[i] = P.aux[(size_t)(r0 + i) * d.D + dd];
+      if (d.posterior == GPKL_POST_BIDIAG) {
+        s.var[i] = P.aux[((size_t)(r0 + i) * d.D + dd) * 2];
+        s.hd[i] = P.aux[((size_t)(r0 + i) * d.D + dd) * 2 + 1];
+      }
       float gs = 0.0f;
       for (int sidx = 0; sidx < S; ++sidx) {
         const float gz = P.g_z ? P.g_z[((size_t)S * r0 + (size_t)sidx * T + i) * d.D + dd] : 0.0f;
@@ -423,6 +472,46 @@ __global__ void __launch_bounds__(NT) bwd_generic(Params P, int Tcap, int ld_cap
       if (threadIdx.x == 0) {
         P.gq_pairs[p] = (float)gq;
         if (want_lp) P.gp_pairs[p] = (float)gp;
+      }
+    } else if (d.posterior == GPKL_POST_BIDIAG) {
+      // W-bar = g K^-1 W + sum_s g_z,s eps_s^T (upper part), B-bar = -W^T W-bar W^T on the two diagonals,
+      // plus g/b_i from the log-determinant term.
+      bidiag_inverse(s.Bq, ld, T, s.var, s.hd);
+      // H = K^-1 = X^T X, lower triangle, into the (dead) LC triangle of Bp
+      for (int e = threadIdx.x; e < T * T; e += NT) {
+        const int k = e / T, i = e - k * T;
+        if (i >= k) {
+          float dot = 0.0f;
+          for (int r = i; r < T; ++r) dot = fmaf(XR(s.Bp, r, i), XR(s.Bp, r, k), dot);
+          LC(s.Bp, i, k) = dot;
+        }
+      }
+      __syncthreads();
+      // U^T = triu(W-bar)^T into the XR triangle of Bq:  XR(Bq, l, k) = W-bar[k][l], k <= l
+      for (int e = threadIdx.x; e < T * T; e += NT) {
+        const int l = e / T, k = e - l * T;
+        if (k <= l) {
+          float q = 0.0f;
+          for (int a = 0; a <= l; ++a) {
+            const float h = (k >= a) ? LC(s.Bp, k, a) : LC(s.Bp, a, k);
+            q = fmaf(h, s.Bq[(size_t)a * ld + l], q);
+          }
+          float ge = 0.0f;
+          for (int sidx = 0; sidx < S; ++sidx) ge = fmaf(s.u[(size_t)sidx * T + k], s.v[(size_t)sidx * T + l], ge);
+          XR(s.Bq, l, k) = g * q + ge;
+        }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < T; i += NT) {
+        float bb = 0.0f, cc = 0.0f;
+        for (int l = i; l < T; ++l) {
+          float pl = 0.0f;  // (W^T triu(W-bar))[i][l]
+          for (int k = 0; k <= i; ++k) pl = fmaf(s.Bq[(size_t)k * ld + i], XR(s.Bq, l, k), pl);
+          bb = fmaf(s.Bq[(size_t)i * ld + l], pl, bb);
+          if (l >= i + 1) cc = fmaf(s.Bq[(size_t)(i + 1) * ld + l], pl, cc);
+        }
+        P.g_aux[((size_t)(r0 + i) * d.D + dd) * 2] = -bb + g / s.var[i];
+        P.g_aux[((size_t)(r0 + i) * d.D + dd) * 2 + 1] = (i + 1 < T) ? -cc : 0.0f;
       }
     } else {  // GPKL_POST_DIAG
       for (int i = threadIdx.x; i < T; i += NT) {

@@ -127,6 +127,18 @@ def test_v2_vs_oracle_irregular_times(cuda_device, B, D, T, S, ragged, kernel, t
     assert_parity(errs, "V2 %s T=%d" % (kernel, T))
 
 
+@pytest.mark.parametrize("kernel", ["rbf", "cauchy"])
+@pytest.mark.parametrize("grid", [True, False])
+@pytest.mark.parametrize("B,D,T,S,ragged", [(3, 4, 1, 1, False), (2, 3, 2, 2, False), (4, 5, 7, 1, True), (3, 5, 16, 2, True),
+                                            (2, 4, 33, 1, True), (2, 6, 48, 1, False), (1, 3, 100, 2, True)])
+def test_v3_bidiag_vs_oracle(cuda_device, B, D, T, S, ragged, grid, kernel):
+    """V3 (bidiagonal-precision posterior, an extension named by north_star; NOT in the reference):
+    checked against the float64 dense oracle only -- parity unpinned by the reference."""
+    case = orc.synthetic_batch(B, D, T, S, ragged=ragged, seed=300 + T, posterior="bidiag", grid=grid)
+    errs = compare(case, cuda_device, floor=not grid, kernel=kernel, posterior="bidiag", S=S, tier="auto", grad_ell_p=False)
+    assert_parity(errs, "V3 %s T=%d" % (kernel, T))
+
+
 @pytest.mark.parametrize("tier,lp", [("generic", True), ("block", False), ("auto", False)])
 @pytest.mark.parametrize("T", [150, 200, 300])
 def test_large_T_workspace_path(cuda_device, T, tier, lp):
