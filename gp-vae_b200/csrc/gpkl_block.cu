@@ -31,22 +31,41 @@ namespace {
 constexpr int NB = 16;
 
 template <int SGN>
+__device__ __forceinline__ void tile_fma(float (&acc)[4][4], const float4& u4, const float4& v4) {
+  const float u[4] = {SGN > 0 ? u4.x : -u4.x, SGN > 0 ? u4.y : -u4.y, SGN > 0 ? u4.z : -u4.z, SGN > 0 ? u4.w : -u4.w};
+  const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(u[r], v[c], acc[r][c]);
+}
+
+// acc (+/-)= sum_{j in [ja, jb)} U[j*ldu + 0..3] (x) V[j*ldv + 0..3].  Main loop in groups of 8 steps with all
+// 16 operand loads issued before the FMAs (memory-level parallelism when the operands come from L1/L2).
+template <int SGN>
 __device__ __forceinline__ void tile_update(float (&acc)[4][4], const float* __restrict__ U, int ldu,
                                             const float* __restrict__ V, int ldv, int ja, int jb) {
   const float* up = U + (size_t)ja * ldu;
   const float* vp = V + (size_t)ja * ldv;
-#pragma unroll 4
-  for (int j = ja; j < jb; ++j) {
+  int j = ja;
+  for (; j + 8 <= jb; j += 8) {
+    float4 u4[8], v4[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      u4[e] = *reinterpret_cast<const float4*>(up + (size_t)e * ldu);
+      v4[e] = *reinterpret_cast<const float4*>(vp + (size_t)e * ldv);
+    }
+    up += (size_t)8 * ldu;
+    vp += (size_t)8 * ldv;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) tile_fma<SGN>(acc, u4[e], v4[e]);
+  }
+  for (; j < jb; ++j) {
     const float4 u4 = *reinterpret_cast<const float4*>(up);
     const float4 v4 = *reinterpret_cast<const float4*>(vp);
     up += ldu;
     vp += ldv;
-    const float u[4] = {SGN > 0 ? u4.x : -u4.x, SGN > 0 ? u4.y : -u4.y, SGN > 0 ? u4.z : -u4.z, SGN > 0 ? u4.w : -u4.w};
-    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(u[r], v[c], acc[r][c]);
+    tile_fma<SGN>(acc, u4, v4);
   }
 }
 
