@@ -69,6 +69,24 @@ __device__ __forceinline__ void tile_update(float (&acc)[4][4], const float* __r
   }
 }
 
+// A warp-aligned group of threads that runs one chain of phases with its own barrier.  bar == 0: the whole
+// CTA (__syncthreads); bar 1/2: the two half-CTA groups that factor K_p and K_q concurrently.
+struct Grp {
+  int tid, nt, bar;
+};
+// Barrier ids must be compile-time constants: a register barrier id makes ptxas reserve all 16 hardware
+// barriers for the CTA (one CTA per SM).  DUAL = false kernels only ever use barrier 0.
+template <bool DUAL>
+__device__ __forceinline__ void grp_sync(const Grp& g) {
+  if (!DUAL || g.bar == 0) {
+    __syncthreads();
+  } else if (g.bar == 1) {
+    asm volatile("bar.sync 1, %0;" ::"r"(g.nt) : "memory");
+  } else {
+    asm volatile("bar.sync 2, %0;" ::"r"(g.nt) : "memory");
+  }
+}
+
 struct Lay {  // shared-memory carve-up (floats), identical on host and device
   int TP, ld, nP, S;
   __host__ __device__ Lay(int Tmax, int S_) : S(S_) {
@@ -79,14 +97,17 @@ struct Lay {  // shared-memory carve-up (floats), identical on host and device
   }
   __host__ __device__ size_t buf() const { return (size_t)(TP + 1) * ld; }
   // shared floats; resident = the two work matrices live in shared memory (else in a workspace slot)
+  // dual: the two chains run concurrently and need a staging panel each
+  __host__ __device__ bool dual(bool resident) const { return resident && TP > 64; }
   __host__ __device__ size_t floats(bool resident) const {
-    return 64 + (resident ? 2 * buf() : 0) + (size_t)NB * ld + ld + 9 * (size_t)TP + 3 * (size_t)S * TP;
+    return 64 + (resident ? 2 * buf() : 0) + (dual(resident) ? 2 : 1) * (size_t)NB * ld + ld + 9 * (size_t)TP +
+           3 * (size_t)S * TP;
   }
 };
 
 struct Sm {
   double* red;
-  float *B1, *B2, *pan, *rdp, *rdq, *ts, *dgp, *dgq, *aa, *al, *pd, *gzs, *mm, *u, *v, *w;
+  float *B1, *B2, *pan, *pan2, *rdp, *rdq, *ts, *dgp, *dgq, *aa, *al, *pd, *gzs, *mm, *u, *v, *w;
   __device__ Sm(float* base, const Lay& L, float* slot) {
     red = reinterpret_cast<double*>(base); base += 64;
     if (slot) {  // large T: matrices in this CTA's workspace slot (global memory, L1/L2 cached)
@@ -97,6 +118,8 @@ struct Sm {
       B2 = base; base += L.buf();
     }
     pan = base; base += (size_t)NB * L.ld;
+    pan2 = base;
+    if (L.dual(slot == nullptr)) base += (size_t)NB * L.ld;
     ts = base; base += L.ld;
     rdp = base; base += L.TP;
     rdq = base; base += L.TP;
@@ -169,11 +192,11 @@ __device__ __forceinline__ void diag_solve16(float (&b)[16], const float* __rest
 
 // Left-looking panel Cholesky with fused kernel-matrix generation.  Result: LC triangle of Bm, inverse
 // diagonal blocks in inv[nP][256], diag(L) in dg.  extra: also carry row TP = m^T (gives L^-1 m).
-template <int KERNEL>
+template <int KERNEL, bool DUAL>
 __device__ __noinline__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool extra, const float* __restrict__ ts,
                            const float* __restrict__ mm, float ell, float sig, float noise, float* __restrict__ pan,
-                           float* __restrict__ dg, float* __restrict__ rdg, int* bad) {
-  const int tid = threadIdx.x, NT = blockDim.x;
+                           float* __restrict__ dg, float* __restrict__ rdg, int* bad, Grp g) {
+  const int tid = g.tid, NT = g.nt;
   const int cg = tid & 3, rg = tid >> 2, NRG = NT >> 2;
   const int ld = L.ld, TP = L.TP;
   const KernC<KERNEL> kc(ell, sig);
@@ -223,9 +246,9 @@ __device__ __noinline__ void chol_block(float* __restrict__ Bm, const Lay& L, in
       for (int c = 0; c < 4; ++c)
         *reinterpret_cast<float4*>(pan + (size_t)(4 * cg + c) * ld + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
     }
-    __syncthreads();
+    grp_sync<DUAL>(g);
     if (tid < 32) diag_factor(Bm, ld, j0, T, pan, dg, rdg, bad);
-    __syncthreads();
+    grp_sync<DUAL>(g);
     // rows below the diagonal block: L[i, j0:j0+16] = pan[i, :] L_dd^-T, one row per thread
     const int nbelow = Tact - j0 - NB;
     const int nrows = nbelow + (extra ? 1 : 0);
@@ -238,20 +261,20 @@ __device__ __noinline__ void chol_block(float* __restrict__ Bm, const Lay& L, in
 #pragma unroll
       for (int c = 0; c < 16; ++c) Bm[(size_t)(j0 + c) * ld + i] = b[c];
     }
-    __syncthreads();
+    grp_sync<DUAL>(g);
   }
   // identity padding: diag entries for rows in [Tact, TP) (only dg / rdg are consulted for them)
   for (int i = Tact + tid; i < TP; i += NT) { dg[i] = 1.0f; rdg[i] = 1.0f; }
-  __syncthreads();
+  grp_sync<DUAL>(g);
 }
 
 // X = L^-1 B by 16-row blocks into the XR triangle of Xb.  L: LC triangle of Lb with inverse diagonal
 // reciprocals rdgL.  IDENT: B = I, else B = LC triangle of Bb.  Returns this thread's partial sum of squares
 // of the strictly-lower entries of X (rows/cols < T).
-template <bool IDENT>
+template <bool IDENT, bool DUAL>
 __device__ __noinline__ float solve_block(const float* __restrict__ Lb, const float* __restrict__ rdgL, const float* __restrict__ Bb,
-                             float* __restrict__ Xb, const Lay& L, int T, float* __restrict__ pan) {
-  const int tid = threadIdx.x, NT = blockDim.x;
+                             float* __restrict__ Xb, const Lay& L, int T, float* __restrict__ pan, Grp g) {
+  const int tid = g.tid, NT = g.nt;
   const int ld = L.ld;
   const int Tact = (T + NB - 1) / NB * NB;
   float ssq = 0.0f;
@@ -289,7 +312,7 @@ __device__ __noinline__ float solve_block(const float* __restrict__ Lb, const fl
       for (int r = 0; r < 4; ++r)
         *reinterpret_cast<float4*>(pan + (size_t)(4 * rt + r) * ld + cb) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
     }
-    __syncthreads();
+    grp_sync<DUAL>(g);
     // diagonal block: X[i0:i0+16, col] = L_dd^-1 staged[:, col], one column per thread
     for (int col = tid; col < i0 + NB; col += NT) {
       float b[16];
@@ -305,7 +328,7 @@ __device__ __noinline__ float solve_block(const float* __restrict__ Lb, const fl
         }
       }
     }
-    __syncthreads();
+    grp_sync<DUAL>(g);
   }
   return ssq;
 }
@@ -313,8 +336,8 @@ __device__ __noinline__ float solve_block(const float* __restrict__ Lb, const fl
 // sum_{k != l, k,l < T} dK(k,l)/d ell * sum_{i} XU[i][k] XV[i][l]   (XR triangles of Ub / Vb); thread partial.
 template <int KERNEL>
 __device__ __noinline__ double contract_block(const float* __restrict__ Ub, const float* __restrict__ Vb, const Lay& L, int T,
-                                 const float* __restrict__ ts, float ell, float sig) {
-  const int tid = threadIdx.x, NT = blockDim.x;
+                                 const float* __restrict__ ts, float ell, float sig, Grp g) {
+  const int tid = g.tid, NT = g.nt;
   const int ld = L.ld;
   const int nk = (T + 3) / 4;
   const KernC<KERNEL> kc(ell, sig);
@@ -379,7 +402,28 @@ __device__ __forceinline__ void load_pair(const Params& P, int p, int b, int dd,
   }
 }
 
-template <int KERNEL, int POST>
+// Thread groups of a CTA.  With >= 128 threads and the full-GP posterior the CTA splits into two halves that
+// run the independent prior chain (K_p) and posterior chain (K_q) concurrently on named barriers 1 / 2; with
+// fewer threads (small T, many CTAs per SM) one group runs both chains back to back.
+struct Groups {
+  Grp all, chain;
+  bool g0, g1, dual;
+  __device__ Groups(bool want_dual) {
+    const int tid = threadIdx.x, nt = blockDim.x, half = nt >> 1;
+    dual = want_dual && nt >= 128;
+    all = Grp{tid, nt, 0};
+    if (dual) {
+      g0 = tid < half;
+      g1 = !g0;
+      chain = Grp{g0 ? tid : tid - half, half, g0 ? 1 : 2};
+    } else {
+      g0 = g1 = true;
+      chain = all;
+    }
+  }
+};
+
+template <int KERNEL, int POST, bool DUAL>
 __global__ void __launch_bounds__(256, 2) fwd_block(Params P, int use_slot) {
   extern __shared__ __align__(16) float smem_f[];
   __shared__ int bad;
@@ -388,6 +432,7 @@ __global__ void __launch_bounds__(256, 2) fwd_block(Params P, int use_slot) {
   Sm s(smem_f, L, use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr);
   const int S = d.S, TP = L.TP, ld = L.ld;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
+  const Groups G(DUAL);
   for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
     const int T = P.lengths[b];
@@ -405,22 +450,25 @@ __global__ void __launch_bounds__(256, 2) fwd_block(Params P, int use_slot) {
     load_pair(P, p, b, dd, T, r0, L, s, false);
     __syncthreads();
     phase_mark(P, 1);
-    chol_block<KERNEL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.dgp, s.rdp, &bad);
+    if (G.g0) chol_block<KERNEL, DUAL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
     phase_mark(P, 2);
     double part = 0.0, ldp = 0.0, ldq = 0.0;
     if (POST == GPKL_POST_GP) {
-      chol_block<KERNEL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.dgq, s.rdq, &bad);
-      phase_mark(P, 3);
-      for (int i = threadIdx.x; i < T; i += blockDim.x) {
-        for (int sx = 0; sx < S; ++sx) {
-          const float* ev = s.v + (size_t)sx * TP;
-          float acc = s.mm[i];
-          for (int k = 0; k <= i; ++k) acc = fmaf(s.B2[(size_t)k * ld + i], ev[k], acc);
-          P.z[((size_t)S * r0 + (size_t)sx * T + i) * d.D + dd] = acc;
+      if (G.g1) {
+        chol_block<KERNEL, DUAL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, G.dual ? s.pan2 : s.pan, s.dgq,
+                           s.rdq, &bad, G.chain);
+        for (int i = G.chain.tid; i < T; i += G.chain.nt) {  // z_s = m + L_q eps_s
+          for (int sx = 0; sx < S; ++sx) {
+            const float* ev = s.v + (size_t)sx * TP;
+            float acc = s.mm[i];
+            for (int k = 0; k <= i; ++k) acc = fmaf(s.B2[(size_t)k * ld + i], ev[k], acc);
+            P.z[((size_t)S * r0 + (size_t)sx * T + i) * d.D + dd] = acc;
+          }
         }
       }
+      if (G.dual) __syncthreads();  // join the two chains
       phase_mark(P, 4);
-      const float ssq = solve_block<false>(s.B1, s.rdp, s.B2, s.B1, L, T, s.pan);
+      const float ssq = solve_block<false, DUAL>(s.B1, s.rdp, s.B2, s.B1, L, T, s.pan, G.all);
       phase_mark(P, 5);
       part = (double)ssq;
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
@@ -431,7 +479,7 @@ __global__ void __launch_bounds__(256, 2) fwd_block(Params P, int use_slot) {
         ldq += 2.0 * log(lqd);
       }
     } else {
-      (void)solve_block<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan);
+      (void)solve_block<true, DUAL>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, G.all);
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
         float h = 0.0f;
         for (int k = i; k < T; ++k) { const float x = s.B1[(size_t)(k + 1) * ld + i]; h = fmaf(x, x, h); }
@@ -459,7 +507,7 @@ __global__ void __launch_bounds__(256, 2) fwd_block(Params P, int use_slot) {
   }
 }
 
-template <int KERNEL, int POST>
+template <int KERNEL, int POST, bool DUAL>
 __global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
   extern __shared__ __align__(16) float smem_f[];
   __shared__ int bad;
@@ -469,6 +517,7 @@ __global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
   const int S = d.S, TP = L.TP, ld = L.ld;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
   const double g_sum = P.g_kl_sum ? *P.g_kl_sum : 1.0;
+  const Groups G(DUAL);
   for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
     const int T = P.lengths[b];
@@ -485,15 +534,21 @@ __global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
     __syncthreads();
     phase_mark(P, 17);
     const float lp = P.ell_p[dd];
-    chol_block<KERNEL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad);
-    phase_mark(P, 18);
-    (void)solve_block<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan);  // XR1 = X_p = L_p^-1
-    phase_mark(P, 19);
-    // alpha = X_p^T a ; g_mean = g alpha + sum_s g_z
-    for (int k = threadIdx.x; k < T; k += blockDim.x) {
-      float al = 0.0f;
-      for (int i = k; i < T; ++i) al = fmaf(s.B1[(size_t)(i + 1) * ld + k], s.B1[(size_t)i * ld + TP], al);
-      P.g_mean[(size_t)(r0 + k) * d.D + dd] = g * al + s.gzs[k];
+    const float lq = (POST == GPKL_POST_GP) ? P.ell_q[dd] : lp;
+    double t1 = 0.0;
+    if (G.g0) {  // ---- prior chain: L_p, X_p = L_p^-1, alpha = K_p^-1 m, t1 = <K_p^-1, dK_q/d ell>
+      chol_block<KERNEL, DUAL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
+      phase_mark(P, 18);
+      (void)solve_block<true, DUAL>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, G.chain);
+      phase_mark(P, 19);
+      for (int k = G.chain.tid; k < T; k += G.chain.nt) {
+        float al = 0.0f;
+        for (int i = k; i < T; ++i) al = fmaf(s.B1[(size_t)(i + 1) * ld + k], s.B1[(size_t)i * ld + TP], al);
+        P.g_mean[(size_t)(r0 + k) * d.D + dd] = g * al + s.gzs[k];
+      }
+      phase_mark(P, 20);
+      if (POST == GPKL_POST_GP) t1 = contract_block<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, G.chain);
+      phase_mark(P, 21);
     }
     if (POST == GPKL_POST_DIAG) {
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
@@ -506,27 +561,26 @@ __global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
         P.g_aux[(size_t)(r0 + i) * d.D + dd] = 0.5f * g * (h * vv - 1.0f) + 0.5f * sd * ge;
       }
     } else {
-      const float lq = P.ell_q[dd];
-      phase_mark(P, 20);
-      const double t1 = contract_block<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig);
-      phase_mark(P, 21);
-      chol_block<KERNEL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, s.pan, s.dgq, s.rdq, &bad);
-      phase_mark(P, 22);
-      // w_s = L_q^T g_z,s ; pd = 1/2 sum_s w_s eps_s - g/2
-      for (int k = threadIdx.x; k < T; k += blockDim.x) {
-        float pdk = 0.0f;
-        for (int sx = 0; sx < S; ++sx) {
-          const float* uu = s.u + (size_t)sx * TP;
-          float wk = 0.0f;
-          for (int i = k; i < T; ++i) wk = fmaf(s.B2[(size_t)k * ld + i], uu[i], wk);
-          s.w[(size_t)sx * TP + k] = wk;
-          pdk = fmaf(wk, s.v[(size_t)sx * TP + k], pdk);
+      if (G.g1) {  // ---- posterior chain: L_q, w = L_q^T g_z, X_q = L_q^-1
+        chol_block<KERNEL, DUAL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, G.dual ? s.pan2 : s.pan, s.dgq, s.rdq, &bad,
+                           G.chain);
+        phase_mark(P, 22);
+        for (int k = G.chain.tid; k < T; k += G.chain.nt) {
+          float pdk = 0.0f;
+          for (int sx = 0; sx < S; ++sx) {
+            const float* uu = s.u + (size_t)sx * TP;
+            float wk = 0.0f;
+            for (int i = k; i < T; ++i) wk = fmaf(s.B2[(size_t)k * ld + i], uu[i], wk);
+            s.w[(size_t)sx * TP + k] = wk;
+            pdk = fmaf(wk, s.v[(size_t)sx * TP + k], pdk);
+          }
+          s.pd[k] = 0.5f * pdk - 0.5f * g;
         }
-        s.pd[k] = 0.5f * pdk - 0.5f * g;
+        phase_mark(P, 23);
+        (void)solve_block<true, DUAL>(s.B2, s.rdq, nullptr, s.B2, L, T, G.dual ? s.pan2 : s.pan, G.chain);
+        phase_mark(P, 24);
       }
-      phase_mark(P, 23);
-      (void)solve_block<true>(s.B2, s.rdq, nullptr, s.B2, L, T, s.pan);  // XR2 = X_q  (ends with a barrier)
-      phase_mark(P, 24);
+      __syncthreads();  // join: X_p (dead after t1), X_q, w, pd are complete
       // C' = (Phi(sum_s w_s eps_s^T) - g/2 I) X_q by running prefix sums down each column, into XR1
       for (int l = threadIdx.x; l < T; l += blockDim.x) {
         for (int i = l; i < T; ++i) s.B1[(size_t)(i + 1) * ld + l] = s.pd[i] * s.B2[(size_t)(i + 1) * ld + l];
@@ -542,7 +596,7 @@ __global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
       }
       __syncthreads();
       phase_mark(P, 25);
-      const double t2 = contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig);
+      const double t2 = contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, G.all);
       phase_mark(P, 26);
       const double gq = block_sum(0.5 * (double)g * t1 + t2, s.red);
       phase_mark(P, 27);
@@ -560,7 +614,7 @@ cudaError_t launch_kp(const Params& P, bool backward, cudaStream_t st) {
   if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
   if (!resident && !P.scratch) return cudaErrorInvalidValue;
   const int npairs = P.d.B * P.d.D;
-  const int nt = P.d.T_max <= 64 ? 64 : (resident ? 128 : 256);
+  const int nt = P.d.T_max <= 64 ? 64 : 256;
   int grid;
   if (resident) {
     int per_sm = (int)(kMaxDynSmem / (smem + 1024));
@@ -571,22 +625,15 @@ cudaError_t launch_kp(const Params& P, bool backward, cudaStream_t st) {
   } else {
     grid = npairs < kBlockSlots ? npairs : kBlockSlots;  // one workspace slot per CTA
   }
-  cudaError_t e;
-  if (!backward) {
-    auto kern = fwd_block<KERNEL, POST>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    prof_begin(false, st);
-    kern<<<grid, nt, smem, st>>>(P, resident ? 0 : 1);
-    prof_end(false, st);
-  } else {
-    auto kern = bwd_block<KERNEL, POST>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    prof_begin(true, st);
-    kern<<<grid, nt, smem, st>>>(P, resident ? 0 : 1);
-    prof_end(true, st);
-  }
+  const bool dual = POST == GPKL_POST_GP && L.dual(resident);
+  void (*kern)(Params, int);
+  if (!backward) kern = dual ? fwd_block<KERNEL, POST, true> : fwd_block<KERNEL, POST, false>;
+  else kern = dual ? bwd_block<KERNEL, POST, true> : bwd_block<KERNEL, POST, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  prof_begin(backward, st);
+  kern<<<grid, nt, smem, st>>>(P, resident ? 0 : 1);
+  prof_end(backward, st);
   note_launch();
   return cudaGetLastError();
 }
