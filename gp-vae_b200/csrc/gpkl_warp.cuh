@@ -72,6 +72,7 @@ template <int LP, int R, int KERNEL>
 __device__ __forceinline__ void build_rows(float (&a)[R][LP * R], const float (&trow)[R], const float* __restrict__ ts,
                                            int lig, int T, int Tw, float ell, float sig, float noise) {
   constexpr int TM = LP * R;
+  const KernC<KERNEL> kc(ell, sig);
 #pragma unroll
   for (int k4 = 0; k4 < TM; k4 += 4) {
     if (k4 < Tw) {
@@ -83,7 +84,7 @@ __device__ __forceinline__ void build_rows(float (&a)[R][LP * R], const float (&
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           const int r = lig + LP * j;
-          float v = kern_val<KERNEL>(trow[j] - tv[e], ell, sig);
+          float v = kc.val(trow[j] - tv[e]);
           if (k == r) v += noise;
           a[j][k] = (k <= r && r < T) ? v : ((k == r) ? 1.0f : 0.0f);
         }
@@ -249,7 +250,7 @@ __device__ __forceinline__ float contract_cols(const float (&x)[R][LP * R], cons
                                                const float* __restrict__ ts, const float (&tcol)[R], int lig, int T,
                                                float ell, float sig) {
   constexpr int TM = LP * R;
-  const float inv_sig = 1.0f / sig, il3 = 1.0f / (ell * ell * ell);
+  const KernC<KERNEL> kc(ell, sig);
   float acc = 0.0f;
   for (int l = 0; l < T; ++l) {
     const int ip = TM - 1 - l;
@@ -275,8 +276,7 @@ __device__ __forceinline__ float contract_cols(const float (&x)[R][LP * R], cons
     for (int jj = 0; jj < R; ++jj) {
       const int c = lig + LP * jj;
       const float dt = tcol[jj] - tl;
-      const float kv = kern_val<KERNEL>(dt, ell, sig);
-      const float dk = kern_dell<KERNEL>(dt, kv, il3, inv_sig);
+      const float dk = kc.dell(dt, kc.val(dt));
       if (c != l && c < T) acc = fmaf(dot[jj], dk, acc);
     }
   }
