@@ -156,7 +156,7 @@ int check_desc(const GpklDesc* d) {
 }
 
 int dispatch(const Params& P, bool backward, cudaStream_t st) {
-  // tier selection (GPKL_TIER_AUTO): register-resident warp tier for T <= 32, block tier above (matrices in
+  // tier selection (GPKL_TIER_AUTO): register-resident warp tier for T <= 64, block tier above (matrices in
   // shared memory up to T ~ 144, in an L2-backed workspace slot beyond), generic tier for the combinations
   // the specialised tiers do not implement (d/d ell_p).  Explicit requests are honoured or refused, never silently rerouted.
   cudaError_t e;
@@ -166,7 +166,7 @@ int dispatch(const Params& P, bool backward, cudaStream_t st) {
   } else if (P.d.tier == GPKL_TIER_BLOCK) {
     if (!block_tier_supports(P.d, backward)) return GPKL_ERR_UNSUPPORTED;
     e = launch_block(P, backward, st);
-  } else if (P.d.tier == GPKL_TIER_AUTO && P.d.T_max <= 32 && warp_tier_supports(P.d, backward)) {
+  } else if (P.d.tier == GPKL_TIER_AUTO && P.d.T_max <= 64 && warp_tier_supports(P.d, backward)) {
     e = launch_warp(P, backward, st);
   } else if (P.d.tier == GPKL_TIER_AUTO && block_tier_supports(P.d, backward)) {
     e = launch_block(P, backward, st);

@@ -250,3 +250,35 @@ def test_host_step_matches_device_path(cuda_device):
     assert torch.equal(hs.g_mean, bwd["g_mean"].cpu()) and torch.equal(hs.g_ell_q, bwd["g_ell_q"].cpu())
     assert torch.equal(hs.g_ell_p, bwd["g_ell_p"].cpu())
     assert hs.h2d_bytes > 0 and hs.d2h_bytes > 0
+
+
+def test_cuda_graph_capture(cuda_device):
+    """The C ABI does no allocation / synchronisation on the data path: forward+backward capture into a CUDA
+    graph and replay bit-identically (warp tier T=20 and block tier T=80)."""
+    import gpkl
+    dev = cuda_device
+    for T in (20, 80):
+        case = orc.synthetic_batch(3, 4, T, 1, ragged=True, seed=T)
+        c = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
+        args = (c["mean"], c["times"], c["lengths"], c["ell_q"], c["ell_p"], c["eps"])
+        ref_f = gpkl.gp_prior_kl_forward(*args)
+        ref_b = gpkl.gp_prior_kl_backward(*args, c["g_z"])
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):        # warm the workspace cache on the capture stream
+            gpkl.gp_prior_kl_forward(*args)
+            gpkl.gp_prior_kl_backward(*args, c["g_z"])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            f = gpkl.gp_prior_kl_forward(*args)
+            b = gpkl.gp_prior_kl_backward(*args, c["g_z"])
+        for t in (f["z"], f["kl_pairs"], b["g_mean"], b["g_ell_q"]):
+            t.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(f["z"], ref_f["z"]) and torch.equal(f["kl_pairs"], ref_f["kl_pairs"])
+        assert float(f["kl_sum"]) == float(ref_f["kl_sum"])
+        assert torch.equal(b["g_mean"], ref_b["g_mean"]) and torch.equal(b["g_ell_q"], ref_b["g_ell_q"])
