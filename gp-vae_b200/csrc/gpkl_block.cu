@@ -87,6 +87,21 @@ __device__ __forceinline__ void grp_sync(const Grp& g) {
   }
 }
 
+// Workspace variant (T > ~144): operand slabs are staged global -> shared with cp.async, double buffered.
+constexpr int STG_KC = 8;                             // contraction steps per stage (Cholesky / solve)
+constexpr int STG_RCH = 768;                          // rows (columns) of one staged super-chunk
+constexpr int STG_SLD = 16 + STG_RCH;                 // floats per staged step: 16-wide operand | RCH-wide operand
+constexpr int STG_MT = STG_RCH / (4 * 64);            // 4x4 tiles per thread per super-chunk (64 tile rows x 256 threads)
+constexpr int STG_FLOATS = 2 * STG_KC * STG_SLD;      // two stages
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct Lay {  // shared-memory carve-up (floats), identical on host and device
   int TP, ld, nP, S;
   __host__ __device__ Lay(int Tmax, int S_) : S(S_) {
@@ -100,19 +115,21 @@ struct Lay {  // shared-memory carve-up (floats), identical on host and device
   // dual: the two chains run concurrently and need a staging panel each
   __host__ __device__ bool dual(bool resident) const { return resident && TP > 64; }
   __host__ __device__ size_t floats(bool resident) const {
-    return 64 + (resident ? 2 * buf() : 0) + (dual(resident) ? 2 : 1) * (size_t)NB * ld + ld + 9 * (size_t)TP +
-           3 * (size_t)S * TP;
+    return 64 + (resident ? 2 * buf() : (size_t)STG_FLOATS) + (dual(resident) ? 2 : 1) * (size_t)NB * ld + ld +
+           9 * (size_t)TP + 3 * (size_t)S * TP;
   }
 };
 
 struct Sm {
   double* red;
-  float *B1, *B2, *pan, *pan2, *rdp, *rdq, *ts, *dgp, *dgq, *aa, *al, *pd, *gzs, *mm, *u, *v, *w;
+  float *B1, *B2, *stg, *pan, *pan2, *rdp, *rdq, *ts, *dgp, *dgq, *aa, *al, *pd, *gzs, *mm, *u, *v, *w;
   __device__ Sm(float* base, const Lay& L, float* slot) {
     red = reinterpret_cast<double*>(base); base += 64;
-    if (slot) {  // large T: matrices in this CTA's workspace slot (global memory, L1/L2 cached)
+    stg = nullptr;
+    if (slot) {  // large T: matrices in this CTA's workspace slot; operand slabs staged through stg
       B1 = slot;
       B2 = slot + L.buf();
+      stg = base; base += STG_FLOATS;
     } else {
       B1 = base; base += L.buf();
       B2 = base; base += L.buf();
@@ -381,6 +398,76 @@ __device__ __noinline__ double contract_block(const float* __restrict__ Ub, cons
   return total;
 }
 
+// Workspace variant of contract_block: 64x64 output blocks (one 4x4 tile per thread, 256 threads); the 64 U
+// columns and 64 V columns of 32 rows at a time are staged with cp.async (zero-filled above the diagonal, so
+// the other triangle of the buffer never leaks in) and consumed from shared memory.
+template <int KERNEL>
+__device__ __noinline__ double contract_block_staged(const float* __restrict__ Ub, const float* __restrict__ Vb,
+                                                     const Lay& L, int T, const float* __restrict__ ts, float ell,
+                                                     float sig, float* __restrict__ stg) {
+  constexpr int KC = 32, SLD = 128;
+  const int tid = threadIdx.x;  // blockDim.x == 256
+  const int ld = L.ld;
+  const int nb = (T + 63) / 64;
+  const KernC<KERNEL> kc(ell, sig);
+  const int kt = tid & 15, lt = tid >> 4;
+  double total = 0.0;
+  for (int bp = 0; bp < nb * nb; ++bp) {
+    const int kb0 = (bp % nb) * 64, lb0 = (bp / nb) * 64;
+    const int kb = kb0 + 4 * kt, lb = lb0 + 4 * lt;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+    const int i_begin = kb0 > lb0 ? kb0 : lb0;  // X[i][k] = 0 for i < k
+    const int nch = (T - i_begin + KC - 1) / KC;
+    auto issue = [&](int c) {
+      float* buf = stg + (c & 1) * (KC * SLD);
+      for (int q = tid; q < KC * 32; q += 256) {
+        const int ii = q >> 5, seg = q & 31;  // seg 0..15: U columns, 16..31: V columns
+        const int i = i_begin + c * KC + ii;
+        const bool isU = seg < 16;
+        const int col = (isU ? kb0 : lb0) + 4 * (seg & 15);
+        const float* base = isU ? Ub : Vb;
+        int valid = (i < T) ? (i - col + 1) : 0;  // columns col..col+3 exist while <= i
+        valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
+        const float* src = valid ? base + (size_t)(i + 1) * ld + col : base;
+        cp_async16(buf + ii * SLD + 4 * seg, src, 4 * valid);
+      }
+      cp_async_commit();
+    };
+    if (nch > 0) issue(0);
+    for (int c = 0; c < nch; ++c) {
+      if (c + 1 < nch) issue(c + 1);
+      else cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+      const float* buf = stg + (c & 1) * (KC * SLD);
+#pragma unroll 8
+      for (int ii = 0; ii < KC; ++ii) {
+        const float4 u4 = *reinterpret_cast<const float4*>(buf + ii * SLD + 4 * kt);
+        const float4 v4 = *reinterpret_cast<const float4*>(buf + ii * SLD + 64 + 4 * lt);
+        tile_fma<1>(acc, u4, v4);
+      }
+      __syncthreads();
+    }
+    float part = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = kb + r, l = lb + c;
+        const bool ok = k < T && l < T && k != l;
+        const float dt = ok ? ts[k] - ts[l] : 0.0f;
+        const float dk = kc.dell(dt, kc.val(dt));
+        part = fmaf(ok ? acc[r][c] : 0.0f, dk, part);
+      }
+    total += (double)part;
+  }
+  return total;
+}
+
 __device__ __forceinline__ void load_pair(const Params& P, int p, int b, int dd, int T, long long r0, const Lay& L,
                                           Sm& s, bool backward) {
   const GpklDesc& d = P.d;
@@ -547,7 +634,9 @@ __global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
         P.g_mean[(size_t)(r0 + k) * d.D + dd] = g * al + s.gzs[k];
       }
       phase_mark(P, 20);
-      if (POST == GPKL_POST_GP) t1 = contract_block<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, G.chain);
+      if (POST == GPKL_POST_GP)
+        t1 = use_slot ? contract_block_staged<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, s.stg)
+                      : contract_block<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, G.chain);
       phase_mark(P, 21);
     }
     if (POST == GPKL_POST_DIAG) {
@@ -596,7 +685,8 @@ __global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
       }
       __syncthreads();
       phase_mark(P, 25);
-      const double t2 = contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, G.all);
+      const double t2 = use_slot ? contract_block_staged<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg)
+                                 : contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, G.all);
       phase_mark(P, 26);
       const double gq = block_sum(0.5 * (double)g * t1 + t2, s.red);
       phase_mark(P, 27);
