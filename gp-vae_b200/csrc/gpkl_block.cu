@@ -156,11 +156,11 @@ struct Sm {
 // One warp: factor the 16x16 diagonal block held in pan (columns 0..15, rows j0..j0+15) in registers with
 // shuffles; writes L_dd into the LC triangle of Bm, diag(L) into dg and 1/diag(L) into rdg.
 __device__ __forceinline__ void diag_factor(float* __restrict__ Bm, int ld, int j0, int T, const float* __restrict__ pan,
-                                            float* __restrict__ dg, float* __restrict__ rdg, int* bad) {
+                                            int ldpan, float* __restrict__ dg, float* __restrict__ rdg, int* bad) {
   const int lane = threadIdx.x & 31, l = lane & 15;
   float a[16];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) a[c] = (c <= l) ? pan[c * ld + j0 + l] : 0.0f;
+  for (int c = 0; c < 16; ++c) a[c] = (c <= l) ? pan[c * ldpan + j0 + l] : 0.0f;
   float dgv = 1.0f, rdv = 1.0f;
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
@@ -209,23 +209,33 @@ __device__ __forceinline__ void diag_solve16(float (&b)[16], const float* __rest
 
 // Left-looking panel Cholesky with fused kernel-matrix generation.  Result: LC triangle of Bm, inverse
 // diagonal blocks in inv[nP][256], diag(L) in dg.  extra: also carry row TP = m^T (gives L^-1 m).
-template <int KERNEL, bool DUAL>
-__device__ __noinline__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool extra, const float* __restrict__ ts,
-                           const float* __restrict__ mm, float ell, float sig, float noise, float* __restrict__ pan,
-                           float* __restrict__ dg, float* __restrict__ rdg, int* bad, Grp g) {
+// Bm is a VIEW: element (i,k) at Bm[k*ldm + i].  Columns [c_begin, c_end) are factored; contributions of columns
+// < kstart are assumed applied already, and with FROM_VIEW the starting values are read from the view (the
+// GEMM phase of the large-T path left them there) instead of being generated.
+template <int KERNEL, bool DUAL, bool FROM_VIEW>
+__device__ __noinline__ void chol_panels(float* __restrict__ Bm, int ldm, int c_begin, int c_end, int kstart, const Lay& L,
+                                         int T, bool extra, const float* __restrict__ ts, const float* __restrict__ mm,
+                                         float ell, float sig, float noise, float* __restrict__ pan,
+                                         float* __restrict__ dg, float* __restrict__ rdg, int* bad, Grp g) {
   const int tid = g.tid, NT = g.nt;
   const int cg = tid & 3, rg = tid >> 2, NRG = NT >> 2;
-  const int ld = L.ld, TP = L.TP;
+  const int ld = L.ld, TP = L.TP;  // ld: stride of the staging panel `pan`
   const KernC<KERNEL> kc(ell, sig);
   // rows beyond the last real row are identity padding and decouple: only panels that contain real rows matter
   const int Tact = (T + NB - 1) / NB * NB;
   const int rows_end = extra ? TP + 4 : Tact;
-  for (int j0 = 0; j0 < Tact; j0 += NB) {
+  for (int j0 = c_begin; j0 < c_end; j0 += NB) {
     const int cb = j0 + 4 * cg;
     for (int rb = j0 + 4 * rg; rb < rows_end; rb += 4 * NRG) {
       if (rb >= Tact && rb < TP) continue;  // identity padding rows
       float acc[4][4];
-      if (rb + 3 < T && cb + 3 < T) {  // all-real tile: no padding logic
+      if (FROM_VIEW) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 a4 = *reinterpret_cast<const float4*>(Bm + (size_t)(cb + c) * ldm + rb);
+          acc[0][c] = a4.x; acc[1][c] = a4.y; acc[2][c] = a4.z; acc[3][c] = a4.w;
+        }
+      } else if (rb + 3 < T && cb + 3 < T) {  // all-real tile: no padding logic
         const float4 tr4 = *reinterpret_cast<const float4*>(ts + rb);
         const float4 tc4 = *reinterpret_cast<const float4*>(ts + cb);
         const float tr[4] = {tr4.x, tr4.y, tr4.z, tr4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
@@ -258,13 +268,13 @@ __device__ __noinline__ void chol_block(float* __restrict__ Bm, const Lay& L, in
             acc[r][c] = (i < T && k < T) ? v : (i == k ? 1.0f : 0.0f);
           }
       }
-      tile_update<-1>(acc, Bm + rb, ld, Bm + cb, ld, 0, j0);
+      tile_update<-1>(acc, Bm + rb, ldm, Bm + cb, ldm, kstart, j0);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         *reinterpret_cast<float4*>(pan + (size_t)(4 * cg + c) * ld + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
     }
     grp_sync<DUAL>(g);
-    if (tid < 32) diag_factor(Bm, ld, j0, T, pan, dg, rdg, bad);
+    if (tid < 32) diag_factor(Bm, ldm, j0, T, pan, ld, dg, rdg, bad);
     grp_sync<DUAL>(g);
     // rows below the diagonal block: L[i, j0:j0+16] = pan[i, :] L_dd^-T, one row per thread
     const int nbelow = Tact - j0 - NB;
@@ -274,28 +284,43 @@ __device__ __noinline__ void chol_block(float* __restrict__ Bm, const Lay& L, in
       float b[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) b[c] = pan[(size_t)c * ld + i];
-      diag_solve16(b, Bm, ld, j0, rdg);
+      diag_solve16(b, Bm, ldm, j0, rdg);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) Bm[(size_t)(j0 + c) * ld + i] = b[c];
+      for (int c = 0; c < 16; ++c) Bm[(size_t)(j0 + c) * ldm + i] = b[c];
     }
     grp_sync<DUAL>(g);
   }
   // identity padding: diag entries for rows in [Tact, TP) (only dg / rdg are consulted for them)
-  for (int i = Tact + tid; i < TP; i += NT) { dg[i] = 1.0f; rdg[i] = 1.0f; }
+  if (c_end >= Tact) {
+    for (int i = Tact + tid; i < TP; i += NT) { dg[i] = 1.0f; rdg[i] = 1.0f; }
+  }
   grp_sync<DUAL>(g);
+}
+
+// Resident path: the whole factorisation, kernel entries generated on the fly.
+template <int KERNEL, bool DUAL>
+__device__ __forceinline__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool extra, const float* __restrict__ ts,
+                                           const float* __restrict__ mm, float ell, float sig, float noise,
+                                           float* __restrict__ pan, float* __restrict__ dg, float* __restrict__ rdg, int* bad,
+                                           Grp g) {
+  const int Tact = (T + NB - 1) / NB * NB;
+  chol_panels<KERNEL, DUAL, false>(Bm, L.ld, 0, Tact, 0, L, T, extra, ts, mm, ell, sig, noise, pan, dg, rdg, bad, g);
 }
 
 // X = L^-1 B by 16-row blocks into the XR triangle of Xb.  L: LC triangle of Lb with inverse diagonal
 // reciprocals rdgL.  IDENT: B = I, else B = LC triangle of Bb.  Returns this thread's partial sum of squares
 // of the strictly-lower entries of X (rows/cols < T).
-template <bool IDENT, bool DUAL>
-__device__ __noinline__ float solve_block(const float* __restrict__ Lb, const float* __restrict__ rdgL, const float* __restrict__ Bb,
-                             float* __restrict__ Xb, const Lay& L, int T, float* __restrict__ pan, Grp g) {
+// Xb is a VIEW of the solution: X(i,k) at Xb[(i+1)*ldx + k].  Rows [r_begin, r_end) are solved; contributions of
+// rows < kstart are assumed applied already and with FROM_VIEW the starting values are read from the view (the GEMM
+// phase of the large-T path left them there) instead of the right-hand side.
+template <bool IDENT, bool DUAL, bool FROM_VIEW>
+__device__ __noinline__ float solve_rows(const float* __restrict__ Lb, const float* __restrict__ rdgL, const float* __restrict__ Bb,
+                                         float* __restrict__ Xb, int ldx, int r_begin, int r_end, int kstart, const Lay& L,
+                                         int T, float* __restrict__ pan, Grp g) {
   const int tid = g.tid, NT = g.nt;
   const int ld = L.ld;
-  const int Tact = (T + NB - 1) / NB * NB;
   float ssq = 0.0f;
-  for (int i0 = 0; i0 < Tact; i0 += NB) {
+  for (int i0 = r_begin; i0 < r_end; i0 += NB) {
     const int ntile = 4 * (i0 / 4 + 4);
     for (int id = tid; id < ntile; id += NT) {
       const int rt = id & 3, ct = id >> 2;
@@ -308,14 +333,16 @@ __device__ __noinline__ float solve_block(const float* __restrict__ Lb, const fl
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int row = rb + r, col = cb + c;
-          acc[r][c] = (col <= row) ? (IDENT ? (row == col ? 1.0f : 0.0f) : Bb[(size_t)col * ld + row]) : 0.0f;
+          if (FROM_VIEW) acc[r][c] = Xb[(size_t)(row + 1) * ldx + col];
+          else acc[r][c] = (col <= row) ? (IDENT ? (row == col ? 1.0f : 0.0f) : Bb[(size_t)col * ld + row]) : 0.0f;
         }
-      // contraction over already solved rows k in [cb, i0); X[k][col] exists only for col <= k
+      // contraction over already solved rows k in [max(cb, kstart), i0); X[k][col] exists only for col <= k
       int k = cb < i0 ? cb : i0;
+      if (k < kstart) k = kstart;
       const int khead = (k + 3 < i0) ? k + 3 : i0;
       for (; k < khead; ++k) {
         const float4 u4 = *reinterpret_cast<const float4*>(Lb + (size_t)k * ld + rb);
-        const float4 v4 = *reinterpret_cast<const float4*>(Xb + (size_t)(k + 1) * ld + cb);
+        const float4 v4 = *reinterpret_cast<const float4*>(Xb + (size_t)(k + 1) * ldx + cb);
         const float u[4] = {u4.x, u4.y, u4.z, u4.w};
         const float v[4] = {cb <= k ? v4.x : 0.0f, cb + 1 <= k ? v4.y : 0.0f, cb + 2 <= k ? v4.z : 0.0f,
                             cb + 3 <= k ? v4.w : 0.0f};
@@ -324,7 +351,7 @@ __device__ __noinline__ float solve_block(const float* __restrict__ Lb, const fl
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(-u[r], v[c], acc[r][c]);
       }
-      tile_update<-1>(acc, Lb + rb, ld, Xb + ld + cb, ld, k, i0);
+      tile_update<-1>(acc, Lb + rb, ld, Xb + ldx + cb, ldx, k, i0);
 #pragma unroll
       for (int r = 0; r < 4; ++r)
         *reinterpret_cast<float4*>(pan + (size_t)(4 * rt + r) * ld + cb) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
@@ -340,7 +367,7 @@ __device__ __noinline__ float solve_block(const float* __restrict__ Lb, const fl
       for (int r = 0; r < 16; ++r) {
         const int row = i0 + r;
         if (col <= row) {
-          Xb[(size_t)(row + 1) * ld + col] = b[r];
+          Xb[(size_t)(row + 1) * ldx + col] = b[r];
           if (col < row && row < T) ssq = fmaf(b[r], b[r], ssq);
         }
       }
@@ -348,6 +375,15 @@ __device__ __noinline__ float solve_block(const float* __restrict__ Lb, const fl
     grp_sync<DUAL>(g);
   }
   return ssq;
+}
+
+// Resident path: X = L^-1 B over all rows.
+template <bool IDENT, bool DUAL>
+__device__ __forceinline__ float solve_block(const float* __restrict__ Lb, const float* __restrict__ rdgL,
+                                             const float* __restrict__ Bb, float* __restrict__ Xb, const Lay& L, int T,
+                                             float* __restrict__ pan, Grp g) {
+  const int Tact = (T + NB - 1) / NB * NB;
+  return solve_rows<IDENT, DUAL, false>(Lb, rdgL, Bb, Xb, L.ld, 0, Tact, 0, L, T, pan, g);
 }
 
 // sum_{k != l, k,l < T} dK(k,l)/d ell * sum_{i} XU[i][k] XV[i][l]   (XR triangles of Ub / Vb); thread partial.
