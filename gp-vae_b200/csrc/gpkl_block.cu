@@ -88,11 +88,12 @@ __device__ __forceinline__ void grp_sync(const Grp& g) {
 }
 
 // Workspace variant (T > ~144): operand slabs are staged global -> shared with cp.async, double buffered.
-constexpr int STG_KC = 8;                             // contraction steps per stage (Cholesky / solve)
-constexpr int STG_RCH = 768;                          // rows (columns) of one staged super-chunk
-constexpr int STG_SLD = 16 + STG_RCH;                 // floats per staged step: 16-wide operand | RCH-wide operand
-constexpr int STG_MT = STG_RCH / (4 * 64);            // 4x4 tiles per thread per super-chunk (64 tile rows x 256 threads)
-constexpr int STG_FLOATS = 2 * STG_KC * STG_SLD;      // two stages
+constexpr int STG_FLOATS = 8192;                      // two stages of the largest staged phase (contraction: 2*32*128)
+constexpr int GM_KC = 16;                             // GEMM phase: contraction steps per stage
+constexpr int GM_SLD = 192;                           // floats per staged step: 128 A values | 64 B values
+constexpr int NBL = 64;                               // large-T panel width (columns / rows per GEMM phase)
+constexpr int GEMM_TMAX = 512;                        // the shared-memory panel fits up to this T
+constexpr int GEMM_TMIN = 256;                        // below this the per-panel overheads outweigh the GEMM phase
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -114,22 +115,27 @@ struct Lay {  // shared-memory carve-up (floats), identical on host and device
   // shared floats; resident = the two work matrices live in shared memory (else in a workspace slot)
   // dual: the two chains run concurrently and need a staging panel each
   __host__ __device__ bool dual(bool resident) const { return resident && TP > 64; }
+  // gemm: workspace path whose 64-wide panels live in shared memory and are updated by the staged GEMM tile
+  __host__ __device__ bool gemm(bool resident) const { return !resident && TP > GEMM_TMIN && TP <= GEMM_TMAX; }
   __host__ __device__ size_t floats(bool resident) const {
-    return 64 + (resident ? 2 * buf() : (size_t)STG_FLOATS) + (dual(resident) ? 2 : 1) * (size_t)NB * ld + ld +
-           9 * (size_t)TP + 3 * (size_t)S * TP;
+    return 64 + (resident ? 2 * buf() : (size_t)STG_FLOATS) + (gemm(resident) ? (size_t)NBL * ld : 0) +
+           (dual(resident) ? 2 : 1) * (size_t)NB * ld + ld + 9 * (size_t)TP + 3 * (size_t)S * TP;
   }
 };
 
 struct Sm {
   double* red;
-  float *B1, *B2, *stg, *pan, *pan2, *rdp, *rdq, *ts, *dgp, *dgq, *aa, *al, *pd, *gzs, *mm, *u, *v, *w;
+  float *B1, *B2, *stg, *wide, *pan, *pan2, *rdp, *rdq, *ts, *dgp, *dgq, *aa, *al, *pd, *gzs, *mm, *u, *v, *w;
   __device__ Sm(float* base, const Lay& L, float* slot) {
     red = reinterpret_cast<double*>(base); base += 64;
     stg = nullptr;
+    wide = nullptr;
     if (slot) {  // large T: matrices in this CTA's workspace slot; operand slabs staged through stg
       B1 = slot;
       B2 = slot + L.buf();
       stg = base; base += STG_FLOATS;
+      wide = base;  // 64-wide panel (Cholesky) / 64-row block (solve) of the GEMM path
+      if (L.gemm(false)) base += (size_t)NBL * L.ld;
     } else {
       B1 = base; base += L.buf();
       B2 = base; base += L.buf();
@@ -386,6 +392,193 @@ __device__ __forceinline__ float solve_block(const float* __restrict__ Lb, const
   return solve_rows<IDENT, DUAL, false>(Lb, rdgL, Bb, Xb, L.ld, 0, Tact, 0, L, T, pan, g);
 }
 
+// ---- GEMM-structured phases of the workspace path (144 < T <= 512, 256 threads) -------------------------------
+// acc[8][4] (+/-)= sum_{k in [k0,k1)} A(arow0 + 8*ty + r, k) * B(bcol0 + 4*tx + c, k),  ty = tid/16, tx = tid%16.
+// Operands are k-major in global memory (A(i,k) at Ag[k*lda + i], B(j,k) at Bg[k*ldb + j]) and are staged 16 steps
+// at a time with cp.async, double buffered: one stage = 768 16-byte copies, ~512 FMAs per thread per barrier pair.
+// Rows >= arow_lim / columns >= bcol_lim are zero-filled; with A_TRI also A(i,k) for i > k (the row-major lower
+// triangle of an already solved X, whose other triangle holds a different matrix).
+template <int SGN, bool A_TRI>
+__device__ __forceinline__ void gemm_tile_128x64(float (&acc)[8][4], const float* __restrict__ Ag, int lda, int arow0,
+                                                 int arow_lim, const float* __restrict__ Bg, int ldb, int bcol0,
+                                                 int bcol_lim, int k0, int k1, float* __restrict__ stg) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int nch = (k1 - k0 + GM_KC - 1) / GM_KC;
+  auto issue = [&](int c) {
+    float* buf = stg + (c & 1) * (GM_KC * GM_SLD);
+#pragma unroll
+    for (int rnd = 0; rnd < 3; ++rnd) {
+      const int q = tid + 256 * rnd;  // 16 steps x 48 float4
+      const int kk = q / 48, e = q - kk * 48;
+      const int k = k0 + c * GM_KC + kk;
+      if (e < 32) {
+        const int row = arow0 + 4 * e;
+        int valid = (k < k1 && row < arow_lim) ? 4 : 0;
+        if (A_TRI && valid) {
+          const int v = k - row + 1;
+          valid = v < 0 ? 0 : (v > 4 ? 4 : v);
+        }
+        cp_async16(buf + kk * GM_SLD + 4 * e, valid ? Ag + (size_t)k * lda + row : Ag, 4 * valid);
+      } else {
+        const int col = bcol0 + 4 * (e - 32);
+        const int valid = (k < k1 && col < bcol_lim) ? 4 : 0;
+        cp_async16(buf + kk * GM_SLD + 128 + 4 * (e - 32), valid ? Bg + (size_t)k * ldb + col : Bg, 4 * valid);
+      }
+    }
+    cp_async_commit();
+  };
+  if (nch > 0) issue(0);
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) issue(c + 1);
+    else cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* buf = stg + (c & 1) * (GM_KC * GM_SLD);
+#pragma unroll
+    for (int kk = 0; kk < GM_KC; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(buf + kk * GM_SLD + 8 * ty);
+      const float4 a1 = *reinterpret_cast<const float4*>(buf + kk * GM_SLD + 8 * ty + 4);
+      const float4 b4 = *reinterpret_cast<const float4*>(buf + kk * GM_SLD + 128 + 4 * tx);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) acc[r][cc] = fmaf(SGN > 0 ? a[r] : -a[r], b[cc], acc[r][cc]);
+    }
+    __syncthreads();
+  }
+}
+
+// Large-T Cholesky: 64-column panels.  GEMM phase: panel = K - L[:, 0:J0] L[J0:J0+64, 0:J0]^T into the shared-memory
+// panel `wide` (K generated in the accumulator init); then the panel is factored in shared memory by the 16-column
+// code on a view of `wide`; then its lower triangle is copied to the global factor.
+template <int KERNEL>
+__device__ __noinline__ void chol_gemm(float* __restrict__ Bm, const Lay& L, int T, bool extra, const float* __restrict__ ts,
+                                       const float* __restrict__ mm, float ell, float sig, float noise,
+                                       float* __restrict__ pan, float* __restrict__ wide, float* __restrict__ stg,
+                                       float* __restrict__ dg, float* __restrict__ rdg, int* bad) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int ld = L.ld, TP = L.TP;
+  const KernC<KERNEL> kc(ell, sig);
+  const int Tact = (T + NB - 1) / NB * NB;
+  const int rows_end = extra ? TP + 4 : Tact;
+  const Grp all{tid, (int)blockDim.x, 0};
+  for (int J0 = 0; J0 < Tact; J0 += NBL) {
+    const int ncols = (Tact - J0 < NBL) ? Tact - J0 : NBL;
+    float* Pv = wide - (size_t)J0 * ld;  // view: column c (absolute) at Pv[c*ld + row]
+    const int cb = J0 + 4 * tx;
+    for (int rb0 = J0; rb0 < rows_end; rb0 += 128) {
+      float acc[8][4];
+      float tc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tc[c] = (cb + c < TP) ? ts[cb + c] : 0.0f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int i = rb0 + 8 * ty + r;
+        const float ti = (i < ld) ? ts[i] : 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int k = cb + c;
+          const float v = kc.val(ti - tc[c]) + (i == k ? noise : 0.0f);
+          const float pad = (i == k) ? 1.0f : ((extra && i == TP && k < T) ? mm[k < TP ? k : 0] : 0.0f);
+          acc[r][c] = (i < T && k < T) ? v : pad;
+        }
+      }
+      gemm_tile_128x64<-1, false>(acc, Bm, ld, rb0, rows_end, Bm, ld, J0, J0 + ncols, 0, J0, stg);
+      const int row0 = rb0 + 8 * ty;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (4 * tx + c < ncols) {
+          float* dst = Pv + (size_t)(cb + c) * ld + row0;
+          if (row0 < rows_end) *reinterpret_cast<float4*>(dst) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+          if (row0 + 4 < rows_end) *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4][c], acc[5][c], acc[6][c], acc[7][c]);
+        }
+      }
+    }
+    __syncthreads();
+    chol_panels<KERNEL, false, true>(Pv, ld, J0, J0 + ncols, J0, L, T, extra, ts, mm, ell, sig, noise, pan, dg, rdg, bad, all);
+    // copy the finished panel's lower triangle (and the extra rows) to the global factor
+    const int nr4 = rows_end >> 2;
+    for (int idx = tid; idx < ncols * nr4; idx += blockDim.x) {
+      const int cl = idx / nr4, r4 = 4 * (idx - cl * nr4);
+      const int c = J0 + cl;
+      if (r4 + 3 < c) continue;              // above the diagonal: the other triangle of the buffer
+      if (r4 >= Tact && r4 < TP) continue;   // identity padding rows are never written
+      const float4 v = *reinterpret_cast<const float4*>(Pv + (size_t)c * ld + r4);
+      float* dst = Bm + (size_t)c * ld + r4;
+      if (r4 >= c) {
+        *reinterpret_cast<float4*>(dst) = v;
+      } else {
+        if (r4 + 1 >= c) dst[1] = v.y;
+        if (r4 + 2 >= c) dst[2] = v.z;
+        dst[3] = v.w;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Large-T solve X = L^-1 B by 64-row blocks: GEMM phase rows[I0:I0+64] = B - L[rows, 0:I0] X[0:I0, :] into the
+// shared-memory block `wide` (X operand zero-filled above its diagonal), then the 64x64 diagonal part by the 16-row
+// code on a view of `wide`, then the rows are copied to the global XR triangle.
+template <bool IDENT>
+__device__ __noinline__ float solve_gemm(const float* __restrict__ Lb, const float* __restrict__ rdgL,
+                                         const float* __restrict__ Bb, float* __restrict__ Xb, const Lay& L, int T,
+                                         float* __restrict__ pan, float* __restrict__ wide, float* __restrict__ stg) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int ld = L.ld;
+  const int Tact = (T + NB - 1) / NB * NB;
+  const Grp all{tid, (int)blockDim.x, 0};
+  float ssq = 0.0f;
+  for (int I0 = 0; I0 < Tact; I0 += NBL) {
+    const int nrows = (Tact - I0 < NBL) ? Tact - I0 : NBL;
+    const int ncols = I0 + nrows;
+    float* Qv = wide - (size_t)(I0 + 1) * ld;  // X view: X(i,k) at Qv[(i+1)*ld + k]
+    for (int cb0 = 0; cb0 < ncols; cb0 += 128) {
+      float acc[8][4];  // acc[a][b] = X[I0 + 4*tx + b][cb0 + 8*ty + a]
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int col = cb0 + 8 * ty + a, row = I0 + 4 * tx + b;
+          acc[a][b] = (row < ncols && col <= row) ? (IDENT ? (row == col ? 1.0f : 0.0f) : Bb[(size_t)col * ld + row]) : 0.0f;
+        }
+      // A operand: X(k, col) for k < I0 (global, zero above its diagonal); B operand: L(I0 + r, k)
+      gemm_tile_128x64<-1, true>(acc, Xb + ld, ld, cb0, ld, Lb, ld, I0, I0 + nrows, cb0, I0, stg);
+      const int col0 = cb0 + 8 * ty;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int row = I0 + 4 * tx + b;
+        if (row < ncols && col0 < ld) {
+          float* dst = Qv + (size_t)(row + 1) * ld + col0;
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[0][b], acc[1][b], acc[2][b], acc[3][b]);
+          if (col0 + 4 < ld) *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4][b], acc[5][b], acc[6][b], acc[7][b]);
+        }
+      }
+    }
+    __syncthreads();
+    ssq += solve_rows<IDENT, false, true>(Lb, rdgL, Bb, Qv, ld, I0, I0 + nrows, I0, L, T, pan, all);
+    const int nc4 = ncols >> 2;
+    for (int idx = tid; idx < nrows * nc4; idx += blockDim.x) {
+      const int r = idx / nc4, c4 = 4 * (idx - r * nc4);
+      const int row = I0 + r;
+      if (c4 > row) continue;
+      const float4 v = *reinterpret_cast<const float4*>(wide + (size_t)r * ld + c4);
+      float* dst = Xb + (size_t)(row + 1) * ld + c4;
+      if (c4 + 3 <= row) {
+        *reinterpret_cast<float4*>(dst) = v;
+      } else {
+        dst[0] = v.x;
+        if (c4 + 1 <= row) dst[1] = v.y;
+        if (c4 + 2 <= row) dst[2] = v.z;
+      }
+    }
+    __syncthreads();
+  }
+  return ssq;
+}
+
 // sum_{k != l, k,l < T} dK(k,l)/d ell * sum_{i} XU[i][k] XV[i][l]   (XR triangles of Ub / Vb); thread partial.
 template <int KERNEL>
 __device__ __noinline__ double contract_block(const float* __restrict__ Ub, const float* __restrict__ Vb, const Lay& L, int T,
@@ -546,8 +739,8 @@ struct Groups {
   }
 };
 
-template <int KERNEL, int POST, bool DUAL>
-__global__ void __launch_bounds__(256, 2) fwd_block(Params P, int use_slot) {
+template <int KERNEL, int POST, bool DUAL, bool SLOT>
+__global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use_slot) {
   extern __shared__ __align__(16) float smem_f[];
   __shared__ int bad;
   const GpklDesc& d = P.d;
@@ -573,13 +766,17 @@ __global__ void __launch_bounds__(256, 2) fwd_block(Params P, int use_slot) {
     load_pair(P, p, b, dd, T, r0, L, s, false);
     __syncthreads();
     phase_mark(P, 1);
-    if (G.g0) chol_block<KERNEL, DUAL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
+    const bool gm = SLOT && L.gemm(false);  // large T: GEMM-structured phases on shared-memory panels
+    if (gm) chol_gemm<KERNEL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.wide, s.stg, s.dgp, s.rdp, &bad);
+    else if (G.g0) chol_block<KERNEL, DUAL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
     phase_mark(P, 2);
     double part = 0.0, ldp = 0.0, ldq = 0.0;
     if (POST == GPKL_POST_GP) {
+      if (gm) chol_gemm<KERNEL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
       if (G.g1) {
-        chol_block<KERNEL, DUAL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, G.dual ? s.pan2 : s.pan, s.dgq,
-                           s.rdq, &bad, G.chain);
+        if (!gm)
+          chol_block<KERNEL, DUAL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, G.dual ? s.pan2 : s.pan, s.dgq,
+                                   s.rdq, &bad, G.chain);
         for (int i = G.chain.tid; i < T; i += G.chain.nt) {  // z_s = m + L_q eps_s
           for (int sx = 0; sx < S; ++sx) {
             const float* ev = s.v + (size_t)sx * TP;
@@ -591,7 +788,8 @@ __global__ void __launch_bounds__(256, 2) fwd_block(Params P, int use_slot) {
       }
       if (G.dual) __syncthreads();  // join the two chains
       phase_mark(P, 4);
-      const float ssq = solve_block<false, DUAL>(s.B1, s.rdp, s.B2, s.B1, L, T, s.pan, G.all);
+      const float ssq = gm ? solve_gemm<false>(s.B1, s.rdp, s.B2, s.B1, L, T, s.pan, s.wide, s.stg)
+                           : solve_block<false, DUAL>(s.B1, s.rdp, s.B2, s.B1, L, T, s.pan, G.all);
       phase_mark(P, 5);
       part = (double)ssq;
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
@@ -602,7 +800,8 @@ __global__ void __launch_bounds__(256, 2) fwd_block(Params P, int use_slot) {
         ldq += 2.0 * log(lqd);
       }
     } else {
-      (void)solve_block<true, DUAL>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, G.all);
+      if (gm) (void)solve_gemm<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, s.wide, s.stg);
+      else (void)solve_block<true, DUAL>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, G.all);
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
         float h = 0.0f;
         for (int k = i; k < T; ++k) { const float x = s.B1[(size_t)(k + 1) * ld + i]; h = fmaf(x, x, h); }
@@ -630,8 +829,8 @@ __global__ void __launch_bounds__(256, 2) fwd_block(Params P, int use_slot) {
   }
 }
 
-template <int KERNEL, int POST, bool DUAL>
-__global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
+template <int KERNEL, int POST, bool DUAL, bool SLOT>
+__global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use_slot) {
   extern __shared__ __align__(16) float smem_f[];
   __shared__ int bad;
   const GpklDesc& d = P.d;
@@ -658,11 +857,14 @@ __global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
     phase_mark(P, 17);
     const float lp = P.ell_p[dd];
     const float lq = (POST == GPKL_POST_GP) ? P.ell_q[dd] : lp;
+    const bool gm = SLOT && L.gemm(false);  // large T: GEMM-structured phases on shared-memory panels
     double t1 = 0.0;
     if (G.g0) {  // ---- prior chain: L_p, X_p = L_p^-1, alpha = K_p^-1 m, t1 = <K_p^-1, dK_q/d ell>
-      chol_block<KERNEL, DUAL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
+      if (gm) chol_gemm<KERNEL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.wide, s.stg, s.dgp, s.rdp, &bad);
+      else chol_block<KERNEL, DUAL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
       phase_mark(P, 18);
-      (void)solve_block<true, DUAL>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, G.chain);
+      if (gm) (void)solve_gemm<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, s.wide, s.stg);
+      else (void)solve_block<true, DUAL>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, G.chain);
       phase_mark(P, 19);
       for (int k = G.chain.tid; k < T; k += G.chain.nt) {
         float al = 0.0f;
@@ -671,7 +873,7 @@ __global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
       }
       phase_mark(P, 20);
       if (POST == GPKL_POST_GP)
-        t1 = use_slot ? contract_block_staged<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, s.stg)
+        t1 = SLOT ? contract_block_staged<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, s.stg)
                       : contract_block<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, G.chain);
       phase_mark(P, 21);
     }
@@ -687,8 +889,10 @@ __global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
       }
     } else {
       if (G.g1) {  // ---- posterior chain: L_q, w = L_q^T g_z, X_q = L_q^-1
-        chol_block<KERNEL, DUAL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, G.dual ? s.pan2 : s.pan, s.dgq, s.rdq, &bad,
-                           G.chain);
+        if (gm) chol_gemm<KERNEL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
+        else
+          chol_block<KERNEL, DUAL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, G.dual ? s.pan2 : s.pan, s.dgq, s.rdq,
+                                   &bad, G.chain);
         phase_mark(P, 22);
         for (int k = G.chain.tid; k < T; k += G.chain.nt) {
           float pdk = 0.0f;
@@ -702,7 +906,8 @@ __global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
           s.pd[k] = 0.5f * pdk - 0.5f * g;
         }
         phase_mark(P, 23);
-        (void)solve_block<true, DUAL>(s.B2, s.rdq, nullptr, s.B2, L, T, G.dual ? s.pan2 : s.pan, G.chain);
+        if (gm) (void)solve_gemm<true>(s.B2, s.rdq, nullptr, s.B2, L, T, s.pan, s.wide, s.stg);
+        else (void)solve_block<true, DUAL>(s.B2, s.rdq, nullptr, s.B2, L, T, G.dual ? s.pan2 : s.pan, G.chain);
         phase_mark(P, 24);
       }
       __syncthreads();  // join: X_p (dead after t1), X_q, w, pd are complete
@@ -721,7 +926,7 @@ __global__ void __launch_bounds__(256, 2) bwd_block(Params P, int use_slot) {
       }
       __syncthreads();
       phase_mark(P, 25);
-      const double t2 = use_slot ? contract_block_staged<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg)
+      const double t2 = SLOT ? contract_block_staged<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg)
                                  : contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, G.all);
       phase_mark(P, 26);
       const double gq = block_sum(0.5 * (double)g * t1 + t2, s.red);
@@ -753,8 +958,9 @@ cudaError_t launch_kp(const Params& P, bool backward, cudaStream_t st) {
   }
   const bool dual = POST == GPKL_POST_GP && L.dual(resident);
   void (*kern)(Params, int);
-  if (!backward) kern = dual ? fwd_block<KERNEL, POST, true> : fwd_block<KERNEL, POST, false>;
-  else kern = dual ? bwd_block<KERNEL, POST, true> : bwd_block<KERNEL, POST, false>;
+  if (!resident) kern = backward ? bwd_block<KERNEL, POST, false, true> : fwd_block<KERNEL, POST, false, true>;
+  else if (!backward) kern = dual ? fwd_block<KERNEL, POST, true, false> : fwd_block<KERNEL, POST, false, false>;
+  else kern = dual ? bwd_block<KERNEL, POST, true, false> : bwd_block<KERNEL, POST, false, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   prof_begin(backward, st);
