@@ -398,7 +398,7 @@ __device__ __forceinline__ float solve_block(const float* __restrict__ Lb, const
 // at a time with cp.async, double buffered: one stage = 768 16-byte copies, ~512 FMAs per thread per barrier pair.
 // Rows >= arow_lim / columns >= bcol_lim are zero-filled; with A_TRI also A(i,k) for i > k (the row-major lower
 // triangle of an already solved X, whose other triangle holds a different matrix).
-template <int SGN, bool A_TRI>
+template <int SGN, bool A_TRI, bool B_TRI = false>
 __device__ __forceinline__ void gemm_tile_128x64(float (&acc)[8][4], const float* __restrict__ Ag, int lda, int arow0,
                                                  int arow_lim, const float* __restrict__ Bg, int ldb, int bcol0,
                                                  int bcol_lim, int k0, int k1, float* __restrict__ stg) {
@@ -421,7 +421,11 @@ __device__ __forceinline__ void gemm_tile_128x64(float (&acc)[8][4], const float
         cp_async16(buf + kk * GM_SLD + 4 * e, valid ? Ag + (size_t)k * lda + row : Ag, 4 * valid);
       } else {
         const int col = bcol0 + 4 * (e - 32);
-        const int valid = (k < k1 && col < bcol_lim) ? 4 : 0;
+        int valid = (k < k1 && col < bcol_lim) ? 4 : 0;
+        if (B_TRI && valid) {
+          const int v = k - col + 1;
+          valid = v < 0 ? 0 : (v > 4 ? 4 : v);
+        }
         cp_async16(buf + kk * GM_SLD + 128 + 4 * (e - 32), valid ? Bg + (size_t)k * ldb + col : Bg, 4 * valid);
       }
     }
@@ -621,6 +625,46 @@ __device__ __noinline__ double contract_block(const float* __restrict__ Ub, cons
         const float dt = tk[r] - tl[c];
         const float dk = kc.dell(dt, kc.val(dt));
         part = fmaf((k < T && l < T && k != l) ? acc[r][c] : 0.0f, dk, part);  // branch-free
+      }
+    total += (double)part;
+  }
+  return total;
+}
+
+// Large-T contraction on the staged GEMM tile: 128 (k) x 64 (l) output blocks, contraction over the row index i
+// of the two row-major lower triangles (both zero-filled above their diagonals while staging), kernel derivative
+// in the epilogue.
+template <int KERNEL>
+__device__ __noinline__ double contract_gemm(const float* __restrict__ Ub, const float* __restrict__ Vb, const Lay& L, int T,
+                                             const float* __restrict__ ts, float ell, float sig, float* __restrict__ stg) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int ld = L.ld;
+  const KernC<KERNEL> kc(ell, sig);
+  const int nkb = (T + 127) / 128, nlb = (T + 63) / 64;
+  double total = 0.0;
+  for (int bp = 0; bp < nkb * nlb; ++bp) {
+    const int kb0 = (bp % nkb) * 128, lb0 = (bp / nkb) * 64;
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+    const int i0 = (kb0 > lb0 ? kb0 : lb0) / GM_KC * GM_KC;  // X[i][k] = 0 for i < k
+    gemm_tile_128x64<1, true, true>(acc, Ub + ld, ld, kb0, ld, Vb + ld, ld, lb0, ld, i0, T, stg);
+    float tk[8], tl[4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) tk[r] = (kb0 + 8 * ty + r < T) ? ts[kb0 + 8 * ty + r] : 0.0f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tl[c] = (lb0 + 4 * tx + c < T) ? ts[lb0 + 4 * tx + c] : 0.0f;
+    float part = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = kb0 + 8 * ty + r, l = lb0 + 4 * tx + c;
+        const float dt = tk[r] - tl[c];
+        const float dk = kc.dell(dt, kc.val(dt));
+        part = fmaf((k < T && l < T && k != l) ? acc[r][c] : 0.0f, dk, part);
       }
     total += (double)part;
   }
@@ -866,14 +910,26 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
       if (gm) (void)solve_gemm<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, s.wide, s.stg);
       else (void)solve_block<true, DUAL>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, G.chain);
       phase_mark(P, 19);
+      // a = L_p^-1 m (the extra row of the factor) into shared memory once, then alpha = X_p^T a with the
+      // column loads issued 8 rows ahead
+      for (int i = G.chain.tid; i < T; i += G.chain.nt) s.aa[i] = s.B1[(size_t)i * ld + TP];
+      grp_sync<DUAL>(G.chain);
       for (int k = G.chain.tid; k < T; k += G.chain.nt) {
+        const float* __restrict__ xp = s.B1 + ld + k;  // X_p(i, k) at xp[i*ld]
         float al = 0.0f;
-        for (int i = k; i < T; ++i) al = fmaf(s.B1[(size_t)(i + 1) * ld + k], s.B1[(size_t)i * ld + TP], al);
+        for (int i0 = k; i0 < T; i0 += 8) {
+          float xv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xv[e] = (i0 + e < T) ? xp[(size_t)(i0 + e) * ld] : 0.0f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) al = fmaf(xv[e], (i0 + e < T) ? s.aa[i0 + e] : 0.0f, al);
+        }
         P.g_mean[(size_t)(r0 + k) * d.D + dd] = g * al + s.gzs[k];
       }
       phase_mark(P, 20);
       if (POST == GPKL_POST_GP)
-        t1 = SLOT ? contract_block_staged<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, s.stg)
+        t1 = gm ? contract_gemm<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, s.stg)
+           : SLOT ? contract_block_staged<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, s.stg)
                       : contract_block<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, G.chain);
       phase_mark(P, 21);
     }
@@ -911,22 +967,44 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
         phase_mark(P, 24);
       }
       __syncthreads();  // join: X_p (dead after t1), X_q, w, pd are complete
-      // C' = (Phi(sum_s w_s eps_s^T) - g/2 I) X_q by running prefix sums down each column, into XR1
+      // C' = (Phi(sum_s w_s eps_s^T) - g/2 I) X_q by running prefix sums down each column, into XR1.  Loads are
+      // issued 8 rows ahead of the dependent prefix arithmetic (the matrices may live in global memory).
       for (int l = threadIdx.x; l < T; l += blockDim.x) {
-        for (int i = l; i < T; ++i) s.B1[(size_t)(i + 1) * ld + l] = s.pd[i] * s.B2[(size_t)(i + 1) * ld + l];
-        for (int sx = 0; sx < S; ++sx) {
-          const float* ww = s.w + (size_t)sx * TP;
-          const float* vv = s.v + (size_t)sx * TP;
-          float cum = 0.0f;
-          for (int i = l; i < T; ++i) {
-            s.B1[(size_t)(i + 1) * ld + l] = fmaf(ww[i], cum, s.B1[(size_t)(i + 1) * ld + l]);
-            cum = fmaf(vv[i], s.B2[(size_t)(i + 1) * ld + l], cum);
+        const float* __restrict__ xq = s.B2 + ld + l;  // X_q(i, l) at xq[i*ld]
+        float* __restrict__ cp = s.B1 + ld + l;        // C'(i, l) at cp[i*ld]
+        for (int sx0 = 0; sx0 < S; sx0 += 4) {
+          const int ns = (S - sx0 < 4) ? S - sx0 : 4;
+          float cum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          for (int i0 = l; i0 < T; i0 += 8) {
+            float xv[8], base[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int i = i0 + e;
+              xv[e] = (i < T) ? xq[(size_t)i * ld] : 0.0f;
+              base[e] = (sx0 == 0) ? 0.0f : ((i < T) ? cp[(size_t)i * ld] : 0.0f);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int i = i0 + e;
+              if (i < T) {
+                float cv = (sx0 == 0) ? s.pd[i] * xv[e] : base[e];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if (q < ns) {
+                    cv = fmaf(s.w[(size_t)(sx0 + q) * TP + i], cum[q], cv);
+                    cum[q] = fmaf(s.v[(size_t)(sx0 + q) * TP + i], xv[e], cum[q]);
+                  }
+                }
+                cp[(size_t)i * ld] = cv;
+              }
+            }
           }
         }
       }
       __syncthreads();
       phase_mark(P, 25);
-      const double t2 = SLOT ? contract_block_staged<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg)
+      const double t2 = gm ? contract_gemm<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg)
+                        : SLOT ? contract_block_staged<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg)
                                  : contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, G.all);
       phase_mark(P, 26);
       const double gq = block_sum(0.5 * (double)g * t1 + t2, s.red);
