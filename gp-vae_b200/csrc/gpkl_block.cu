@@ -91,6 +91,7 @@ __device__ __forceinline__ void grp_sync(const Grp& g) {
 constexpr int STG_FLOATS = 8192;                      // two stages of the largest staged phase (contraction: 2*32*128)
 constexpr int GM_KC = 16;                             // GEMM phase: contraction steps per stage
 constexpr int GM_SLD = 192;                           // floats per staged step: 128 A values | 64 B values
+constexpr int GM_NS = 4;                              // pipeline depth (4 x 12 KB <= stg + pan)
 constexpr int NBL = 64;                               // large-T panel width (columns / rows per GEMM phase)
 constexpr int GEMM_TMAX = 512;                        // the shared-memory panel fits up to this T
 constexpr int GEMM_TMIN = 256;                        // below this the per-panel overheads outweigh the GEMM phase
@@ -133,9 +134,9 @@ struct Sm {
     if (slot) {  // large T: matrices in this CTA's workspace slot; operand slabs staged through stg
       B1 = slot;
       B2 = slot + L.buf();
-      stg = base; base += STG_FLOATS;
       wide = base;  // 64-wide panel (Cholesky) / 64-row block (solve) of the GEMM path
       if (L.gemm(false)) base += (size_t)NBL * L.ld;
+      stg = base; base += STG_FLOATS;  // immediately followed by pan: GEMM phases stage through stg + pan
     } else {
       B1 = base; base += L.buf();
       B2 = base; base += L.buf();
@@ -405,39 +406,43 @@ __device__ __forceinline__ void gemm_tile_128x64(float (&acc)[8][4], const float
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int nch = (k1 - k0 + GM_KC - 1) / GM_KC;
   auto issue = [&](int c) {
-    float* buf = stg + (c & 1) * (GM_KC * GM_SLD);
+    float* buf = stg + (c % GM_NS) * (GM_KC * GM_SLD);
+    if (c < nch) {
 #pragma unroll
-    for (int rnd = 0; rnd < 3; ++rnd) {
-      const int q = tid + 256 * rnd;  // 16 steps x 48 float4
-      const int kk = q / 48, e = q - kk * 48;
-      const int k = k0 + c * GM_KC + kk;
-      if (e < 32) {
-        const int row = arow0 + 4 * e;
-        int valid = (k < k1 && row < arow_lim) ? 4 : 0;
-        if (A_TRI && valid) {
-          const int v = k - row + 1;
-          valid = v < 0 ? 0 : (v > 4 ? 4 : v);
+      for (int rnd = 0; rnd < 3; ++rnd) {
+        const int q = tid + 256 * rnd;  // 16 steps x 48 float4
+        const int kk = q / 48, e = q - kk * 48;
+        const int k = k0 + c * GM_KC + kk;
+        if (e < 32) {
+          const int row = arow0 + 4 * e;
+          int valid = (k < k1 && row < arow_lim) ? 4 : 0;
+          if (A_TRI && valid) {
+            const int v = k - row + 1;
+            valid = v < 0 ? 0 : (v > 4 ? 4 : v);
+          }
+          cp_async16(buf + kk * GM_SLD + 4 * e, valid ? Ag + (size_t)k * lda + row : Ag, 4 * valid);
+        } else {
+          const int col = bcol0 + 4 * (e - 32);
+          int valid = (k < k1 && col < bcol_lim) ? 4 : 0;
+          if (B_TRI && valid) {
+            const int v = k - col + 1;
+            valid = v < 0 ? 0 : (v > 4 ? 4 : v);
+          }
+          cp_async16(buf + kk * GM_SLD + 128 + 4 * (e - 32), valid ? Bg + (size_t)k * ldb + col : Bg, 4 * valid);
         }
-        cp_async16(buf + kk * GM_SLD + 4 * e, valid ? Ag + (size_t)k * lda + row : Ag, 4 * valid);
-      } else {
-        const int col = bcol0 + 4 * (e - 32);
-        int valid = (k < k1 && col < bcol_lim) ? 4 : 0;
-        if (B_TRI && valid) {
-          const int v = k - col + 1;
-          valid = v < 0 ? 0 : (v > 4 ? 4 : v);
-        }
-        cp_async16(buf + kk * GM_SLD + 128 + 4 * (e - 32), valid ? Bg + (size_t)k * ldb + col : Bg, 4 * valid);
       }
     }
-    cp_async_commit();
+    cp_async_commit();  // (possibly empty) group: keeps the group count uniform
   };
-  if (nch > 0) issue(0);
+  // GM_NS-deep pipeline, one barrier per stage: the barrier of iteration c publishes stage c and also guarantees
+  // that every thread is done with stage c-1, whose buffer the copy issued right after it overwrites.
+#pragma unroll
+  for (int c = 0; c < GM_NS - 1; ++c) issue(c);
   for (int c = 0; c < nch; ++c) {
-    if (c + 1 < nch) issue(c + 1);
-    else cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<GM_NS - 2>();
     __syncthreads();
-    const float* buf = stg + (c & 1) * (GM_KC * GM_SLD);
+    issue(c + GM_NS - 1);
+    const float* buf = stg + (c % GM_NS) * (GM_KC * GM_SLD);
 #pragma unroll
     for (int kk = 0; kk < GM_KC; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(buf + kk * GM_SLD + 8 * ty);
@@ -450,8 +455,9 @@ __device__ __forceinline__ void gemm_tile_128x64(float (&acc)[8][4], const float
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) acc[r][cc] = fmaf(SGN > 0 ? a[r] : -a[r], b[cc], acc[r][cc]);
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
+  __syncthreads();  // the staging area (stg + pan) is free again
 }
 
 // Large-T Cholesky: 64-column panels.  GEMM phase: panel = K - L[:, 0:J0] L[J0:J0+64, 0:J0]^T into the shared-memory
@@ -634,7 +640,8 @@ __device__ __noinline__ double contract_block(const float* __restrict__ Ub, cons
 // Large-T contraction on the staged GEMM tile: 128 (k) x 64 (l) output blocks, contraction over the row index i
 // of the two row-major lower triangles (both zero-filled above their diagonals while staging), kernel derivative
 // in the epilogue.
-template <int KERNEL>
+// SYM: U == V, so (U^T V) is symmetric: only blocks that contain entries with k > l are computed, weighted twice.
+template <int KERNEL, bool SYM>
 __device__ __noinline__ double contract_gemm(const float* __restrict__ Ub, const float* __restrict__ Vb, const Lay& L, int T,
                                              const float* __restrict__ ts, float ell, float sig, float* __restrict__ stg) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -644,6 +651,7 @@ __device__ __noinline__ double contract_gemm(const float* __restrict__ Ub, const
   double total = 0.0;
   for (int bp = 0; bp < nkb * nlb; ++bp) {
     const int kb0 = (bp % nkb) * 128, lb0 = (bp / nkb) * 64;
+    if (SYM && lb0 >= kb0 + 127) continue;  // no entry with k > l in this block
     float acc[8][4];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -664,7 +672,8 @@ __device__ __noinline__ double contract_gemm(const float* __restrict__ Ub, const
         const int k = kb0 + 8 * ty + r, l = lb0 + 4 * tx + c;
         const float dt = tk[r] - tl[c];
         const float dk = kc.dell(dt, kc.val(dt));
-        part = fmaf((k < T && l < T && k != l) ? acc[r][c] : 0.0f, dk, part);
+        const bool on = SYM ? (k < T && l < k) : (k < T && l < T && k != l);
+        part = fmaf(on ? acc[r][c] : 0.0f, SYM ? 2.0f * dk : dk, part);
       }
     total += (double)part;
   }
@@ -928,7 +937,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
       }
       phase_mark(P, 20);
       if (POST == GPKL_POST_GP)
-        t1 = gm ? contract_gemm<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, s.stg)
+        t1 = gm ? contract_gemm<KERNEL, true>(s.B1, s.B1, L, T, s.ts, lq, sig, s.stg)
            : SLOT ? contract_block_staged<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, s.stg)
                       : contract_block<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, G.chain);
       phase_mark(P, 21);
@@ -1003,7 +1012,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
       }
       __syncthreads();
       phase_mark(P, 25);
-      const double t2 = gm ? contract_gemm<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg)
+      const double t2 = gm ? contract_gemm<KERNEL, false>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg)
                         : SLOT ? contract_block_staged<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg)
                                  : contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, G.all);
       phase_mark(P, 26);
