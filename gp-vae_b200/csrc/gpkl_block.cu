@@ -94,7 +94,7 @@ constexpr int GM_SLD = 192;                           // floats per staged step:
 constexpr int GM_NS = 4;                              // pipeline depth (4 x 12 KB <= stg + pan)
 constexpr int NBL = 64;                               // large-T panel width (columns / rows per GEMM phase)
 constexpr int GEMM_TMAX = 512;                        // the shared-memory panel fits up to this T
-constexpr int GEMM_TMIN = 256;                        // below this the per-panel overheads outweigh the GEMM phase
+constexpr int GEMM_TMIN = 144;                        // below this the per-panel overheads outweigh the GEMM phase
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
