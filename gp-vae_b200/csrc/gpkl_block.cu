@@ -88,10 +88,14 @@ __device__ __forceinline__ void grp_sync(const Grp& g) {
 }
 
 // Workspace variant (T > ~144): operand slabs are staged global -> shared with cp.async, double buffered.
-constexpr int STG_FLOATS = 8192;                      // two stages of the largest staged phase (contraction: 2*32*128)
+// staging floats: >= 2*32*128 for the 64x64 staged contraction, and stg + pan (16*(TP+4) floats, TP >= 160 on the
+// GEMM path) must hold the GM_NS stages of the GEMM tile: 9728 + 16*164 = 12352 >= 4*16*192 = 12288
+constexpr int STG_FLOATS = 9728;
 constexpr int GM_KC = 16;                             // GEMM phase: contraction steps per stage
 constexpr int GM_SLD = 192;                           // floats per staged step: 128 A values | 64 B values
-constexpr int GM_NS = 4;                              // pipeline depth (4 x 12 KB <= stg + pan)
+constexpr int GM_NS = 4;                              // pipeline depth (4 x 12 KB <= stg + pan, see STG_FLOATS)
+static_assert(STG_FLOATS + 16 * 164 >= GM_NS * GM_KC * GM_SLD, "staging area too small for the GEMM pipeline");
+static_assert(STG_FLOATS >= 2 * 32 * 128, "staging area too small for the staged contraction");
 constexpr int NBL = 64;                               // large-T panel width (columns / rows per GEMM phase)
 constexpr int GEMM_TMAX = 512;                        // the shared-memory panel fits up to this T
 constexpr int GEMM_TMIN = 144;                        // below this the per-panel overheads outweigh the GEMM phase
