@@ -344,6 +344,63 @@ extern "C" int gpkl_fp32_peak_launch(float* sink, int32_t iters, double* flops, 
   return cudaGetLastError() == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
 }
 
+// ---- reconstruction term ------------------------------------------------------------------------
+namespace {
+struct ReconWs {
+  int64_t* offsets;
+  double* partials;
+  size_t total;
+};
+ReconWs plan_recon(int B, void* base) {
+  ReconWs w;
+  unsigned char* b = static_cast<unsigned char*>(base);
+  size_t off = 0;
+  w.offsets = reinterpret_cast<int64_t*>(b + off);
+  off += align_up(((size_t)B + 1) * sizeof(int64_t));
+  w.partials = reinterpret_cast<double*>(b + off);
+  off += align_up((size_t)kNumSMs * 8 * sizeof(double));
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t gpkl_recon_workspace_bytes(int32_t B) { return B < 0 ? 0 : plan_recon(B, nullptr).total; }
+
+extern "C" int gpkl_recon_forward(int32_t B, int32_t F, int32_t S, int64_t total_T, const float* x, const float* x_decode,
+                                  const int32_t* lengths, double* recon, void* workspace, size_t ws_bytes, void* stream) {
+  if (B < 0 || F <= 0 || S < 1 || total_T < 0) return GPKL_ERR_DESC;
+  if (!recon) return GPKL_ERR_NULL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0 || total_T == 0) {
+    cudaMemsetAsync(recon, 0, sizeof(double), st);
+    return GPKL_OK;
+  }
+  if (!x || !x_decode || !lengths || !workspace) return GPKL_ERR_NULL;
+  const ReconWs w = plan_recon(B, workspace);
+  if (ws_bytes < w.total) return GPKL_ERR_WORKSPACE;
+  offsets_kernel<<<1, 1024, 0, st>>>(lengths, B, w.offsets);
+  note_launch();
+  const cudaError_t e = launch_recon_fwd(x, x_decode, reinterpret_cast<const long long*>(w.offsets), B, F, S,
+                                         (long long)S * total_T, w.partials, recon, st);
+  return e == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
+}
+
+extern "C" int gpkl_recon_backward(int32_t B, int32_t F, int32_t S, int64_t total_T, const float* x,
+                                   const float* x_decode, const int32_t* lengths, const double* g_recon,
+                                   float* g_x_decode, void* workspace, size_t ws_bytes, void* stream) {
+  if (B < 0 || F <= 0 || S < 1 || total_T < 0) return GPKL_ERR_DESC;
+  if (B == 0 || total_T == 0) return GPKL_OK;
+  if (!x || !x_decode || !lengths || !g_x_decode || !workspace) return GPKL_ERR_NULL;
+  const ReconWs w = plan_recon(B, workspace);
+  if (ws_bytes < w.total) return GPKL_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  offsets_kernel<<<1, 1024, 0, st>>>(lengths, B, w.offsets);
+  note_launch();
+  const cudaError_t e = launch_recon_bwd(x, x_decode, reinterpret_cast<const long long*>(w.offsets), B, F, S,
+                                         (long long)S * total_T, g_recon, g_x_decode, st);
+  return e == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
+}
+
 // ---- host-buffer step ---------------------------------------------------------------------------
 namespace {
 struct Staging {

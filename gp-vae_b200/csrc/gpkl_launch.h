@@ -34,4 +34,11 @@ bool block_tier_resident(const GpklDesc& d);
 size_t block_slot_floats(const GpklDesc& d);  // 0 when resident
 cudaError_t launch_block(const Params& P, bool backward, cudaStream_t st);
 
+// reconstruction term (gpkl_recon.cu), SURVEY.md S8(f) row 1
+int recon_grid(long long rows);
+cudaError_t launch_recon_fwd(const float* x, const float* xd, const long long* off, int B, int F, int S, long long rows,
+                             double* partials, double* out, cudaStream_t st);
+cudaError_t launch_recon_bwd(const float* x, const float* xd, const long long* off, int B, int F, int S, long long rows,
+                             const double* g_recon, float* g_xd, cudaStream_t st);
+
 }  // namespace gpkl

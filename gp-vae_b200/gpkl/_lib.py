@@ -14,7 +14,8 @@ FLAG_GRAD_ELL_P = 1
 # every symbol include/gpkl.h declares (tests check the library exports exactly these)
 SYMBOLS = ("gpkl_version", "gpkl_strerror", "gpkl_workspace_bytes", "gpkl_forward", "gpkl_backward",
            "gpkl_step_host_bytes", "gpkl_step_host", "gpkl_launch_count", "gpkl_profile_enable",
-           "gpkl_profile_read", "gpkl_fp32_peak_launch")
+           "gpkl_profile_read", "gpkl_fp32_peak_launch", "gpkl_recon_workspace_bytes", "gpkl_recon_forward",
+           "gpkl_recon_backward")
 
 
 class GpklDesc(ctypes.Structure):
@@ -60,6 +61,13 @@ def lib():
                                     ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)]
     L.gpkl_fp32_peak_launch.restype = i32
     L.gpkl_fp32_peak_launch.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_double), vp]
+    i64 = ctypes.c_int64
+    L.gpkl_recon_workspace_bytes.restype = sz
+    L.gpkl_recon_workspace_bytes.argtypes = [ctypes.c_int32]
+    L.gpkl_recon_forward.restype = i32
+    L.gpkl_recon_forward.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, i64, vp, vp, vp, vp, vp, sz, vp]
+    L.gpkl_recon_backward.restype = i32
+    L.gpkl_recon_backward.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, i64, vp, vp, vp, vp, vp, vp, sz, vp]
     _lib = L
     return L
 

@@ -211,3 +211,57 @@ class HostStep:
         outs = [z, klp, self.kl_sum, gm, self.g_ell_q if self.posterior == "gp" else None, self.g_ell_p, ga]
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in outs if t is not None)
         return self
+
+
+# ---- reconstruction term + beta-weighted loss ---------------------------------------------
+def _recon_ws(B, device):
+    n = _lib.lib().gpkl_recon_workspace_bytes(int(B))
+    key = ("recon", device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 1 << 16), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws, n
+
+
+class BernoulliRecon(torch.autograd.Function):
+    """recon(x, x_decode) of Full_GP_VAE_dynamic_time.py:349-356 as one streaming CUDA pass (float64 scalar)."""
+
+    @staticmethod
+    def forward(ctx, x, x_decode, lengths, S):
+        if not x.is_cuda:
+            raise RuntimeError("gpkl: tensors must live on a CUDA device (there is no CPU implementation)")
+        total_T, F = x.shape
+        B = lengths.shape[0]
+        assert x_decode.shape == (S * total_T, F) and lengths.dtype == torch.int32
+        assert x.dtype == torch.float32 and x_decode.dtype == torch.float32 and x.is_contiguous() and x_decode.is_contiguous()
+        out = torch.empty((), dtype=torch.float64, device=x.device)
+        ws, n = _recon_ws(B, x.device)
+        _lib.check(_lib.lib().gpkl_recon_forward(B, F, S, total_T, _ptr(x), _ptr(x_decode), _ptr(lengths), _ptr(out),
+                                                 _ptr(ws), n, _stream(x.device)))
+        ctx.save_for_backward(x, x_decode, lengths)
+        ctx.S = S
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, x_decode, lengths = ctx.saved_tensors
+        total_T, F = x.shape
+        B = lengths.shape[0]
+        gx = torch.empty_like(x_decode)
+        ws, n = _recon_ws(B, x.device)
+        g = g.to(torch.float64).reshape(()).contiguous()
+        _lib.check(_lib.lib().gpkl_recon_backward(B, F, ctx.S, total_T, _ptr(x), _ptr(x_decode), _ptr(lengths), _ptr(g),
+                                                  _ptr(gx), _ptr(ws), n, _stream(x.device)))
+        return None, gx, None, None
+
+
+def bernoulli_recon(x, x_decode, lengths, S=1):
+    """sum_recon_loss of the reference (Full_GP_VAE_dynamic_time.py:349-356): Bernoulli NLL with the 1e-10 guards,
+    mean over the S samples, sum over time and batch; differentiable in x_decode."""
+    return BernoulliRecon.apply(x, x_decode, lengths, int(S))
+
+
+def elbo_loss(x, x_decode, lengths, kl_sum, beta=1.0, S=1):
+    """loss = recon + beta * KL  (Full_GP_VAE_dynamic_time.py:358-360; beta warm-up: syndata/GP_VAE_syn_data.py:361-364)."""
+    return bernoulli_recon(x, x_decode, lengths, S) + beta * kl_sum

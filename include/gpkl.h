@@ -110,6 +110,19 @@ int gpkl_step_host(const GpklDesc* desc, const float* mean_host, const float* ti
                    float* g_ell_q_host, float* g_ell_p_host, float* g_aux_host,
                    void* staging, size_t staging_bytes, void* stream);
 
+/* ---- reconstruction term (first "next" row after the path) ------------------------------------
+ * recon = sum over rows of mean_s  -sum_f [ x log(1e-10 + xd) + (1-x) log(1 - xd + 1e-10) ]      (float64 scalar)
+ * replaces src/Models/Full_GP_VAE_dynamic_time.py:323-327 (x tiled over the S samples) and :349-356; the loss is
+ * recon + beta * kl_sum (:360).  x [total_T, F] f32 targets, x_decode [S*total_T, F] f32 in the layout of z (per
+ * sequence S blocks of [T_b, F]); lengths [B] i32.  Backward: g_x_decode = d(g_recon*recon)/d x_decode, g_recon a
+ * DEVICE f64 scalar (NULL == 1).  Workspace: gpkl_recon_workspace_bytes(B). */
+size_t gpkl_recon_workspace_bytes(int32_t B);
+int gpkl_recon_forward(int32_t B, int32_t F, int32_t S, int64_t total_T, const float* x, const float* x_decode,
+                       const int32_t* lengths, double* recon, void* workspace, size_t ws_bytes, void* stream);
+int gpkl_recon_backward(int32_t B, int32_t F, int32_t S, int64_t total_T, const float* x, const float* x_decode,
+                        const int32_t* lengths, const double* g_recon, float* g_x_decode, void* workspace,
+                        size_t ws_bytes, void* stream);
+
 /* ---- measurement hooks (bench.py; not part of the data path) ------------------------------------
  * These are the only process-global state in the library and are not thread safe.
  * gpkl_launch_count: kernels this library has launched since load (bench.py's gpu_launches).

@@ -144,6 +144,27 @@ def run_diag(name):
           kl_sum=kl_sum, kl_pairs=kl.reshape(-1), g_mean=mean.grad, g_logvar=logvar.grad)
 
 
+def run_recon(name):
+    """Reconstruction term + loss: the reference has them inline in main() (Full_GP_VAE_dynamic_time.py:323-327,
+    :349-356, :360), so those SOURCE LINES are read from the reference at generation time and executed under the stub
+    (nothing of the reference is copied into this repository)."""
+    import textwrap
+    src = open(os.path.join(REF, "Full_GP_VAE_dynamic_time.py")).read().split("\n")
+    code = textwrap.dedent("\n".join(src[322:327] + src[348:356] + [src[359]]))
+    g = torch.Generator().manual_seed(21)
+    lengths = [4, 2, 5]
+    F, S = 7, 2
+    total = sum(lengths)
+    x = (torch.rand(total, F, generator=g) < 0.3).float()
+    x_decode = (torch.rand(S * total, F, generator=g) * 0.96 + 0.02).clone().requires_grad_(True)
+    ns = dict(tf=tf, x=x, sequence_sizes_placeholder=torch.tensor(lengths, dtype=torch.int32), number_samples=S,
+              x_decode=x_decode, beta=0.7, sum_gp_kl=torch.tensor(12.5, dtype=torch.float64))
+    exec(code, ns)
+    ns["sum_recon_loss"].backward()
+    _save(name, variant="recon", S=S, lengths=np.asarray(lengths, np.int32), x=x, x_decode=x_decode,
+          recon=ns["sum_recon_loss"], loss=ns["loss"], beta=0.7, kl=12.5, g_x_decode=x_decode.grad)
+
+
 def main():
     torch.manual_seed(0)
     # G1 -- SURVEY.md Appendix B golden case (regular grid, B=3 D=4 T=6)
@@ -178,6 +199,8 @@ def main():
               torch.tensor([0.8, 1.0, 1.7]), torch.tensor([1.0, 1.4, 0.9]), seed=14)
     # G2 -- V2 diagonal posterior
     run_diag("g2_v2_diag")
+    # G6 -- reconstruction term and beta-weighted loss (next row after the path)
+    run_recon("g6_recon_loss")
 
 
 if __name__ == "__main__":

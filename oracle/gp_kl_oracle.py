@@ -218,6 +218,21 @@ def gp_prior_kl_grads(mean, times, lengths, ell_q, ell_p, eps, g_z, g_kl_sum=1.0
     return out, grads
 
 
+def bernoulli_recon(x, x_decode, lengths, S=1):
+    """sum_recon_loss of the reference (Full_GP_VAE_dynamic_time.py:323-327 tiles x over the samples; :349 the
+    Bernoulli NLL per row in float32; :350-356 float64, mean over samples, sum over time and batch).
+    x [sum_T, F] f32, x_decode [S*sum_T, F] f32 laid out like z (per sequence S blocks of [T_b, F])."""
+    lengths_l = [int(a) for a in lengths.tolist()]
+    rows = []
+    off = 0
+    for T in lengths_l:
+        rows += [x[off:off + T]] * S
+        off += T
+    x_tile = torch.cat(rows, 0) if rows else x[:0]
+    rec = -(x_tile * torch.log(1e-10 + x_decode) + (1.0 - x_tile) * torch.log(1.0 - x_decode + 1e-10)).sum(1)
+    return rec.to(torch.float64).sum() / S   # mean over the S samples of every (sequence, time) row, then the sum
+
+
 def gp_kl_div_numpy(m, Kq, Kp):
     """Single-pair numpy float64 transcription of gp_kl_div (Full_GP_VAE_dynamic_time.py:242-260),
     independent of torch -- second opinion for the golden tests."""

@@ -28,7 +28,7 @@ def load_golden(name):
             out[k] = str(v)
         elif v.ndim == 0 and k in ("S",):
             out[k] = int(v)
-        elif v.ndim == 0 and k in ("noise",):
+        elif v.ndim == 0 and k in ("noise", "beta", "kl"):
             out[k] = float(v)
         else:
             out[k] = torch.from_numpy(v)

@@ -107,3 +107,14 @@ def test_oracle_gradcheck_fd(posterior, kernel):
             fd = (loss(*args_p) - loss(*args_m)) / (2 * h)
             an = float(grads[key].reshape(-1)[j])
             assert abs(fd - an) < 1e-5 * max(1.0, abs(an)), (key, j, fd, an)
+
+
+def test_recon_loss_matches_reference_lines():
+    """G6: the reference's inline reconstruction/loss lines (dyn:323-327, :349-356, :360) executed under the stub."""
+    g = load_golden("g6_recon_loss")
+    xd = g["x_decode"].clone().requires_grad_(True)
+    rec = orc.bernoulli_recon(g["x"], xd, g["lengths"], g["S"])
+    rec.backward()
+    assert abs(float(rec) - float(g["recon"])) < 1e-12 * abs(float(g["recon"]))
+    assert abs(float(rec) + g["beta"] * g["kl"] - float(g["loss"])) < 1e-12 * abs(float(g["loss"]))
+    assert rel_err(xd.grad, g["g_x_decode"]) < 1e-6
