@@ -17,6 +17,7 @@ OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "gpkl", "libgpkl.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
+FLAGS += os.environ.get("GPKL_EXTRA_NVCC_FLAGS", "").split()  # debug builds only, e.g. -DGPKL_PANEL_TRACE
 
 # warp tier instantiations: (lanes per pair, rows per lane)
 WARP_CFGS = [(8, 1), (16, 1), (32, 1), (16, 3), (32, 2)]

@@ -30,6 +30,19 @@ namespace {
 
 constexpr int NB = 16;
 
+#ifdef GPKL_PANEL_TRACE  // debug build only (tools/phase_trace.py): per-phase cycles of the panel loops
+// Every thread keeps its own counters in registers (a thread-0-only probe makes the warp diverge, and the
+// shuffles of diag_factor then take the compiler's slow divergent path); thread 0 of CTA 0 publishes them.
+__device__ long long g_ptrace[8];
+#define PT_DECL long long pt_t0 = clock64(), pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PT_ADD(slot) do { const long long pt_t1 = clock64(); pt_acc[slot] += pt_t1 - pt_t0; pt_t0 = pt_t1; } while (0)
+#define PT_FLUSH do { if (blockIdx.x == 0 && g.tid == 0 && g.bar <= 1) for (int i_ = 0; i_ < 8; ++i_) g_ptrace[i_] += pt_acc[i_]; } while (0)
+#else
+#define PT_DECL
+#define PT_ADD(slot)
+#define PT_FLUSH
+#endif
+
 template <int SGN>
 __device__ __forceinline__ void tile_fma(float (&acc)[4][4], const float4& u4, const float4& v4) {
   const float u[4] = {SGN > 0 ? u4.x : -u4.x, SGN > 0 ? u4.y : -u4.y, SGN > 0 ? u4.z : -u4.z, SGN > 0 ? u4.w : -u4.w};
@@ -235,6 +248,7 @@ __device__ __noinline__ void chol_panels(float* __restrict__ Bm, int ldm, int c_
   // rows beyond the last real row are identity padding and decouple: only panels that contain real rows matter
   const int Tact = (T + NB - 1) / NB * NB;
   const int rows_end = extra ? TP + 4 : Tact;
+  PT_DECL;
   for (int j0 = c_begin; j0 < c_end; j0 += NB) {
     const int cb = j0 + 4 * cg;
     for (int rb = j0 + 4 * rg; rb < rows_end; rb += 4 * NRG) {
@@ -284,9 +298,13 @@ __device__ __noinline__ void chol_panels(float* __restrict__ Bm, int ldm, int c_
       for (int c = 0; c < 4; ++c)
         *reinterpret_cast<float4*>(pan + (size_t)(4 * cg + c) * ld + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
     }
+    PT_ADD(0);
     grp_sync<DUAL>(g);
+    PT_ADD(1);
     if (tid < 32) diag_factor(Bm, ldm, j0, T, pan, ld, dg, rdg, bad);
+    PT_ADD(2);
     grp_sync<DUAL>(g);
+    PT_ADD(1);
     // rows below the diagonal block: L[i, j0:j0+16] = pan[i, :] L_dd^-T, one row per thread
     const int nbelow = Tact - j0 - NB;
     const int nrows = nbelow + (extra ? 1 : 0);
@@ -299,8 +317,11 @@ __device__ __noinline__ void chol_panels(float* __restrict__ Bm, int ldm, int c_
 #pragma unroll
       for (int c = 0; c < 16; ++c) Bm[(size_t)(j0 + c) * ldm + i] = b[c];
     }
+    PT_ADD(3);
     grp_sync<DUAL>(g);
+    PT_ADD(1);
   }
+  PT_FLUSH;
   // identity padding: diag entries for rows in [Tact, TP) (only dg / rdg are consulted for them)
   if (c_end >= Tact) {
     for (int i = Tact + tid; i < TP; i += NT) { dg[i] = 1.0f; rdg[i] = 1.0f; }
@@ -331,6 +352,7 @@ __device__ __noinline__ float solve_rows(const float* __restrict__ Lb, const flo
   const int tid = g.tid, NT = g.nt;
   const int ld = L.ld;
   float ssq = 0.0f;
+  PT_DECL;
   for (int i0 = r_begin; i0 < r_end; i0 += NB) {
     const int ntile = 4 * (i0 / 4 + 4);
     for (int id = tid; id < ntile; id += NT) {
@@ -367,7 +389,9 @@ __device__ __noinline__ float solve_rows(const float* __restrict__ Lb, const flo
       for (int r = 0; r < 4; ++r)
         *reinterpret_cast<float4*>(pan + (size_t)(4 * rt + r) * ld + cb) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
     }
+    PT_ADD(4);
     grp_sync<DUAL>(g);
+    PT_ADD(5);
     // diagonal block: X[i0:i0+16, col] = L_dd^-1 staged[:, col], one column per thread
     for (int col = tid; col < i0 + NB; col += NT) {
       float b[16];
@@ -383,8 +407,11 @@ __device__ __noinline__ float solve_rows(const float* __restrict__ Lb, const flo
         }
       }
     }
+    PT_ADD(6);
     grp_sync<DUAL>(g);
+    PT_ADD(5);
   }
+  PT_FLUSH;
   return ssq;
 }
 
@@ -878,6 +905,10 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
       ldq = block_sum(ldq, s.red);
     }
     phase_mark(P, 6);
+#ifdef GPKL_PANEL_TRACE
+    if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0)
+      for (int i = 0; i < 8; ++i) { P.dbg[32 + i] = g_ptrace[i]; g_ptrace[i] = 0; }
+#endif
     if (threadIdx.x == 0) {
       P.kl_pairs[p] = (float)(0.5 * part);
       if (P.logdets) { P.logdets[2 * p] = (float)ldp; P.logdets[2 * p + 1] = (float)ldq; }
@@ -1024,6 +1055,10 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
       phase_mark(P, 27);
       if (threadIdx.x == 0) P.gq_pairs[p] = (float)gq;
     }
+#ifdef GPKL_PANEL_TRACE
+    if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0)
+      for (int i = 0; i < 8; ++i) { P.dbg[40 + i] = g_ptrace[i]; g_ptrace[i] = 0; }
+#endif
     if (threadIdx.x == 0 && bad && P.status) atomicAdd(P.status, 1);
   }
 }

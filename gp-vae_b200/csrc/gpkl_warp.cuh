@@ -28,6 +28,35 @@ namespace {
 
 constexpr int WPC = 4;  // warps per CTA
 
+// Instruction-fetch lockstep (EXPERIMENT, off by default).  The fully unrolled phases below are straight-line
+// code of 100-300 KB that every warp executes exactly once; ncu shows the warps stalled on no_instruction at
+// the first instruction of almost every 128-byte line.  Hypothesis tested: a CTA barrier every few hundred
+// instructions keeps the WPC warps inside the same window of the 32 KB instruction cache so that one fetched
+// line serves all of them.  Measured on c2 (T=48): no change at all (fwd 0.416 ms, bwd 0.806 ms either way) --
+// the stall is the per-warp demand-fetch latency of each line, not L2 instruction bandwidth; what helps is
+// fewer instructions (coarser guards, packed FFMA2) and more resident warps.
+// nl = number of live threads in the CTA (warps with no work have exited); barrier 1 is used for this only.
+#ifndef GPKL_LOCKSTEP
+#define GPKL_LOCKSTEP 0  // barrier every this many unrolled column steps; 0 disables
+#endif
+__device__ __forceinline__ void lockstep(int nl) {
+  if (GPKL_LOCKSTEP > 0) asm volatile("bar.sync 1, %0;" ::"r"(nl));
+}
+template <int STEP>
+__device__ __forceinline__ void lockstep_at(int idx, int nl) {  // idx is a compile-time value after unrolling
+  if (GPKL_LOCKSTEP > 0 && (idx % (STEP * (GPKL_LOCKSTEP > 0 ? GPKL_LOCKSTEP : 1))) == 0) lockstep(nl);
+}
+// Count the live threads of the CTA (called by every thread before any warp exits).
+__device__ __forceinline__ int live_threads(bool warp_has_work) {
+  if (GPKL_LOCKSTEP == 0) return 0;
+  __shared__ int s_live;
+  if (threadIdx.x == 0) s_live = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && warp_has_work) atomicAdd(&s_live, 32);
+  __syncthreads();
+  return s_live;
+}
+
 // Packed lower-triangular storage with 16-byte aligned rows: row i has capacity 4*(i/4+1) floats.
 __host__ __device__ constexpr int poff(int i) { return 8 * (i >> 2) * ((i >> 2) + 1) + (i & 3) * 4 * ((i >> 2) + 1); }
 
@@ -36,6 +65,8 @@ struct Geo {
   static constexpr int TM = LP * R;
   static constexpr int PK = poff(TM);
   static constexpr int G = 32 / LP;  // groups (pairs) per warp
+  // packed FFMA2 (see fma2): PACK = false selects the scalar-FMA form of the same arithmetic
+  static constexpr bool PACK = true;
   // per-group shared floats: 2 packed buffers, 2 column buffers, ts, dgp, dgq, dinv, as, pd + 3*S*TM
   static constexpr int fixed_floats() { return 2 * PK + 2 * TM + 6 * TM; }
 };
@@ -70,11 +101,12 @@ struct Smem {
 // Rows of K(t, ell) (lower triangle incl. diagonal, zeros above; identity on padded rows/cols).
 template <int LP, int R, int KERNEL>
 __device__ __forceinline__ void build_rows(float (&a)[R][LP * R], const float (&trow)[R], const float* __restrict__ ts,
-                                           int lig, int T, int Tw, float ell, float sig, float noise) {
+                                           int lig, int T, int Tw, float ell, float sig, float noise, int nl) {
   constexpr int TM = LP * R;
   const KernC<KERNEL> kc(ell, sig);
 #pragma unroll
   for (int k4 = 0; k4 < TM; k4 += 4) {
+    lockstep_at<4>(k4, nl);
     if (k4 < Tw) {
       const float4 t4 = *reinterpret_cast<const float4*>(ts + k4);
       const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
@@ -101,33 +133,48 @@ __device__ __forceinline__ void build_rows(float (&a)[R][LP * R], const float (&
 // Right-looking Cholesky on register rows.  col: 2*TM floats of shared memory (double buffered).
 template <int LP, int R>
 __device__ __forceinline__ void chol_rows(float (&a)[R][LP * R], int lig, int T, int Tw, float* __restrict__ col,
-                                          float* __restrict__ dg, int& bad) {
+                                          float* __restrict__ dg, int& bad, int nl) {
   constexpr int TM = LP * R;
 #pragma unroll
   for (int j = 0; j < TM; ++j) {
+    lockstep_at<1>(j, nl);
     if (j < Tw) {
       float* cb = col + (j & 1) * TM;
 #pragma unroll
       for (int jj = 0; jj < R; ++jj) cb[lig + LP * jj] = a[jj][j];
       __syncwarp();
       const float d = cb[j];
-      const float sd = sqrtf(d);
-      const float rs = 1.0f / sd;
+      float rs = rsqrtf(d);
+      rs = rs * fmaf(-0.5f * d, rs * rs, 1.5f);  // one Newton step: 1/sqrt(d) to ~1 ulp, branch-free
+      const float sd = d * rs;
       const float rd = rs * rs;
       if (j < T && !(d > 0.0f)) bad = 1;
       float s[R];
 #pragma unroll
       for (int jj = 0; jj < R; ++jj) s[jj] = (lig + LP * jj > j) ? a[jj][j] * rd : 0.0f;
+      float ns[R];
 #pragma unroll
-      for (int k4 = (j + 1) & ~3; k4 < TM; k4 += 4) {
-        if (k4 < Tw) {
-          const float4 c4 = *reinterpret_cast<const float4*>(cb + k4);
-          const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+      for (int jj = 0; jj < R; ++jj) ns[jj] = -s[jj];
+      // (the trailing update is guarded per 16 columns only: finer guards cost more in branches than the
+      //  skipped identity-padding columns save)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (k4 + e > j) {
+      for (int k16 = (j + 1) & ~15; k16 < TM; k16 += 16) {
+        if (k16 < Tw) {
 #pragma unroll
-              for (int jj = 0; jj < R; ++jj) a[jj][k4 + e] = fmaf(-s[jj], cv[e], a[jj][k4 + e]);
+          for (int q = 0; q < 4; ++q) {
+            const int k4 = k16 + 4 * q;
+            if (k4 < ((j + 1) & ~3) || k4 >= TM) continue;  // compile-time after unrolling
+            const float4 c4 = *reinterpret_cast<const float4*>(cb + k4);
+            const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) {
+              if (k4 + e > j) {  // both columns of the pair are trailing columns: one packed FMA per row
+#pragma unroll
+                for (int jj = 0; jj < R; ++jj) fma2<Geo<LP, R>::PACK>(a[jj][k4 + e], a[jj][k4 + e + 1], ns[jj], ns[jj], cv[e], cv[e + 1]);
+              } else if (k4 + e + 1 > j) {
+#pragma unroll
+                for (int jj = 0; jj < R; ++jj) a[jj][k4 + e + 1] = fmaf(ns[jj], cv[e + 1], a[jj][k4 + e + 1]);
+              }
             }
           }
         }
@@ -147,11 +194,12 @@ __device__ __forceinline__ void chol_rows(float (&a)[R][LP * R], int lig, int T,
 // b <- L^-1 b by a column sweep over register rows; solution also written to out[] (shared).
 template <int LP, int R>
 __device__ __forceinline__ void sweep_vec(const float (&a)[R][LP * R], float (&b)[R], int lig, int Tw,
-                                          const float* __restrict__ dinv, float* __restrict__ out) {
+                                          const float* __restrict__ dinv, float* __restrict__ out, int nl) {
   constexpr int TM = LP * R;
 #pragma unroll
   for (int k = 0; k < TM; ++k) {
-    if (k < Tw) {
+    lockstep_at<16>(k, nl);
+    {  // (no guard: padded rows/columns are identity and b is zero there, so the sweep is a no-op on them)
       const float cand = b[k / LP] * dinv[k];
       const float xk = __shfl_sync(0xffffffffu, cand, k % LP, LP);
 #pragma unroll
@@ -193,10 +241,11 @@ __device__ __forceinline__ void load_cols(float (&x)[R][LP * R], int lig, const 
 // In place forward substitution on register columns: x <- L^-1 x, L packed lower in shared memory.
 template <int LP, int R>
 __device__ __forceinline__ void solve_cols(float (&x)[R][LP * R], const float* __restrict__ Lpk,
-                                           const float* __restrict__ dinv, int Tw) {
+                                           const float* __restrict__ dinv, int Tw, int nl) {
   constexpr int TM = LP * R;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
+    lockstep_at<1>(i, nl);
     if (i < Tw) {
       const float* row = Lpk + poff(i);
       float acc[R][2];
@@ -207,10 +256,13 @@ __device__ __forceinline__ void solve_cols(float (&x)[R][LP * R], const float* _
         const float4 l4 = *reinterpret_cast<const float4*>(row + k4);
         const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (k4 + e < i) {
+        for (int e = 0; e < 4; e += 2) {
+          if (k4 + e + 1 < i) {  // both rows of the pair are already solved: one packed FMA per column
 #pragma unroll
-            for (int jj = 0; jj < R; ++jj) acc[jj][e & 1] = fmaf(lv[e], x[jj][k4 + e], acc[jj][e & 1]);
+            for (int jj = 0; jj < R; ++jj) fma2<Geo<LP, R>::PACK>(acc[jj][0], acc[jj][1], lv[e], lv[e + 1], x[jj][k4 + e], x[jj][k4 + e + 1]);
+          } else if (k4 + e < i) {
+#pragma unroll
+            for (int jj = 0; jj < R; ++jj) acc[jj][0] = fmaf(lv[e], x[jj][k4 + e], acc[jj][0]);
           }
         }
       }
@@ -223,6 +275,8 @@ __device__ __forceinline__ void solve_cols(float (&x)[R][LP * R], const float* _
 
 // Column c of a lower-triangular matrix (zeros for i < c) -> packed row TM-1-c, reversed in i, so that
 // other lanes can stream it back with aligned 128-bit broadcast loads at static register positions.
+// Element i sits at position (TM-1-i)^1: reversed by PAIRS, so that a loaded pair (q.x, q.y) lines up with the
+// register pair (x[even], x[odd]) of the packed FMA in contract_cols.
 __device__ __forceinline__ int poff_dyn(int i) {
   const int q = i >> 2, r = i & 3;
   return 8 * q * (q + 1) + 4 * r * (q + 1);
@@ -239,7 +293,7 @@ __device__ __forceinline__ void store_cols_rev(const float (&x)[R][LP * R], int 
     for (int g = 0; g < TM / 4; ++g) {
       if (4 * g <= ip)
         *reinterpret_cast<float4*>(row + 4 * g) =
-            make_float4(x[jj][TM - 1 - 4 * g], x[jj][TM - 2 - 4 * g], x[jj][TM - 3 - 4 * g], x[jj][TM - 4 - 4 * g]);
+            make_float4(x[jj][TM - 2 - 4 * g], x[jj][TM - 1 - 4 * g], x[jj][TM - 4 - 4 * g], x[jj][TM - 3 - 4 * g]);
     }
   }
 }
@@ -255,22 +309,22 @@ __device__ __forceinline__ float contract_cols(const float (&x)[R][LP * R], cons
   for (int l = 0; l < T; ++l) {
     const int ip = TM - 1 - l;
     const float* row = M + poff_dyn(ip);
-    float dot[R];
+    float dot[R], dot1[R];
 #pragma unroll
-    for (int jj = 0; jj < R; ++jj) dot[jj] = 0.0f;
+    for (int jj = 0; jj < R; ++jj) dot[jj] = dot1[jj] = 0.0f;
 #pragma unroll
     for (int g = 0; g < TM / 4; ++g) {
       if (4 * g <= ip) {
         const float4 q = *reinterpret_cast<const float4*>(row + 4 * g);
 #pragma unroll
         for (int jj = 0; jj < R; ++jj) {
-          dot[jj] = fmaf(q.x, x[jj][TM - 1 - 4 * g], dot[jj]);
-          dot[jj] = fmaf(q.y, x[jj][TM - 2 - 4 * g], dot[jj]);
-          dot[jj] = fmaf(q.z, x[jj][TM - 3 - 4 * g], dot[jj]);
-          dot[jj] = fmaf(q.w, x[jj][TM - 4 - 4 * g], dot[jj]);
+          fma2<Geo<LP, R>::PACK>(dot[jj], dot1[jj], q.x, q.y, x[jj][TM - 2 - 4 * g], x[jj][TM - 1 - 4 * g]);
+          fma2<Geo<LP, R>::PACK>(dot[jj], dot1[jj], q.z, q.w, x[jj][TM - 4 - 4 * g], x[jj][TM - 3 - 4 * g]);
         }
       }
     }
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) dot[jj] += dot1[jj];
     const float tl = ts[l];
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) {
@@ -321,6 +375,7 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
   Smem<LP, R> sm(smem_f + (size_t)gslot * group_floats, S);
   const int T = pi.T, lig = pi.lig;
   const int Tw = warp_max(T);
+  const int nl = live_threads(Tw > 0);
   if (Tw == 0) {
     if (pi.active && lig == 0) {
       P.kl_pairs[pi.p] = 0.0f;
@@ -343,8 +398,8 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
   int bad = 0;
   float a[R][TM];
   const float lp = pi.active ? P.ell_p[pi.d] : 1.0f;
-  build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise);
-  chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad);
+  build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise, nl);
+  chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad, nl);
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
@@ -352,45 +407,43 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
   float bvec[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) bvec[j] = mrow[j];
-  sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as);
+  sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as, nl);
   store_rows<LP, R>(a, lig, sm.bufA);
   __syncwarp();
   double part = 0.0, ldp = 0.0, ldq = 0.0;
   if (POST == GPKL_POST_GP) {
     const float lq = pi.active ? P.ell_q[pi.d] : 1.0f;
-    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise);
-    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad);
+    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise, nl);
+    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad, nl);
     // z_s = m + L_q eps_s from the register rows
     for (int s = 0; s < S; ++s) {
-      float zz[R];
+      float zz[R], zz1[R];
 #pragma unroll
-      for (int j = 0; j < R; ++j) zz[j] = mrow[j];
+      for (int j = 0; j < R; ++j) { zz[j] = mrow[j]; zz1[j] = 0.0f; }
 #pragma unroll
       for (int k4 = 0; k4 < TM; k4 += 4) {
-        if (k4 < Tw) {
+        {  // (eps is zero on padded steps: no guard needed)
           const float4 e4 = *reinterpret_cast<const float4*>(sm.vS + s * TM + k4);
 #pragma unroll
           for (int j = 0; j < R; ++j) {
             // entries above the diagonal of a register row hold update garbage (never part of L): mask them
             const int r = lig + LP * j;
-            zz[j] = fmaf(k4 <= r ? a[j][k4] : 0.0f, e4.x, zz[j]);
-            zz[j] = fmaf(k4 + 1 <= r ? a[j][k4 + 1] : 0.0f, e4.y, zz[j]);
-            zz[j] = fmaf(k4 + 2 <= r ? a[j][k4 + 2] : 0.0f, e4.z, zz[j]);
-            zz[j] = fmaf(k4 + 3 <= r ? a[j][k4 + 3] : 0.0f, e4.w, zz[j]);
+            fma2<Geo<LP, R>::PACK>(zz[j], zz1[j], k4 <= r ? a[j][k4] : 0.0f, k4 + 1 <= r ? a[j][k4 + 1] : 0.0f, e4.x, e4.y);
+            fma2<Geo<LP, R>::PACK>(zz[j], zz1[j], k4 + 2 <= r ? a[j][k4 + 2] : 0.0f, k4 + 3 <= r ? a[j][k4 + 3] : 0.0f, e4.z, e4.w);
           }
         }
       }
 #pragma unroll
       for (int j = 0; j < R; ++j) {
         const int r = lig + LP * j;
-        if (r < T) P.z[((size_t)S * pi.r0 + (size_t)s * T + r) * d.D + pi.d] = zz[j];
+        if (r < T) P.z[((size_t)S * pi.r0 + (size_t)s * T + r) * d.D + pi.d] = zz[j] + zz1[j];
       }
     }
     store_rows<LP, R>(a, lig, sm.bufB);
     __syncwarp();
     float (&x)[R][TM] = a;  // reuse the registers: columns of L_q
     load_cols<LP, R>(x, lig, sm.bufB);
-    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
+    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, nl);
     float ssq = 0.0f;
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -417,7 +470,7 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
     for (int i = 0; i < TM; ++i)
 #pragma unroll
       for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
-    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
+    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, nl);
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) {
       const int c = lig + LP * jj;
@@ -460,6 +513,7 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
   Smem<LP, R> sm(smem_f + (size_t)gslot * group_floats, S);
   const int T = pi.T, lig = pi.lig;
   const int Tw = warp_max(T);
+  const int nl = live_threads(Tw > 0);
   if (Tw == 0) {
     if (pi.active && lig == 0 && P.gq_pairs) P.gq_pairs[pi.p] = 0.0f;
     return;
@@ -487,8 +541,8 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
   int bad = 0;
   float a[R][TM];
   const float lp = pi.active ? P.ell_p[pi.d] : 1.0f;
-  build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise);
-  chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad);
+  build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise, nl);
+  chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad, nl);
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
@@ -496,7 +550,7 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
   float bvec[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) bvec[j] = mrow[j];
-  sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as);
+  sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as, nl);
   store_rows<LP, R>(a, lig, sm.bufA);
   __syncwarp();
   // X_p = L_p^-1 as register columns
@@ -505,29 +559,26 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
-  solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
+  solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, nl);
   // alpha_c = <X_p[:,c], a> ; g_mean = g alpha + sum_s g_z
   float hdiag[R];
 #pragma unroll
   for (int jj = 0; jj < R; ++jj) {
-    float al = 0.0f, h = 0.0f;
+    float al = 0.0f, h = 0.0f, al1 = 0.0f, h1 = 0.0f;
 #pragma unroll
     for (int k4 = 0; k4 < TM; k4 += 4) {
-      if (k4 < Tw) {
+      {  // (no guard: padded rows of X_p are identity rows and a is zero there)
         const float4 a4 = *reinterpret_cast<const float4*>(sm.as + k4);
-        al = fmaf(x[jj][k4], a4.x, al);
-        al = fmaf(x[jj][k4 + 1], a4.y, al);
-        al = fmaf(x[jj][k4 + 2], a4.z, al);
-        al = fmaf(x[jj][k4 + 3], a4.w, al);
+        fma2<Geo<LP, R>::PACK>(al, al1, x[jj][k4], x[jj][k4 + 1], a4.x, a4.y);
+        fma2<Geo<LP, R>::PACK>(al, al1, x[jj][k4 + 2], x[jj][k4 + 3], a4.z, a4.w);
         if (POST == GPKL_POST_DIAG) {
-          h = fmaf(x[jj][k4], x[jj][k4], h);
-          h = fmaf(x[jj][k4 + 1], x[jj][k4 + 1], h);
-          h = fmaf(x[jj][k4 + 2], x[jj][k4 + 2], h);
-          h = fmaf(x[jj][k4 + 3], x[jj][k4 + 3], h);
+          fma2<Geo<LP, R>::PACK>(h, h1, x[jj][k4], x[jj][k4 + 1], x[jj][k4], x[jj][k4 + 1]);
+          fma2<Geo<LP, R>::PACK>(h, h1, x[jj][k4 + 2], x[jj][k4 + 3], x[jj][k4 + 2], x[jj][k4 + 3]);
         }
       }
     }
-    hdiag[jj] = h;
+    hdiag[jj] = h + h1;
+    al += al1;
     const int c = lig + LP * jj;
     if (c < T) P.g_mean[(size_t)(pi.r0 + c) * d.D + pi.d] = g * al + gzs[jj];
   }
@@ -551,8 +602,8 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
     float t1 = contract_cols<LP, R, KERNEL>(x, sm.bufB, sm.ts, trow, lig, T, lq, sig);
     __syncwarp();
     // factor K_q
-    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise);
-    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad);
+    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise, nl);
+    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad, nl);
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgq[lig + LP * j];
@@ -566,11 +617,9 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
       for (int s = 0; s < S; ++s) {
         float wk = 0.0f;
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-          if (i < Tw) {
-            const float l = (i >= k) ? sm.bufA[poff(i) + k] : 0.0f;
-            wk = fmaf(l, sm.uS[s * TM + i], wk);
-          }
+        for (int i = 0; i < TM; ++i) {  // (padded rows of L_q are identity rows and g_z is zero there)
+          const float l = (i >= k) ? sm.bufA[poff(i) + k] : 0.0f;
+          wk = fmaf(l, sm.uS[s * TM + i], wk);
         }
         sm.wS[s * TM + k] = wk;
         pdk = fmaf(wk, sm.vS[s * TM + k], pdk);
@@ -583,7 +632,7 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
     for (int i = 0; i < TM; ++i)
 #pragma unroll
       for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
-    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
+    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, nl);
     // C'[:,l] = pd .* X_q[:,l] + sum_s w_s .* prefix(eps_s .* X_q[:,l]) -> reversed-packed rows of bufB
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) {
@@ -592,24 +641,22 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
       float cum = 0.0f;  // sample 0 fused; further samples are added below
 #pragma unroll
       for (int i = 0; i < TM; ++i) {
-        if (i < Tw) {
+        lockstep_at<16>(i, nl);
+        {  // (no guard: on padded steps eps = w = 0 and X_q is the identity, every term stays finite and is
+           //  multiplied by a zero of X_q in the contraction)
           const float xi = x[jj][i];
           float cv = fmaf(sm.pd[i], xi, sm.wS[i] * cum);
           cum = fmaf(sm.vS[i], xi, cum);
-          if (TM - 1 - i <= (ip | 3)) row[TM - 1 - i] = cv;
-        } else {
-          if (TM - 1 - i <= (ip | 3)) row[TM - 1 - i] = 0.0f;
+          if (TM - 1 - i <= (ip | 3)) row[(TM - 1 - i) ^ 1] = cv;
         }
       }
       for (int s = 1; s < S; ++s) {
         float cs = 0.0f;
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
-          if (i < Tw) {
-            const float xi = x[jj][i];
-            if (TM - 1 - i <= (ip | 3)) row[TM - 1 - i] = fmaf(sm.wS[s * TM + i], cs, row[TM - 1 - i]);
-            cs = fmaf(sm.vS[s * TM + i], xi, cs);
-          }
+          const float xi = x[jj][i];
+          if (TM - 1 - i <= (ip | 3)) row[(TM - 1 - i) ^ 1] = fmaf(sm.wS[s * TM + i], cs, row[(TM - 1 - i) ^ 1]);
+          cs = fmaf(sm.vS[s * TM + i], xi, cs);
         }
       }
     }

@@ -7,7 +7,7 @@ dev = torch.device('cuda:0')
 L = gpkl._lib.lib()
 buf = torch.zeros(64, dtype=torch.int64, device=dev)
 for T in [int(a) for a in sys.argv[1:]] or [48, 128]:
-    case = orc.synthetic_batch(1, 1, T, 1, seed=1)
+    case = orc.synthetic_batch(37, 4, T, 1, seed=1)  # 148 pairs: a full grid (single-CTA launches fetch-throttle)
     buf.zero_()
     L.gpkl_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
     run_cuda(case, dev, tier='block', grad_ell_p=False)
@@ -18,3 +18,7 @@ for T in [int(a) for a in sys.argv[1:]] or [48, 128]:
     print('T=%d fwd cycles: load %d chol_p %d chol_q %d z %d solve %d reduce %d | total %d' % tuple([T] + f + [t[6] - t[0]]))
     print('T=%d bwd cycles: load %d chol_p %d inv_p %d alpha %d t1 %d chol_q %d w %d inv_q %d Cprime %d t2 %d red %d | total %d'
           % tuple([T] + b + [t[27] - t[16]]))
+    if any(t[32:48]):
+        names = ['chol.tiles', 'chol.sync', 'chol.diag', 'chol.rows', 'solve.tiles', 'solve.sync', 'solve.diag', 'diag.loop']
+        print('   panel loops (GPKL_PANEL_TRACE build): fwd ' + ' '.join('%s %d' % (n, v) for n, v in zip(names, t[32:40])))
+        print('                                         bwd ' + ' '.join('%s %d' % (n, v) for n, v in zip(names, t[40:48])))
