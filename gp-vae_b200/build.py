@@ -60,9 +60,15 @@ def _compile(job, verbose):
 def build_lib(force=False, verbose=False):
     js = jobs()
     srcs = sorted(set(j[0] for j in js)) + _deps()
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(f) for f in srcs):
+    stamp0 = os.path.join(OBJ, "flags.txt")
+    flags_ok = not os.path.isdir(OBJ) or (os.path.exists(stamp0) and open(stamp0).read() == " ".join(FLAGS))
+    if not force and flags_ok and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(f) for f in srcs):
         return OUT  # library is newer than every source (also the case on the GPU box, where build/ does not travel)
     os.makedirs(OBJ, exist_ok=True)
+    # objects built with other flags (debug builds via GPKL_EXTRA_NVCC_FLAGS) are stale
+    stamp = os.path.join(OBJ, "flags.txt")
+    if not os.path.exists(stamp) or open(stamp).read() != " ".join(FLAGS):
+        force = True
     todo = [j for j in js if force or _stale(j[2], j[0])]
     # longest first
     todo.sort(key=lambda j: ("warp_inst" not in j[0], j[1]), reverse=False)
@@ -73,6 +79,8 @@ def build_lib(force=False, verbose=False):
                 raise RuntimeError("nvcc failed on %s %s" % (job[0], " ".join(job[1])))
             if verbose:
                 sys.stderr.write("== %s %s\n%s" % (os.path.basename(job[0]), " ".join(job[1]), r.stderr))
+    with open(stamp, "w") as f:
+        f.write(" ".join(FLAGS))
     r = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + [j[2] for j in js],
                        capture_output=True, text=True)
     if r.returncode != 0:

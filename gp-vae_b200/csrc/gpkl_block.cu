@@ -47,10 +47,12 @@ template <int SGN>
 __device__ __forceinline__ void tile_fma(float (&acc)[4][4], const float4& u4, const float4& v4) {
   const float u[4] = {SGN > 0 ? u4.x : -u4.x, SGN > 0 ? u4.y : -u4.y, SGN > 0 ? u4.z : -u4.z, SGN > 0 ? u4.w : -u4.w};
   const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+  // packed FFMA2: (acc[r][c], acc[r][c+1]) += u[r] * (v[c], v[c+1]); the scalar u[r] is a broadcast operand and
+  // its sign a modifier of the instruction, so a 4x4 tile step is 8 instructions instead of 16
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(u[r], v[c], acc[r][c]);
+    for (int c = 0; c < 4; c += 2) fma2(acc[r][c], acc[r][c + 1], u[r], u[r], v[c], v[c + 1]);
 }
 
 // acc (+/-)= sum_{j in [ja, jb)} U[j*ldu + 0..3] (x) V[j*ldv + 0..3].  Main loop in groups of 8 steps with all
@@ -225,8 +227,10 @@ __device__ __forceinline__ void diag_solve16(float (&b)[16], const float* __rest
       const float4 l4 = *reinterpret_cast<const float4*>(col + 4 * g);
       const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (4 * g + e > c) b[4 * g + e] = fmaf(-xc, lv[e], b[4 * g + e]);
+      for (int e = 0; e < 4; e += 2) {
+        if (4 * g + e > c) fma2(b[4 * g + e], b[4 * g + e + 1], -xc, -xc, lv[e], lv[e + 1]);
+        else if (4 * g + e + 1 > c) b[4 * g + e + 1] = fmaf(-xc, lv[e + 1], b[4 * g + e + 1]);
+      }
     }
   }
 }
@@ -484,7 +488,10 @@ __device__ __forceinline__ void gemm_tile_128x64(float (&acc)[8][4], const float
 #pragma unroll
       for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) acc[r][cc] = fmaf(SGN > 0 ? a[r] : -a[r], b[cc], acc[r][cc]);
+        for (int cc = 0; cc < 4; cc += 2) {
+          const float ar = SGN > 0 ? a[r] : -a[r];
+          fma2(acc[r][cc], acc[r][cc + 1], ar, ar, b[cc], b[cc + 1]);
+        }
     }
   }
   cp_async_wait<0>();

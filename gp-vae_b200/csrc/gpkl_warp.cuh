@@ -26,7 +26,10 @@
 namespace gpkl {
 namespace {
 
-constexpr int WPC = 4;  // warps per CTA
+#ifndef GPKL_WPC
+#define GPKL_WPC 4
+#endif
+constexpr int WPC = GPKL_WPC;  // warps per CTA
 
 // Instruction-fetch lockstep (EXPERIMENT, off by default).  The fully unrolled phases below are straight-line
 // code of 100-300 KB that every warp executes exactly once; ncu shows the warps stalled on no_instruction at
@@ -116,6 +119,10 @@ __device__ __forceinline__ void build_rows(float (&a)[R][LP * R], const float (&
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           const int r = lig + LP * j;
+          if (k > LP * j + LP - 1) {  // above the diagonal for every lane of this slot (compile-time): no exp
+            a[j][k] = 0.0f;
+            continue;
+          }
           float v = kc.val(trow[j] - tv[e]);
           if (k == r) v += noise;
           a[j][k] = (k <= r && r < T) ? v : ((k == r) ? 1.0f : 0.0f);
@@ -135,10 +142,12 @@ template <int LP, int R>
 __device__ __forceinline__ void chol_rows(float (&a)[R][LP * R], int lig, int T, int Tw, float* __restrict__ col,
                                           float* __restrict__ dg, int& bad, int nl) {
   constexpr int TM = LP * R;
+  // (column steps are guarded in groups of 4: a padded column inside a live group is an identity column and
+  //  factors to itself)
 #pragma unroll
   for (int j = 0; j < TM; ++j) {
     lockstep_at<1>(j, nl);
-    if (j < Tw) {
+    if ((j & ~3) < Tw) {
       float* cb = col + (j & 1) * TM;
 #pragma unroll
       for (int jj = 0; jj < R; ++jj) cb[lig + LP * jj] = a[jj][j];
@@ -246,7 +255,7 @@ __device__ __forceinline__ void solve_cols(float (&x)[R][LP * R], const float* _
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     lockstep_at<1>(i, nl);
-    if (i < Tw) {
+    if ((i & ~3) < Tw) {  // groups of 4 rows: a padded row inside a live group is an identity row
       const float* row = Lpk + poff(i);
       float acc[R][2];
 #pragma unroll

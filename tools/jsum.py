@@ -7,5 +7,5 @@ print('%s | value %.0f %s | %.4f ms/step | e2e %.0f | bwd %.4f ms frac %.4f | fw
     d['config'].get('workload', '?')[:30], d['value'], d['unit'], d['ms_per_step'], d.get('e2e', {}).get('value', 0),
     r.get('launch_ms', 0), r.get('frac', 0), r.get('forward', {}).get('launch_ms', 0), r.get('forward', {}).get('frac', 0),
     d.get('gpu_launches'), d.get('clocks', {}).get('sm_mhz')))
-for k, v in (r.get('sweep') or {}).items():
-    print('   sweep', k, v)
+for v in (r.get('sweep') or []):
+    print('   sweep', v)
