@@ -2,6 +2,7 @@
 // prologue (row offsets) and epilogue (deterministic reductions) kernels, and the host-buffer step.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gpkl_common.cuh"
@@ -24,6 +25,10 @@ long long g_launches = 0;
 }  // namespace
 
 void note_launch(int n) { g_launches += n; }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("GPKL_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 void prof_begin(bool backward, cudaStream_t st) {
   if (!g_prof.on || g_prof.n[backward] >= kProfRing) return;
   cudaEventRecord(g_prof.ev[backward][g_prof.n[backward]][0], st);
@@ -56,9 +61,18 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 // offsets[b] = sum_{b' < b} lengths[b'] ; single CTA, two-level scan.
-__global__ void offsets_kernel(const int32_t* __restrict__ lengths, int B, int64_t* __restrict__ offsets) {
+// Also the shared-prior decision: *prior_flag = 1 iff ell_p[0] == ... == ell_p[D-1] (prior_flag may be NULL).
+__global__ void offsets_kernel(const int32_t* __restrict__ lengths, int B, int64_t* __restrict__ offsets,
+                               const float* __restrict__ ell_p = nullptr, int D = 0, int32_t* __restrict__ prior_flag = nullptr) {
   __shared__ int64_t warp_tot[32];
   const int nt = blockDim.x, tid = threadIdx.x;
+  if (prior_flag) {
+    bool uni = true;
+    const float l0 = ell_p[0];
+    for (int i = tid; i < D; i += nt) uni = uni && (ell_p[i] == l0);
+    const int all = __syncthreads_and(uni ? 1 : 0);
+    if (tid == 0) *prior_flag = all ? 1 : 0;
+  }
   const int chunk = (B + nt - 1) / nt;
   const int lo = min(B, tid * chunk), hi = min(B, lo + chunk);
   int64_t local = 0;
@@ -116,8 +130,18 @@ struct Workspace {
   float* gp_pairs;
   float* scratch;
   size_t scratch_stride;
+  int32_t* prior_flag;  // shared-prior fast path: device flag + per-sequence records (NULL when not eligible)
+  float* prior;
+  size_t prior_stride;
   size_t total;
 };
+
+// The shared-prior fast path applies to the GP posterior when no d/d ell_p is requested (that goes to the generic
+// tier) and the caller did not force the per-pair factorisation.
+bool prior_sharing_eligible(const GpklDesc& d) {
+  return d.posterior == GPKL_POST_GP && !(d.flags & (GPKL_FLAG_GRAD_ELL_P | GPKL_FLAG_PER_PAIR_PRIOR)) &&
+         d.tier != GPKL_TIER_GENERIC && d.B > 0;
+}
 
 Workspace plan(const GpklDesc& d, void* base) {
   Workspace w;
@@ -137,6 +161,16 @@ Workspace plan(const GpklDesc& d, void* base) {
   w.scratch_stride = gs > bs ? gs : bs;
   const size_t nslots = w.scratch_stride ? (size_t)(kBlockSlots > generic_slots(d) ? kBlockSlots : generic_slots(d)) : 0;
   off += align_up(nslots * w.scratch_stride * sizeof(float));
+  w.prior_flag = nullptr;
+  w.prior = nullptr;
+  w.prior_stride = 0;
+  if (prior_sharing_eligible(d)) {
+    w.prior_flag = reinterpret_cast<int32_t*>(b + off);
+    off += align_up(sizeof(int32_t));
+    w.prior = reinterpret_cast<float*>(b + off);
+    w.prior_stride = prior_record_floats(d.T_max);
+    off += align_up((size_t)d.B * w.prior_stride * sizeof(float));
+  }
   w.total = off;
   return w;
 }
@@ -224,7 +258,7 @@ extern "C" int gpkl_forward(const GpklDesc* desc, const float* mean, const float
     cudaMemsetAsync(kl_sum, 0, sizeof(double), st);
     return GPKL_OK;
   }
-  offsets_kernel<<<1, 1024, 0, st>>>(lengths, d.B, w.offsets);
+  offsets_kernel<<<1, 1024, 0, st>>>(lengths, d.B, w.offsets, ell_p, d.D, w.prior_flag);
   note_launch();
   Params P;
   memset(&P, 0, sizeof(P));
@@ -234,6 +268,7 @@ extern "C" int gpkl_forward(const GpklDesc* desc, const float* mean, const float
   P.offsets = w.offsets;
   P.scratch = w.scratch_stride ? w.scratch : nullptr;
   P.scratch_stride = w.scratch_stride;
+  P.prior = w.prior; P.prior_stride = w.prior_stride; P.prior_flag = w.prior_flag;
   P.dbg = g_dbg;
   rc = dispatch(P, false, st);
   if (rc != GPKL_OK) return rc;
@@ -271,7 +306,7 @@ extern "C" int gpkl_backward(const GpklDesc* desc, const float* mean, const floa
     if (want_lp) cudaMemsetAsync(g_ell_p, 0, sizeof(float) * d.D, st);
     return GPKL_OK;
   }
-  offsets_kernel<<<1, 1024, 0, st>>>(lengths, d.B, w.offsets);
+  offsets_kernel<<<1, 1024, 0, st>>>(lengths, d.B, w.offsets, ell_p, d.D, w.prior_flag);
   note_launch();
   Params P;
   memset(&P, 0, sizeof(P));
@@ -282,6 +317,7 @@ extern "C" int gpkl_backward(const GpklDesc* desc, const float* mean, const floa
   P.offsets = w.offsets;
   P.scratch = w.scratch_stride ? w.scratch : nullptr;
   P.scratch_stride = w.scratch_stride;
+  P.prior = w.prior; P.prior_stride = w.prior_stride; P.prior_flag = w.prior_flag;
   P.dbg = g_dbg;
   rc = dispatch(P, true, st);
   if (rc != GPKL_OK) return rc;

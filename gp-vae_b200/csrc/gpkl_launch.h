@@ -15,6 +15,14 @@ constexpr int kNumSMs = 148;
 void note_launch(int n = 1);
 void prof_begin(bool backward, cudaStream_t st);
 void prof_end(bool backward, cudaStream_t st);
+bool pdl_enabled();  // programmatic dependent launch of the per-pair kernels behind the shared-prior pre-pass (GPKL_PDL=0 disables)
+
+// Shared-prior records (Params::prior): floats per sequence, an upper bound over the tiers' layouts
+// (warp tier: packed L_p^-1 rows + diag + K_p^-1, gpkl_warp.cuh PriorRec; block tier: gpkl_block.cu).
+inline size_t prior_record_floats(int T_max) {
+  const size_t TP = ((size_t)(T_max < 1 ? 1 : T_max) + 15) / 16 * 16;
+  return 2 * (TP + 1) * (TP + 4);
+}
 
 // generic tier (gpkl_generic.cu)
 size_t generic_smem_bytes(int T, int S, bool mats_in_smem);

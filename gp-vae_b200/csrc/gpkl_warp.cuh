@@ -21,6 +21,8 @@
 // :100-119) and TF autodiff through them (:361).
 #pragma once
 #include "gpkl_common.cuh"
+#include <string.h>
+
 #include "gpkl_launch.h"
 
 namespace gpkl {
@@ -308,14 +310,27 @@ __device__ __forceinline__ void store_cols_rev(const float (&x)[R][LP * R], int 
 }
 
 // sum_{l != c} dK(c,l)/d ell * <x_c, M_l>  for each register column c; M columns in reversed-packed shared.
-template <int LP, int R, int KERNEL>
+// KINV (shared-prior path): kinv = this sequence's K_p^-1 (row-major, stride TM; symmetric, lane c reads ITS row c),
+// the weight of dK(c,l) becomes hg * K_p^-1(c,l) + <x_c, M_l> (hg = g/2: the prior-side term t1 rides along), and
+// alpha[jj] = sum_l K_p^-1(c,l) mvec[l] is accumulated on the way.
+template <int LP, int R, int KERNEL, bool KINV = false>
 __device__ __forceinline__ float contract_cols(const float (&x)[R][LP * R], const float* __restrict__ M,
                                                const float* __restrict__ ts, const float (&tcol)[R], int lig, int T,
-                                               float ell, float sig) {
+                                               float ell, float sig, const float* __restrict__ kinv = nullptr,
+                                               float hg = 0.0f, const float* __restrict__ mvec = nullptr,
+                                               float* alpha = nullptr) {
   constexpr int TM = LP * R;
   const KernC<KERNEL> kc(ell, sig);
   float acc = 0.0f;
+  float al[R];
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) al[jj] = 0.0f;
   for (int l = 0; l < T; ++l) {
+    float kin[R];
+    if (KINV) {
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) kin[jj] = __ldg(kinv + (size_t)(lig + LP * jj) * TM + l);
+    }
     const int ip = TM - 1 - l;
     const float* row = M + poff_dyn(ip);
     float dot[R], dot1[R];
@@ -335,15 +350,176 @@ __device__ __forceinline__ float contract_cols(const float (&x)[R][LP * R], cons
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) dot[jj] += dot1[jj];
     const float tl = ts[l];
+    if (KINV) {
+      const float ml = mvec[l];
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) {
+        dot[jj] = fmaf(hg, kin[jj], dot[jj]);
+        al[jj] = fmaf(kin[jj], ml, al[jj]);
+      }
+    }
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) {
       const int c = lig + LP * jj;
       const float dt = tcol[jj] - tl;
-      const float dk = kc.dell(dt, kc.val(dt));
+      const float dk = kc.dell(dt, kc.val_fast(dt));
       if (c != l && c < T) acc = fmaf(dot[jj], dk, acc);
     }
   }
+  if (KINV) {
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) alpha[jj] = al[jj];
+  }
   return acc;
+}
+
+
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- shared-prior fast path ------------------------------------------------------------------------------------
+// The reference's prior length scales are one constant for all latent dims (prior_time_chars,
+// Full_GP_VAE_dynamic_time.py:114), so the D pairs of a sequence share K_p.  A pre-pass (prior_warp, one lane
+// group per SEQUENCE) factors it once and leaves a record in the workspace; the per-pair kernels then only
+// factor K_q:   forward   A = L_p^-1 L_q as a PRODUCT with the stored inverse (no substitution chain), a = L_p^-1 m
+//               backward  alpha = K_p^-1 m and t1 = <K_p^-1, dK_q/d ell> straight from the stored K_p^-1 rows.
+// Record (floats): [0, PK) L_p^-1 packed rows (poff layout) | [PK, PK+TM) diag L_p | [PK+TM, +TM*TM) K_p^-1.
+template <int LP, int R>
+struct PriorRec {
+  static constexpr int TM = LP * R, PK = Geo<LP, R>::PK;
+  static constexpr int XP = 0, DG = PK, KI = PK + TM, SIZE = PK + TM + TM * TM;
+};
+
+// sum over i != c of A(i,c)^2, A = X_p L_q: X_p packed rows in shared memory (128-bit broadcast loads, zero padded
+// to the end of each 4-group), L_q as register columns (zero above the diagonal).
+template <int LP, int R>
+__device__ __forceinline__ float mul_cols_ssq(const float (&x)[R][LP * R], const float* __restrict__ Xpk, int lig,
+                                              int Tw) {
+  constexpr int TM = LP * R;
+  float ssq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    if ((i & ~3) < Tw) {  // rows beyond the longest sequence of the warp are identity rows: no off-diagonal part
+      const float* row = Xpk + poff(i);
+      float acc[R][2];
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) acc[jj][0] = acc[jj][1] = 0.0f;
+#pragma unroll
+      for (int k4 = 0; k4 <= i; k4 += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(row + k4);
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+          fma2<Geo<LP, R>::PACK>(acc[jj][0], acc[jj][1], l4.x, l4.y, x[jj][k4], x[jj][k4 + 1]);
+          fma2<Geo<LP, R>::PACK>(acc[jj][0], acc[jj][1], l4.z, l4.w, x[jj][k4 + 2], x[jj][k4 + 3]);
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) {
+        const float v = (i == lig + LP * jj) ? 0.0f : acc[jj][0] + acc[jj][1];
+        ssq = fmaf(v, v, ssq);
+      }
+    }
+  }
+  return ssq;
+}
+
+// Pre-pass: one lane group per sequence, ONE warp per CTA (the unrolled code is instruction-fetch bound per SM, so
+// the few warps of this grid are spread over as many SMs as possible).  If ell_p is one value for all latent dims
+// (device flag written by offsets_kernel; if not, the per-pair kernels take their per-pair path and nothing is
+// done here) it factors K_p(ell_p[0]) exactly as the per-pair path does (build_rows / chol_rows / solve_cols) and writes the record.  WANT_KINV: the backward
+// record (K_p^-1 rows); otherwise the forward record (L_p^-1 rows, diag L_p).
+template <int LP, int R, int KERNEL, bool WANT_KINV>
+__global__ void __launch_bounds__(WPC * 32) prior_warp(Params P, int group_floats) {
+  constexpr int TM = LP * R;
+  constexpr int G = 32 / LP;
+  using Rec = PriorRec<LP, R>;
+  extern __shared__ __align__(16) float smem_f[];
+  const GpklDesc& d = P.d;
+  // Let the per-pair kernel (launched with programmatic stream serialisation) start right away: it only reads the
+  // records after its own griddep_wait(), i.e. after this grid has completed.
+  griddep_launch_dependents();
+  if (*P.prior_flag == 0) return;  // ell_p differs between latent dims (offsets_kernel checked): per-pair path
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lig = lane % LP;
+  const int b = (blockIdx.x * (blockDim.x >> 5) + warp) * G + lane / LP;
+  const bool active = b < d.B;
+  const float lp = P.ell_p[0];
+  Smem<LP, R> sm(smem_f + (size_t)(warp * G + lane / LP) * group_floats, d.S);
+  const int T = active ? P.lengths[b] : 0;
+  const int Tw = warp_max(T);
+  // (no early exit for empty sequences: their record is the identity, and a pair of an empty sequence that shares
+  //  a warp with live pairs reads it)
+  const float noise = d.noise, sig = (float)(1.0 - (double)noise);
+  float trow[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int r = lig + LP * j;
+    trow[j] = (r < T) ? P.times[(size_t)b * d.T_max + r] : 0.0f;
+    sm.ts[r] = trow[j];
+  }
+  __syncwarp();
+  int bad = 0;
+  float a[R][TM];
+  build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise, 0);
+  chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad, 0);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
+  store_rows<LP, R>(a, lig, sm.bufA);
+  __syncwarp();
+  float (&x)[R][TM] = a;  // X_p = L_p^-1 as register columns
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
+  solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, 0);
+  // columns -> packed rows (entries above the diagonal inside the last 4-group of a row are exact zeros)
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      const int c = lig + LP * jj;
+      if (c <= (i | 3)) sm.bufB[poff(i) + c] = x[jj][i];
+    }
+  __syncwarp();
+  float* rec = P.prior + (size_t)(active ? b : 0) * P.prior_stride;
+  if (!WANT_KINV) {
+    if (active) {
+      for (int q = lig; q < Rec::PK / 4; q += LP)
+        reinterpret_cast<float4*>(rec + Rec::XP)[q] = reinterpret_cast<const float4*>(sm.bufB)[q];
+#pragma unroll
+      for (int j = 0; j < R; ++j) rec[Rec::DG + lig + LP * j] = sm.dgp[lig + LP * j];
+    }
+  } else {
+    // K_p^-1(c, l) = <X_p[:, c], X_p[:, l]>, four l at a time; symmetric, so lane c stores element (l, c): coalesced
+    for (int l4 = 0; l4 < TM; l4 += 4) {
+      float dot[R][4];
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) dot[jj][0] = dot[jj][1] = dot[jj][2] = dot[jj][3] = 0.0f;
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        // row i holds columns 0..(i|3); for l4 > i the 4-group lies outside the row
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (l4 <= i) v = *reinterpret_cast<const float4*>(sm.bufB + poff(i) + l4);
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+          fma2<Geo<LP, R>::PACK>(dot[jj][0], dot[jj][1], x[jj][i], x[jj][i], v.x, v.y);
+          fma2<Geo<LP, R>::PACK>(dot[jj][2], dot[jj][3], x[jj][i], x[jj][i], v.z, v.w);
+        }
+      }
+      if (active) {
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) rec[Rec::KI + (size_t)(l4 + e) * TM + lig + LP * jj] = dot[jj][e];
+      }
+    }
+  }
+  bad = __any_sync(0xffffffffu, bad && active) ? 1 : 0;
+  if (bad && P.status && (threadIdx.x & 31) == 0) atomicAdd(P.status, 1);
 }
 
 struct PairInfo {
@@ -365,12 +541,6 @@ __device__ __forceinline__ PairInfo pair_info(const Params& P) {
   pi.T = pi.active ? P.lengths[pi.b] : 0;
   pi.r0 = pi.active ? P.offsets[pi.b] : 0;
   return pi;
-}
-
-__device__ __forceinline__ int warp_max(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
 }
 
 template <int LP, int R, int KERNEL, int POST>
@@ -406,19 +576,23 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
   __syncwarp();
   int bad = 0;
   float a[R][TM];
-  const float lp = pi.active ? P.ell_p[pi.d] : 1.0f;
-  build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise, nl);
-  chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad, nl);
-  __syncwarp();
+  // shared-prior fast path: the pre-pass found one ell_p for all latent dims and left this sequence's record
+  const bool shared = (POST == GPKL_POST_GP) && P.prior != nullptr && *P.prior_flag != 0;
+  if (!shared) {
+    const float lp = pi.active ? P.ell_p[pi.d] : 1.0f;
+    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise, nl);
+    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad, nl);
+    __syncwarp();
 #pragma unroll
-  for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
-  __syncwarp();
-  float bvec[R];
+    for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
+    __syncwarp();
+    float bvec[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) bvec[j] = mrow[j];
-  sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as, nl);
-  store_rows<LP, R>(a, lig, sm.bufA);
-  __syncwarp();
+    for (int j = 0; j < R; ++j) bvec[j] = mrow[j];
+    sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as, nl);
+    store_rows<LP, R>(a, lig, sm.bufA);
+    __syncwarp();
+  }
   double part = 0.0, ldp = 0.0, ldq = 0.0;
   if (POST == GPKL_POST_GP) {
     const float lq = pi.active ? P.ell_q[pi.d] : 1.0f;
@@ -452,15 +626,49 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
     __syncwarp();
     float (&x)[R][TM] = a;  // reuse the registers: columns of L_q
     load_cols<LP, R>(x, lig, sm.bufB);
-    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, nl);
     float ssq = 0.0f;
+    if (!shared) {
+      solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, nl);
 #pragma unroll
-    for (int i = 0; i < TM; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-      for (int jj = 0; jj < R; ++jj) {
-        const float v = (i == lig + LP * jj) ? 0.0f : x[jj][i];
-        ssq = fmaf(v, v, ssq);
+        for (int jj = 0; jj < R; ++jj) {
+          const float v = (i == lig + LP * jj) ? 0.0f : x[jj][i];
+          ssq = fmaf(v, v, ssq);
+        }
+    } else {
+      // (the record is first needed here, after the whole K_q chain: the pre-pass overlaps it, see griddep_wait)
+      griddep_wait();
+      // bufA <- L_p^-1 packed rows, dgp <- diag L_p (this sequence's record), a = L_p^-1 m by row dot products
+      using Rec = PriorRec<LP, R>;
+      const float* __restrict__ rec = P.prior + (size_t)pi.b * P.prior_stride;
+      for (int q = lig; q < Rec::PK / 4; q += LP)
+        reinterpret_cast<float4*>(sm.bufA)[q] = __ldg(reinterpret_cast<const float4*>(rec + Rec::XP) + q);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        sm.dgp[lig + LP * j] = __ldg(rec + Rec::DG + lig + LP * j);
+        sm.col[lig + LP * j] = mrow[j];
       }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int r = lig + LP * j;
+        const float* row = sm.bufA + poff_dyn(r);
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int k4 = 0; k4 < LP * j + LP; k4 += 4) {
+          if (k4 <= r && k4 < Tw) {
+            const float4 l4 = *reinterpret_cast<const float4*>(row + k4);
+            const float4 m4 = *reinterpret_cast<const float4*>(sm.col + k4);
+            fma2<Geo<LP, R>::PACK>(s0, s1, l4.x, l4.y, m4.x, m4.y);
+            fma2<Geo<LP, R>::PACK>(s0, s1, l4.z, l4.w, m4.z, m4.w);
+          }
+        }
+        sm.as[r] = s0 + s1;
+      }
+      __syncwarp();
+      ssq = mul_cols_ssq<LP, R>(x, sm.bufA, lig, Tw);  // A = L_p^-1 L_q as a product with the stored inverse
+    }
     part = (double)ssq;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
@@ -549,47 +757,51 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
   __syncwarp();
   int bad = 0;
   float a[R][TM];
-  const float lp = pi.active ? P.ell_p[pi.d] : 1.0f;
-  build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise, nl);
-  chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad, nl);
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
-  __syncwarp();
-  float bvec[R];
-#pragma unroll
-  for (int j = 0; j < R; ++j) bvec[j] = mrow[j];
-  sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as, nl);
-  store_rows<LP, R>(a, lig, sm.bufA);
-  __syncwarp();
-  // X_p = L_p^-1 as register columns
   float (&x)[R][TM] = a;
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
-  solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, nl);
-  // alpha_c = <X_p[:,c], a> ; g_mean = g alpha + sum_s g_z
   float hdiag[R];
+  // shared-prior fast path: the pre-pass found one ell_p for all latent dims and left this sequence's K_p^-1
+  const bool shared = (POST == GPKL_POST_GP) && P.prior != nullptr && *P.prior_flag != 0;
+  if (!shared) {
+    const float lp = pi.active ? P.ell_p[pi.d] : 1.0f;
+    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise, nl);
+    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad, nl);
+    __syncwarp();
 #pragma unroll
-  for (int jj = 0; jj < R; ++jj) {
-    float al = 0.0f, h = 0.0f, al1 = 0.0f, h1 = 0.0f;
+    for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
+    __syncwarp();
+    float bvec[R];
 #pragma unroll
-    for (int k4 = 0; k4 < TM; k4 += 4) {
-      {  // (no guard: padded rows of X_p are identity rows and a is zero there)
-        const float4 a4 = *reinterpret_cast<const float4*>(sm.as + k4);
-        fma2<Geo<LP, R>::PACK>(al, al1, x[jj][k4], x[jj][k4 + 1], a4.x, a4.y);
-        fma2<Geo<LP, R>::PACK>(al, al1, x[jj][k4 + 2], x[jj][k4 + 3], a4.z, a4.w);
-        if (POST == GPKL_POST_DIAG) {
-          fma2<Geo<LP, R>::PACK>(h, h1, x[jj][k4], x[jj][k4 + 1], x[jj][k4], x[jj][k4 + 1]);
-          fma2<Geo<LP, R>::PACK>(h, h1, x[jj][k4 + 2], x[jj][k4 + 3], x[jj][k4 + 2], x[jj][k4 + 3]);
+    for (int j = 0; j < R; ++j) bvec[j] = mrow[j];
+    sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as, nl);
+    store_rows<LP, R>(a, lig, sm.bufA);
+    __syncwarp();
+    // X_p = L_p^-1 as register columns
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
+    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, nl);
+    // alpha_c = <X_p[:,c], a> ; g_mean = g alpha + sum_s g_z
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      float al = 0.0f, h = 0.0f, al1 = 0.0f, h1 = 0.0f;
+#pragma unroll
+      for (int k4 = 0; k4 < TM; k4 += 4) {
+        {  // (no guard: padded rows of X_p are identity rows and a is zero there)
+          const float4 a4 = *reinterpret_cast<const float4*>(sm.as + k4);
+          fma2<Geo<LP, R>::PACK>(al, al1, x[jj][k4], x[jj][k4 + 1], a4.x, a4.y);
+          fma2<Geo<LP, R>::PACK>(al, al1, x[jj][k4 + 2], x[jj][k4 + 3], a4.z, a4.w);
+          if (POST == GPKL_POST_DIAG) {
+            fma2<Geo<LP, R>::PACK>(h, h1, x[jj][k4], x[jj][k4 + 1], x[jj][k4], x[jj][k4 + 1]);
+            fma2<Geo<LP, R>::PACK>(h, h1, x[jj][k4 + 2], x[jj][k4 + 3], x[jj][k4 + 2], x[jj][k4 + 3]);
+          }
         }
       }
+      hdiag[jj] = h + h1;
+      al += al1;
+      const int c = lig + LP * jj;
+      if (c < T) P.g_mean[(size_t)(pi.r0 + c) * d.D + pi.d] = g * al + gzs[jj];
     }
-    hdiag[jj] = h + h1;
-    al += al1;
-    const int c = lig + LP * jj;
-    if (c < T) P.g_mean[(size_t)(pi.r0 + c) * d.D + pi.d] = g * al + gzs[jj];
   }
   if (POST == GPKL_POST_DIAG) {
 #pragma unroll
@@ -606,10 +818,13 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
   } else {
     const float lq = pi.active ? P.ell_q[pi.d] : 1.0f;
     // t1 = sum_{k != l} dK_q(k,l) (X_p^T X_p)_kl
-    store_cols_rev<LP, R>(x, lig, sm.bufB);
-    __syncwarp();
-    float t1 = contract_cols<LP, R, KERNEL>(x, sm.bufB, sm.ts, trow, lig, T, lq, sig);
-    __syncwarp();
+    float t1 = 0.0f;
+    if (!shared) {
+      store_cols_rev<LP, R>(x, lig, sm.bufB);
+      __syncwarp();
+      t1 = contract_cols<LP, R, KERNEL>(x, sm.bufB, sm.ts, trow, lig, T, lq, sig);
+      __syncwarp();
+    }
     // factor K_q
     build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise, nl);
     chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad, nl);
@@ -670,7 +885,27 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
       }
     }
     __syncwarp();
-    const float t2 = contract_cols<LP, R, KERNEL>(x, sm.bufB, sm.ts, trow, lig, T, lq, sig);
+    float t2;
+    if (!shared) {
+      t2 = contract_cols<LP, R, KERNEL>(x, sm.bufB, sm.ts, trow, lig, T, lq, sig);
+    } else {
+      // The record (this sequence's K_p^-1) is first needed here, after the whole K_q chain, so the pre-pass overlaps
+      // it (griddep_wait).  alpha = K_p^-1 m and t1 = <K_p^-1, dK_q/d ell> ride along in the same contraction loop
+      // (same dK weights), so t2 below already contains g/2 * t1.
+      griddep_wait();
+      using Rec = PriorRec<LP, R>;
+      const float* __restrict__ rec = P.prior + (size_t)pi.b * P.prior_stride;
+#pragma unroll
+      for (int j = 0; j < R; ++j) sm.as[lig + LP * j] = mrow[j];
+      __syncwarp();
+      float alpha[R];
+      t2 = contract_cols<LP, R, KERNEL, true>(x, sm.bufB, sm.ts, trow, lig, T, lq, sig, rec + Rec::KI, 0.5f * g, sm.as, alpha);
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) {
+        const int c = lig + LP * jj;
+        if (c < T) P.g_mean[(size_t)(pi.r0 + c) * d.D + pi.d] = g * alpha[jj] + gzs[jj];
+      }
+    }
     const double gq = group_sum<LP>(0.5 * (double)g * (double)t1 + (double)t2);
     if (pi.active && lig == 0) P.gq_pairs[pi.p] = (float)gq;
   }
@@ -693,21 +928,44 @@ cudaError_t launch_cfg(const Params& P, cudaStream_t st) {
   const int per_cta = WPC * (32 / LP);
   const int grid = (npairs + per_cta - 1) / per_cta;
   cudaError_t e;
+  bool pdl = false;
+  // (the profiling events bracket pre-pass + per-pair kernel: an event recorded between the two would break the
+  //  programmatic dependency and serialise them)
+  prof_begin(BWD, st);
+  if (POST == GPKL_POST_GP && P.prior != nullptr) {  // shared-prior pre-pass: one lane group per sequence
+    auto pk = prior_warp<LP, R, KERNEL, BWD>;
+    const int G = 32 / LP;
+    pk<<<(P.d.B + G - 1) / G, 32, (size_t)G * group_floats * sizeof(float), st>>>(P, group_floats);
+    note_launch();
+    pdl = pdl_enabled();
+  }
+  // With a pre-pass in front, the per-pair kernel is its programmatic dependent: it starts while the pre-pass
+  // runs and waits (griddepcontrol.wait) only where it first touches the records.
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(WPC * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   if constexpr (!BWD) {
     auto kern = fwd_warp<LP, R, KERNEL, POST>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    prof_begin(false, st);
-    kern<<<grid, WPC * 32, smem, st>>>(P, group_floats);
+    e = cudaLaunchKernelEx(&cfg, kern, P, group_floats);
     prof_end(false, st);
   } else {
     auto kern = bwd_warp<LP, R, KERNEL, POST>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    prof_begin(true, st);
-    kern<<<grid, WPC * 32, smem, st>>>(P, group_floats);
+    e = cudaLaunchKernelEx(&cfg, kern, P, group_floats);
     prof_end(true, st);
   }
+  if (e != cudaSuccess) return e;
   note_launch();
   return cudaGetLastError();
 }

@@ -10,6 +10,7 @@ KERNELS = {"rbf": 0, "cauchy": 1}
 POSTERIORS = {"gp": 0, "diag": 1, "bidiag": 2}
 TIERS = {"auto": 0, "generic": 1, "warp": 2, "block": 3}
 FLAG_GRAD_ELL_P = 1
+FLAG_PER_PAIR_PRIOR = 2
 
 # every symbol include/gpkl.h declares (tests check the library exports exactly these)
 SYMBOLS = ("gpkl_version", "gpkl_strerror", "gpkl_workspace_bytes", "gpkl_forward", "gpkl_backward",

@@ -11,7 +11,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import GpklDesc, KERNELS, POSTERIORS, TIERS, FLAG_GRAD_ELL_P
+from ._lib import GpklDesc, KERNELS, POSTERIORS, TIERS, FLAG_GRAD_ELL_P, FLAG_PER_PAIR_PRIOR
 
 _WS = {}
 
@@ -64,11 +64,13 @@ def _check_inputs(mean, times, lengths, ell_q, ell_p, eps, aux, posterior, S):
 
 
 def gp_prior_kl_forward(mean, times, lengths, ell_q, ell_p, eps, *, aux=None, kernel="rbf", posterior="gp",
-                        noise=1e-3, S=1, tier="auto", want_logdets=False, want_status=False):
-    """Raw forward through the C ABI (gpkl_forward).  Returns dict(z, kl_sum, kl_pairs[, logdets, status])."""
+                        noise=1e-3, S=1, tier="auto", want_logdets=False, want_status=False, shared_prior=True):
+    """Raw forward through the C ABI (gpkl_forward).  Returns dict(z, kl_sum, kl_pairs[, logdets, status]).
+    shared_prior=False forces the per-pair prior factorisation (GPKL_FLAG_PER_PAIR_PRIOR); by default the library
+    factors K_p once per sequence when it finds ell_p identical for all latent dims (the reference's prior)."""
     B, D, T_max, total_T = _check_inputs(mean, times, lengths, ell_q, ell_p, eps, aux, posterior, S)
     dev = mean.device
-    desc = _make_desc(B, D, T_max, S, total_T, kernel, posterior, noise, 0, tier)
+    desc = _make_desc(B, D, T_max, S, total_T, kernel, posterior, noise, 0 if shared_prior else FLAG_PER_PAIR_PRIOR, tier)
     ws, n = _workspace(desc, dev)
     z = torch.empty(S * total_T, D, dtype=torch.float32, device=dev)
     kl_pairs = torch.empty(B * D, dtype=torch.float32, device=dev)
@@ -89,12 +91,13 @@ def gp_prior_kl_forward(mean, times, lengths, ell_q, ell_p, eps, *, aux=None, ke
 
 def gp_prior_kl_backward(mean, times, lengths, ell_q, ell_p, eps, g_z, g_kl_sum=None, g_kl_pairs=None, *, aux=None,
                          kernel="rbf", posterior="gp", noise=1e-3, S=1, tier="auto", grad_ell_p=False,
-                         out=None):
+                         out=None, shared_prior=True):
     """Raw backward through the C ABI (gpkl_backward).  g_kl_sum: 0-d float64 CUDA tensor or None (== 1).
     `out` may carry preallocated g_mean / g_ell_q / g_ell_p / g_aux (e.g. views into a gradient bucket)."""
     B, D, T_max, total_T = _check_inputs(mean, times, lengths, ell_q, ell_p, eps, aux, posterior, S)
     dev = mean.device
-    desc = _make_desc(B, D, T_max, S, total_T, kernel, posterior, noise, FLAG_GRAD_ELL_P if grad_ell_p else 0, tier)
+    desc = _make_desc(B, D, T_max, S, total_T, kernel, posterior, noise,
+                      (FLAG_GRAD_ELL_P if grad_ell_p else 0) | (0 if shared_prior else FLAG_PER_PAIR_PRIOR), tier)
     ws, n = _workspace(desc, dev)
     out = dict(out or {})
     g_mean = out.get("g_mean")

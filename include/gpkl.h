@@ -45,7 +45,15 @@ extern "C" {
 enum { GPKL_KERNEL_RBF = 0, GPKL_KERNEL_CAUCHY = 1 };
 enum { GPKL_POST_GP = 0, GPKL_POST_DIAG = 1, GPKL_POST_BIDIAG = 2 };
 enum { GPKL_TIER_AUTO = 0, GPKL_TIER_GENERIC = 1, GPKL_TIER_WARP = 2, GPKL_TIER_BLOCK = 3 };
-enum { GPKL_FLAG_GRAD_ELL_P = 1 };   /* backward also produces d/d ell_p (Full_GP_VAE_fixed_for_MovMnist.py:96) */
+enum {
+  GPKL_FLAG_GRAD_ELL_P = 1,     /* backward also produces d/d ell_p (Full_GP_VAE_fixed_for_MovMnist.py:96) */
+  /* The reference's prior length scales are one constant for every latent dimension
+   * (prior_time_chars = tf.constant(1.0, [latent_size, 1]), Full_GP_VAE_dynamic_time.py:114), so K_p of a
+   * sequence is the same matrix for its D pairs ("each batch has the SAME matrix", :108-109).  When the device
+   * finds ell_p[0] == ... == ell_p[D-1] the hot tiers factor K_p once per SEQUENCE (a small pre-pass into the
+   * workspace) instead of once per pair.  This flag forces the per-pair factorisation (A/B tests). */
+  GPKL_FLAG_PER_PAIR_PRIOR = 2
+};
 
 enum {
   GPKL_OK = 0,

@@ -15,7 +15,7 @@ def to_dev(case, dev):
 
 
 def run_cuda(case, dev, *, kernel="rbf", posterior="gp", noise=1e-3, S=1, tier="auto", grad_ell_p=True,
-             g_kl_pairs=None, g_kl_sum=1.0):
+             g_kl_pairs=None, g_kl_sum=1.0, shared_prior=True):
     import gpkl
     c = to_dev(case, dev)
     aux = c.get("aux")
@@ -23,12 +23,12 @@ def run_cuda(case, dev, *, kernel="rbf", posterior="gp", noise=1e-3, S=1, tier="
         aux = c.get("logvar")
     fwd = gpkl.gp_prior_kl_forward(c["mean"], c["times"], c["lengths"].to(torch.int32), c["ell_q"], c["ell_p"],
                                    c["eps"], aux=aux, kernel=kernel, posterior=posterior, noise=noise, S=S, tier=tier,
-                                   want_logdets=True, want_status=True)
+                                   want_logdets=True, want_status=True, shared_prior=shared_prior)
     gks = torch.tensor(float(g_kl_sum), dtype=torch.float64, device=dev)
     gkp = None if g_kl_pairs is None else g_kl_pairs.to(dev).float().contiguous()
     bwd = gpkl.gp_prior_kl_backward(c["mean"], c["times"], c["lengths"].to(torch.int32), c["ell_q"], c["ell_p"],
                                     c["eps"], c.get("g_z"), gks, gkp, aux=aux, kernel=kernel, posterior=posterior,
-                                    noise=noise, S=S, tier=tier, grad_ell_p=grad_ell_p)
+                                    noise=noise, S=S, tier=tier, grad_ell_p=grad_ell_p, shared_prior=shared_prior)
     torch.cuda.synchronize()
     return fwd, bwd
 
@@ -66,7 +66,7 @@ def reference_rounding_floor(case, **ocfg):
 def compare(case, dev, floor=False, **cfg):
     """Returns dict of scale-relative errors CUDA vs oracle (plus the reference rounding floor on request)."""
     fwd, bwd = run_cuda(case, dev, **cfg)
-    ocfg = {k: v for k, v in cfg.items() if k not in ("tier", "grad_ell_p")}
+    ocfg = {k: v for k, v in cfg.items() if k not in ("tier", "grad_ell_p", "shared_prior")}
     out, grads = run_oracle(case, **ocfg)
     errs = {
         "kl_pairs": rel_err(fwd["kl_pairs"], out["kl_pairs"]),
