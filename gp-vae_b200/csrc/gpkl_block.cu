@@ -22,6 +22,8 @@
 //              derivative evaluated in the epilogue (never stored).
 // Math: SURVEY.md Appendix A; reference replaced: src/Models/Full_GP_VAE_dynamic_time.py:149-172, :174-195,
 // :242-260 (+ TF autodiff :361); V2 src/Models/VAE_GPprior_diag_cov.py:64-71, :100-119.
+#include <string.h>
+
 #include "gpkl_common.cuh"
 #include "gpkl_launch.h"
 
@@ -181,6 +183,8 @@ struct Sm {
 
 // One warp: factor the 16x16 diagonal block held in pan (columns 0..15, rows j0..j0+15) in registers with
 // shuffles; writes L_dd into the LC triangle of Bm, diag(L) into dg and 1/diag(L) into rdg.
+// XRC: also write the block row-major into the XR triangle (element (i,k) at Bm[(i+1)*ld + k]).
+template <bool XRC = false>
 __device__ __forceinline__ void diag_factor(float* __restrict__ Bm, int ld, int j0, int T, const float* __restrict__ pan,
                                             int ldpan, float* __restrict__ dg, float* __restrict__ rdg, int* bad) {
   const int lane = threadIdx.x & 31, l = lane & 15;
@@ -207,7 +211,10 @@ __device__ __forceinline__ void diag_factor(float* __restrict__ Bm, int ld, int 
   if (lane < 16) {
 #pragma unroll
     for (int c = 0; c < 16; ++c)
-      if (c <= l) Bm[(size_t)(j0 + c) * ld + j0 + l] = a[c];
+      if (c <= l) {
+        Bm[(size_t)(j0 + c) * ld + j0 + l] = a[c];
+        if (XRC) Bm[(size_t)(j0 + l + 1) * ld + j0 + c] = a[c];
+      }
     dg[j0 + l] = dgv;
     rdg[j0 + l] = rdv;
   }
@@ -240,7 +247,9 @@ __device__ __forceinline__ void diag_solve16(float (&b)[16], const float* __rest
 // Bm is a VIEW: element (i,k) at Bm[k*ldm + i].  Columns [c_begin, c_end) are factored; contributions of columns
 // < kstart are assumed applied already, and with FROM_VIEW the starting values are read from the view (the
 // GEMM phase of the large-T path left them there) instead of being generated.
-template <int KERNEL, bool DUAL, bool FROM_VIEW>
+// XRC (resident buffers only): the factor is ALSO written row-major into the XR triangle of the same buffer
+// (element (i,k) at Bm[(i+1)*ldm + k]) -- the k-major operand of the shared-prior product A = L_p^-1 L_q.
+template <int KERNEL, bool DUAL, bool FROM_VIEW, bool XRC = false>
 __device__ __noinline__ void chol_panels(float* __restrict__ Bm, int ldm, int c_begin, int c_end, int kstart, const Lay& L,
                                          int T, bool extra, const float* __restrict__ ts, const float* __restrict__ mm,
                                          float ell, float sig, float noise, float* __restrict__ pan,
@@ -305,7 +314,7 @@ __device__ __noinline__ void chol_panels(float* __restrict__ Bm, int ldm, int c_
     PT_ADD(0);
     grp_sync<DUAL>(g);
     PT_ADD(1);
-    if (tid < 32) diag_factor(Bm, ldm, j0, T, pan, ld, dg, rdg, bad);
+    if (tid < 32) diag_factor<XRC>(Bm, ldm, j0, T, pan, ld, dg, rdg, bad);
     PT_ADD(2);
     grp_sync<DUAL>(g);
     PT_ADD(1);
@@ -320,6 +329,11 @@ __device__ __noinline__ void chol_panels(float* __restrict__ Bm, int ldm, int c_
       diag_solve16(b, Bm, ldm, j0, rdg);
 #pragma unroll
       for (int c = 0; c < 16; ++c) Bm[(size_t)(j0 + c) * ldm + i] = b[c];
+      if (XRC && i < TP) {
+        float* xr = Bm + (size_t)(i + 1) * ldm + j0;
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(xr + c) = make_float4(b[c], b[c + 1], b[c + 2], b[c + 3]);
+      }
     }
     PT_ADD(3);
     grp_sync<DUAL>(g);
@@ -334,13 +348,13 @@ __device__ __noinline__ void chol_panels(float* __restrict__ Bm, int ldm, int c_
 }
 
 // Resident path: the whole factorisation, kernel entries generated on the fly.
-template <int KERNEL, bool DUAL>
+template <int KERNEL, bool DUAL, bool XRC = false>
 __device__ __forceinline__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool extra, const float* __restrict__ ts,
                                            const float* __restrict__ mm, float ell, float sig, float noise,
                                            float* __restrict__ pan, float* __restrict__ dg, float* __restrict__ rdg, int* bad,
                                            Grp g) {
   const int Tact = (T + NB - 1) / NB * NB;
-  chol_panels<KERNEL, DUAL, false>(Bm, L.ld, 0, Tact, 0, L, T, extra, ts, mm, ell, sig, noise, pan, dg, rdg, bad, g);
+  chol_panels<KERNEL, DUAL, false, XRC>(Bm, L.ld, 0, Tact, 0, L, T, extra, ts, mm, ell, sig, noise, pan, dg, rdg, bad, g);
 }
 
 // X = L^-1 B by 16-row blocks into the XR triangle of Xb.  L: LC triangle of Lb with inverse diagonal
@@ -501,7 +515,8 @@ __device__ __forceinline__ void gemm_tile_128x64(float (&acc)[8][4], const float
 // Large-T Cholesky: 64-column panels.  GEMM phase: panel = K - L[:, 0:J0] L[J0:J0+64, 0:J0]^T into the shared-memory
 // panel `wide` (K generated in the accumulator init); then the panel is factored in shared memory by the 16-column
 // code on a view of `wide`; then its lower triangle is copied to the global factor.
-template <int KERNEL>
+// XRC: the panel is ALSO copied out row-major into the XR triangle (element (i,k) at Bm[(i+1)*ld + k]).
+template <int KERNEL, bool XRC = false>
 __device__ __noinline__ void chol_gemm(float* __restrict__ Bm, const Lay& L, int T, bool extra, const float* __restrict__ ts,
                                        const float* __restrict__ mm, float ell, float sig, float noise,
                                        float* __restrict__ pan, float* __restrict__ wide, float* __restrict__ stg,
@@ -561,6 +576,26 @@ __device__ __noinline__ void chol_gemm(float* __restrict__ Bm, const Lay& L, int
         if (r4 + 1 >= c) dst[1] = v.y;
         if (r4 + 2 >= c) dst[2] = v.z;
         dst[3] = v.w;
+      }
+    }
+    if (XRC) {
+      // row-major copy: consecutive threads take consecutive rows (conflict-free panel reads), each writes the four
+      // columns c4..c4+3 of its row as one 16-byte store (scalars where the group straddles the diagonal)
+      const int nrows = Tact - J0;
+      for (int idx = tid; idx < (ncols >> 2) * nrows; idx += blockDim.x) {
+        const int cq = idx / nrows, r = J0 + (idx - cq * nrows);
+        const int c4 = J0 + 4 * cq;
+        if (c4 > r) continue;
+        const float v0 = Pv[(size_t)c4 * ld + r], v1 = Pv[(size_t)(c4 + 1) * ld + r], v2 = Pv[(size_t)(c4 + 2) * ld + r],
+                    v3 = Pv[(size_t)(c4 + 3) * ld + r];
+        float* dst = Bm + (size_t)(r + 1) * ld + c4;
+        if (c4 + 3 <= r) {
+          *reinterpret_cast<float4*>(dst) = make_float4(v0, v1, v2, v3);
+        } else {
+          dst[0] = v0;
+          if (c4 + 1 <= r) dst[1] = v1;
+          if (c4 + 2 <= r) dst[2] = v2;
+        }
       }
     }
     __syncthreads();
@@ -628,9 +663,12 @@ __device__ __noinline__ float solve_gemm(const float* __restrict__ Lb, const flo
 }
 
 // sum_{k != l, k,l < T} dK(k,l)/d ell * sum_{i} XU[i][k] XV[i][l]   (XR triangles of Ub / Vb); thread partial.
+// kinv != NULL (shared-prior path): the weight of dK(k,l) becomes hg * kinv[k*ld + l] + (U^T V)_kl, i.e. the prior-side
+// term g/2 <K_p^-1, dK_q/d ell> rides along in the same epilogue (kinv = this sequence's K_p^-1 record, row stride ld).
 template <int KERNEL>
 __device__ __noinline__ double contract_block(const float* __restrict__ Ub, const float* __restrict__ Vb, const Lay& L, int T,
-                                 const float* __restrict__ ts, float ell, float sig, Grp g) {
+                                 const float* __restrict__ ts, float ell, float sig, Grp g,
+                                 const float* __restrict__ kinv = nullptr, float hg = 0.0f) {
   const int tid = g.tid, NT = g.nt;
   const int ld = L.ld;
   const int nk = (T + 3) / 4;
@@ -657,6 +695,14 @@ __device__ __noinline__ double contract_block(const float* __restrict__ Ub, cons
         for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(u[r], v[c], acc[r][c]);
     }
     tile_update<1>(acc, Ub + ld + kb, ld, Vb + ld + lb, ld, i, T);
+    if (kinv) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(kinv + (size_t)(kb + r) * ld + lb));
+        acc[r][0] = fmaf(hg, q.x, acc[r][0]); acc[r][1] = fmaf(hg, q.y, acc[r][1]);
+        acc[r][2] = fmaf(hg, q.z, acc[r][2]); acc[r][3] = fmaf(hg, q.w, acc[r][3]);
+      }
+    }
     const float4 tk4 = *reinterpret_cast<const float4*>(ts + kb);
     const float4 tl4 = *reinterpret_cast<const float4*>(ts + lb);
     const float tk[4] = {tk4.x, tk4.y, tk4.z, tk4.w}, tl[4] = {tl4.x, tl4.y, tl4.z, tl4.w};
@@ -667,7 +713,7 @@ __device__ __noinline__ double contract_block(const float* __restrict__ Ub, cons
       for (int c = 0; c < 4; ++c) {
         const int k = kb + r, l = lb + c;
         const float dt = tk[r] - tl[c];
-        const float dk = kc.dell(dt, kc.val(dt));
+        const float dk = kc.dell(dt, kc.val_fast(dt));
         part = fmaf((k < T && l < T && k != l) ? acc[r][c] : 0.0f, dk, part);  // branch-free
       }
     total += (double)part;
@@ -681,7 +727,8 @@ __device__ __noinline__ double contract_block(const float* __restrict__ Ub, cons
 // SYM: U == V, so (U^T V) is symmetric: only blocks that contain entries with k > l are computed, weighted twice.
 template <int KERNEL, bool SYM>
 __device__ __noinline__ double contract_gemm(const float* __restrict__ Ub, const float* __restrict__ Vb, const Lay& L, int T,
-                                             const float* __restrict__ ts, float ell, float sig, float* __restrict__ stg) {
+                                             const float* __restrict__ ts, float ell, float sig, float* __restrict__ stg,
+                                             const float* __restrict__ kinv = nullptr, float hg = 0.0f) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int ld = L.ld;
   const KernC<KERNEL> kc(ell, sig);
@@ -709,9 +756,11 @@ __device__ __noinline__ double contract_gemm(const float* __restrict__ Ub, const
       for (int c = 0; c < 4; ++c) {
         const int k = kb0 + 8 * ty + r, l = lb0 + 4 * tx + c;
         const float dt = tk[r] - tl[c];
-        const float dk = kc.dell(dt, kc.val(dt));
+        const float dk = kc.dell(dt, kc.val_fast(dt));
         const bool on = SYM ? (k < T && l < k) : (k < T && l < T && k != l);
-        part = fmaf(on ? acc[r][c] : 0.0f, SYM ? 2.0f * dk : dk, part);
+        float w = acc[r][c];
+        if (!SYM && kinv && on) w = fmaf(hg, __ldg(kinv + (size_t)k * ld + l), w);
+        part = fmaf(on ? w : 0.0f, SYM ? 2.0f * dk : dk, part);
       }
     total += (double)part;
   }
@@ -724,7 +773,8 @@ __device__ __noinline__ double contract_gemm(const float* __restrict__ Ub, const
 template <int KERNEL>
 __device__ __noinline__ double contract_block_staged(const float* __restrict__ Ub, const float* __restrict__ Vb,
                                                      const Lay& L, int T, const float* __restrict__ ts, float ell,
-                                                     float sig, float* __restrict__ stg) {
+                                                     float sig, float* __restrict__ stg,
+                                                     const float* __restrict__ kinv = nullptr, float hg = 0.0f) {
   constexpr int KC = 32, SLD = 128;
   const int tid = threadIdx.x;  // blockDim.x == 256
   const int ld = L.ld;
@@ -780,12 +830,103 @@ __device__ __noinline__ double contract_block_staged(const float* __restrict__ U
         const int k = kb + r, l = lb + c;
         const bool ok = k < T && l < T && k != l;
         const float dt = ok ? ts[k] - ts[l] : 0.0f;
-        const float dk = kc.dell(dt, kc.val(dt));
-        part = fmaf(ok ? acc[r][c] : 0.0f, dk, part);
+        const float dk = kc.dell(dt, kc.val_fast(dt));
+        float w = acc[r][c];
+        if (kinv && ok) w = fmaf(hg, __ldg(kinv + (size_t)k * ld + l), w);
+        part = fmaf(ok ? w : 0.0f, dk, part);
       }
     total += (double)part;
   }
   return total;
+}
+
+
+// ---- shared-prior fast path ------------------------------------------------------------------------------------
+// The reference's prior length scales are one constant for all latent dims (prior_time_chars,
+// Full_GP_VAE_dynamic_time.py:114): the D pairs of a sequence share K_p.  A pre-pass (prior_block, one CTA per
+// SEQUENCE) factors it once and leaves a record in the workspace; the per-pair kernels then only factor K_q.
+//   forward record  [0, TP*ld)            X_p = L_p^-1 as a full square, COLUMN-major (X(i,k) at rec[k*ld + i]), exact
+//                                         zeros above the diagonal, identity on the padding
+//                   [TP*ld, TP*ld + TP)   diag L_p
+//   backward record [0, TP*ld)            K_p^-1 = X_p^T X_p, full symmetric square, row stride ld
+// Forward: A = L_p^-1 L_q is the PRODUCT X_p L_q (no substitution chain, no barriers); the contraction index needs
+// L_q row-major, which the factorisation leaves in the XR triangle (XRC).  Backward: alpha = K_p^-1 m, and the prior
+// term g/2 <K_p^-1, dK_q/d ell> rides in the epilogue of the posterior contraction (kinv argument).
+__host__ __device__ inline size_t rec_dg_offset(const Lay& L) { return (size_t)L.TP * L.ld; }
+
+// sum_{c < i < T} A(i,c)^2, A = X L:  Xc column-major with explicit zeros above the diagonal (X(i,k) at Xc[k*ldx+i]),
+// Lq's row-major copy in the XR triangle of Lb (L(k,c) at Lb[(k+1)*ld + c], garbage above the diagonal).  Thread partial.
+__device__ __noinline__ float product_ssq_block(const float* __restrict__ Xc, int ldx, const float* __restrict__ Lb,
+                                                const Lay& L, int T, Grp g) {
+  const int ld = L.ld;
+  const int nt = (T + 3) / 4;
+  float ssq = 0.0f;
+  for (int id = g.tid; id < nt * nt; id += g.nt) {
+    const int it = id % nt, ct = id / nt;
+    if (ct > it) continue;
+    const int rb = 4 * it, cb = 4 * ct;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+    // k in [cb, rb + 4): L(k,c) = 0 for k < c, X(i,k) = 0 for k > i.  Head steps touch L's diagonal: mask the garbage.
+    int k = cb;
+    const int kend = rb + 4;
+    const int khead = (cb + 3 < kend) ? cb + 3 : kend;
+    for (; k < khead; ++k) {
+      const float4 u4 = *reinterpret_cast<const float4*>(Xc + (size_t)k * ldx + rb);
+      const float4 v4 = *reinterpret_cast<const float4*>(Lb + (size_t)(k + 1) * ld + cb);
+      const float u[4] = {u4.x, u4.y, u4.z, u4.w};
+      const float v[4] = {cb <= k ? v4.x : 0.0f, cb + 1 <= k ? v4.y : 0.0f, cb + 2 <= k ? v4.z : 0.0f, cb + 3 <= k ? v4.w : 0.0f};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(u[r], v[c], acc[r][c]);
+    }
+    tile_update<1>(acc, Xc + rb, ldx, Lb + ld + cb, ld, k, kend);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = rb + r, cc = cb + c;
+        const float v = (cc < i && i < T) ? acc[r][c] : 0.0f;
+        ssq = fmaf(v, v, ssq);
+      }
+  }
+  return ssq;
+}
+
+// The same on the staged GEMM tile (large T): 128 (i) x 64 (c) output blocks, A operand = the record (global, zeros
+// above the diagonal), B operand = Lq's row-major copy in the workspace slot (zero-filled above its diagonal).
+__device__ __noinline__ float product_ssq_gemm(const float* __restrict__ Xc, const float* __restrict__ Lb, const Lay& L, int T,
+                                               float* __restrict__ stg) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int ld = L.ld;
+  const int Tact = (T + NB - 1) / NB * NB;
+  const int nib = (T + 127) / 128, ncb = (T + 63) / 64;
+  float ssq = 0.0f;
+  for (int bp = 0; bp < nib * ncb; ++bp) {
+    const int i0 = (bp % nib) * 128, c0 = (bp / nib) * 64;
+    if (c0 > i0 + 127) continue;  // entirely above the diagonal
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+    const int k0 = c0 / GM_KC * GM_KC;
+    const int k1 = (i0 + 128 < Tact) ? i0 + 128 : Tact;
+    gemm_tile_128x64<1, false, true>(acc, Xc, ld, i0, L.TP, Lb + ld, ld, c0, ld, k0, k1, stg);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = i0 + 8 * ty + r, cc = c0 + 4 * tx + c;
+        const float v = (cc < i && i < T) ? acc[r][c] : 0.0f;
+        ssq = fmaf(v, v, ssq);
+      }
+  }
+  return ssq;
 }
 
 __device__ __forceinline__ void load_pair(const Params& P, int p, int b, int dd, int T, long long r0, const Lay& L,
@@ -830,6 +971,110 @@ struct Groups {
   }
 };
 
+
+// Pre-pass of the shared-prior path: one CTA per sequence (grid-stride).  Factors K_p(ell_p[0]) with the same code as
+// the per-pair path, inverts the factor and writes the record (layout above).  WANT_KINV: backward record.
+template <int KERNEL, bool SLOT, bool WANT_KINV>
+__global__ void __launch_bounds__(256, SLOT ? 1 : 2) prior_block(Params P, int use_slot) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ int bad;
+  griddep_launch_dependents();  // the per-pair kernel may start; it reads the records after its griddep_wait()
+  if (*P.prior_flag == 0) return;  // ell_p differs between latent dims (offsets_kernel checked): per-pair path
+  const GpklDesc& d = P.d;
+  const Lay L(d.T_max, d.S);
+  Sm s(smem_f, L, use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr);
+  const int TP = L.TP, ld = L.ld;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const float noise = d.noise, sig = (float)(1.0 - (double)noise);
+  const float lp = P.ell_p[0];
+  const Grp all{tid, nt, 0};
+  const bool gm = SLOT && L.gemm(false);
+  for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
+    const int T = max(P.lengths[b], 0);
+    const int Tact = (T + NB - 1) / NB * NB;
+    float* __restrict__ rec = P.prior + (size_t)b * P.prior_stride;
+    __syncthreads();
+    if (tid == 0) bad = 0;
+    for (int i = tid; i < ld; i += nt) s.ts[i] = (i < T) ? P.times[(size_t)b * d.T_max + i] : 0.0f;
+    for (int i = tid; i < TP; i += nt) s.mm[i] = 0.0f;
+    __syncthreads();
+    if (T > 0) {
+      if (gm) {
+        chol_gemm<KERNEL>(s.B1, L, T, false, s.ts, s.mm, lp, sig, noise, s.pan, s.wide, s.stg, s.dgp, s.rdp, &bad);
+        (void)solve_gemm<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, s.wide, s.stg);
+      } else {
+        chol_block<KERNEL, false>(s.B1, L, T, false, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, all);
+        (void)solve_block<true, false>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, all);
+      }
+      __syncthreads();
+    }
+    if (!WANT_KINV) {
+      for (int idx = tid; idx < TP * ld; idx += nt) {
+        const int k = idx / ld, i = idx - k * ld;
+        float v;
+        if (i < Tact && k < Tact) v = (i >= k) ? s.B1[(size_t)(i + 1) * ld + k] : 0.0f;
+        else v = (i == k) ? 1.0f : 0.0f;
+        rec[idx] = v;
+      }
+      for (int i = tid; i < TP; i += nt) rec[rec_dg_offset(L) + i] = (i < Tact) ? s.dgp[i] : 1.0f;
+    } else {
+      // identity outside the factored range, then K_p^-1 = X^T X over it
+      for (int idx = tid; idx < TP * ld; idx += nt) {
+        const int k = idx / ld, l = idx - k * ld;
+        if (k >= Tact || l >= Tact) rec[idx] = (k == l) ? 1.0f : 0.0f;
+      }
+      if (gm) {
+        const int tx = tid & 15, ty = tid >> 4;
+        const int nkb = (Tact + 127) / 128, nlb = (Tact + 63) / 64;
+        for (int bp = 0; bp < nkb * nlb; ++bp) {
+          const int kb0 = (bp % nkb) * 128, lb0 = (bp / nkb) * 64;
+          float acc[8][4];
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+          const int i0 = (kb0 > lb0 ? kb0 : lb0) / GM_KC * GM_KC;
+          gemm_tile_128x64<1, true, true>(acc, s.B1 + ld, ld, kb0, ld, s.B1 + ld, ld, lb0, ld, i0, Tact, s.stg);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int k = kb0 + 8 * ty + r, l = lb0 + 4 * tx;
+            if (k < Tact && l < Tact)
+              *reinterpret_cast<float4*>(rec + (size_t)k * ld + l) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+          }
+        }
+      } else {
+        const int nk = Tact / 4;
+        for (int id = tid; id < nk * nk; id += nt) {
+          const int lt = id % nk, kt = id / nk;
+          const int kb = 4 * kt, lb = 4 * lt;
+          float acc[4][4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+          int i = kb > lb ? kb : lb;
+          const int ihead = (i + 3 < Tact) ? i + 3 : Tact;
+          for (; i < ihead; ++i) {
+            const float4 u4 = *reinterpret_cast<const float4*>(s.B1 + (size_t)(i + 1) * ld + kb);
+            const float4 v4 = *reinterpret_cast<const float4*>(s.B1 + (size_t)(i + 1) * ld + lb);
+            const float u[4] = {kb <= i ? u4.x : 0.0f, kb + 1 <= i ? u4.y : 0.0f, kb + 2 <= i ? u4.z : 0.0f, kb + 3 <= i ? u4.w : 0.0f};
+            const float v[4] = {lb <= i ? v4.x : 0.0f, lb + 1 <= i ? v4.y : 0.0f, lb + 2 <= i ? v4.z : 0.0f, lb + 3 <= i ? v4.w : 0.0f};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(u[r], v[c], acc[r][c]);
+          }
+          tile_update<1>(acc, s.B1 + ld + kb, ld, s.B1 + ld + lb, ld, i, Tact);
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            *reinterpret_cast<float4*>(rec + (size_t)(kb + r) * ld + lb) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        }
+      }
+    }
+    if (tid == 0 && bad && P.status) atomicAdd(P.status, 1);
+  }
+}
+
 template <int KERNEL, int POST, bool DUAL, bool SLOT>
 __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use_slot) {
   extern __shared__ __align__(16) float smem_f[];
@@ -840,6 +1085,8 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
   const int S = d.S, TP = L.TP, ld = L.ld;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
   const Groups G(DUAL);
+  // shared-prior fast path: the pre-pass found one ell_p for all latent dims and left per-sequence records
+  const bool shared = (POST == GPKL_POST_GP) && !DUAL && P.prior != nullptr && *P.prior_flag != 0;
   for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
     const int T = P.lengths[b];
@@ -858,11 +1105,66 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
     __syncthreads();
     phase_mark(P, 1);
     const bool gm = SLOT && L.gemm(false);  // large T: GEMM-structured phases on shared-memory panels
-    if (gm) chol_gemm<KERNEL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.wide, s.stg, s.dgp, s.rdp, &bad);
-    else if (G.g0) chol_block<KERNEL, DUAL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
+    if (!shared) {
+      if (gm) chol_gemm<KERNEL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.wide, s.stg, s.dgp, s.rdp, &bad);
+      else if (G.g0) chol_block<KERNEL, DUAL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
+    }
     phase_mark(P, 2);
     double part = 0.0, ldp = 0.0, ldq = 0.0;
-    if (POST == GPKL_POST_GP) {
+    if (POST == GPKL_POST_GP && shared) {
+      // ---- shared-prior path: only K_q is factored here (all threads); L_p^-1 and diag L_p come from the record
+      if (gm) chol_gemm<KERNEL, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
+      else chol_block<KERNEL, false, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.dgq, s.rdq, &bad, G.all);
+      for (int i = threadIdx.x; i < T; i += blockDim.x) {  // z_s = m + L_q eps_s
+        for (int sx = 0; sx < S; ++sx) {
+          const float* ev = s.v + (size_t)sx * TP;
+          float acc = s.mm[i];
+          for (int k = 0; k <= i; ++k) acc = fmaf(s.B2[(size_t)k * ld + i], ev[k], acc);
+          P.z[((size_t)S * r0 + (size_t)sx * T + i) * d.D + dd] = acc;
+        }
+      }
+      phase_mark(P, 4);
+      griddep_wait();  // the record is first needed here: the pre-pass overlaps the K_q factorisation
+      const float* __restrict__ rec = P.prior + (size_t)b * P.prior_stride;
+      for (int i = threadIdx.x; i < TP; i += blockDim.x) s.dgp[i] = __ldg(rec + rec_dg_offset(L) + i);
+      float ssq;
+      if (gm) {
+        for (int i = threadIdx.x; i < T; i += blockDim.x) {  // a = L_p^-1 m from the record (coalesced over i)
+          float a0 = 0.0f, a1 = 0.0f;
+          int k = 0;
+          for (; k + 8 <= i + 1; k += 8) {
+            float xv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xv[e] = __ldg(rec + (size_t)(k + e) * ld + i);
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) { a0 = fmaf(xv[e], s.mm[k + e], a0); a1 = fmaf(xv[e + 1], s.mm[k + e + 1], a1); }
+          }
+          for (; k <= i; ++k) a0 = fmaf(__ldg(rec + (size_t)k * ld + i), s.mm[k], a0);
+          s.aa[i] = a0 + a1;
+        }
+        ssq = product_ssq_gemm(rec, s.B2, L, T, s.stg);
+      } else {
+        for (int q = threadIdx.x; q < TP * ld / 4; q += blockDim.x)
+          reinterpret_cast<float4*>(s.B1)[q] = __ldg(reinterpret_cast<const float4*>(rec) + q);
+        __syncthreads();
+        for (int i = threadIdx.x; i < T; i += blockDim.x) {
+          float a0 = 0.0f;
+          for (int k = 0; k <= i; ++k) a0 = fmaf(s.B1[(size_t)k * ld + i], s.mm[k], a0);
+          s.aa[i] = a0;
+        }
+        ssq = product_ssq_block(s.B1, ld, s.B2, L, T, G.all);
+      }
+      __syncthreads();
+      phase_mark(P, 5);
+      part = (double)ssq;
+      for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        const double lpd = (double)s.dgp[i], lqd = (double)s.dgq[i];
+        const double av = (double)s.aa[i];
+        part += diag_term(lqd / lpd) + av * av;
+        ldp += 2.0 * log(lpd);
+        ldq += 2.0 * log(lqd);
+      }
+    } else if (POST == GPKL_POST_GP) {
       if (gm) chol_gemm<KERNEL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
       if (G.g1) {
         if (!gm)
@@ -935,6 +1237,8 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
   const double g_sum = P.g_kl_sum ? *P.g_kl_sum : 1.0;
   const Groups G(DUAL);
+  // shared-prior fast path: the pre-pass found one ell_p for all latent dims and left per-sequence records
+  const bool shared = (POST == GPKL_POST_GP) && !DUAL && P.prior != nullptr && *P.prior_flag != 0;
   for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
     const int T = P.lengths[b];
@@ -954,7 +1258,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
     const float lq = (POST == GPKL_POST_GP) ? P.ell_q[dd] : lp;
     const bool gm = SLOT && L.gemm(false);  // large T: GEMM-structured phases on shared-memory panels
     double t1 = 0.0;
-    if (G.g0) {  // ---- prior chain: L_p, X_p = L_p^-1, alpha = K_p^-1 m, t1 = <K_p^-1, dK_q/d ell>
+    if (!shared && G.g0) {  // ---- prior chain: L_p, X_p = L_p^-1, alpha = K_p^-1 m, t1 = <K_p^-1, dK_q/d ell>
       if (gm) chol_gemm<KERNEL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.wide, s.stg, s.dgp, s.rdp, &bad);
       else chol_block<KERNEL, DUAL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
       phase_mark(P, 18);
@@ -1054,9 +1358,30 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
       }
       __syncthreads();
       phase_mark(P, 25);
-      const double t2 = gm ? contract_gemm<KERNEL, false>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg)
-                        : SLOT ? contract_block_staged<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg)
-                                 : contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, G.all);
+      // shared-prior path: alpha = K_p^-1 m from the record (K_p^-1 symmetric: coalesced over k), and the prior term
+      // g/2 <K_p^-1, dK_q/d ell> rides in the epilogue of the contraction below (t1 stays 0)
+      const float* __restrict__ kinv = nullptr;
+      if (shared) {
+        griddep_wait();  // the record is first needed here: the pre-pass overlaps the whole K_q chain
+        kinv = P.prior + (size_t)b * P.prior_stride;
+        for (int k = threadIdx.x; k < T; k += blockDim.x) {
+          float a0 = 0.0f, a1 = 0.0f;
+          int l = 0;
+          for (; l + 8 <= T; l += 8) {
+            float xv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xv[e] = __ldg(kinv + (size_t)(l + e) * ld + k);
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) { a0 = fmaf(xv[e], s.mm[l + e], a0); a1 = fmaf(xv[e + 1], s.mm[l + e + 1], a1); }
+          }
+          for (; l < T; ++l) a0 = fmaf(__ldg(kinv + (size_t)l * ld + k), s.mm[l], a0);
+          P.g_mean[(size_t)(r0 + k) * d.D + dd] = g * (a0 + a1) + s.gzs[k];
+        }
+      }
+      const float hg = 0.5f * g;
+      const double t2 = gm ? contract_gemm<KERNEL, false>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg, kinv, hg)
+                        : SLOT ? contract_block_staged<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg, kinv, hg)
+                                 : contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, G.all, kinv, hg);
       phase_mark(P, 26);
       const double gq = block_sum(0.5 * (double)g * t1 + t2, s.red);
       phase_mark(P, 27);
@@ -1071,7 +1396,8 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
 }
 
 template <int KERNEL, int POST>
-cudaError_t launch_kp(const Params& P, bool backward, cudaStream_t st) {
+cudaError_t launch_kp(const Params& P_in, bool backward, cudaStream_t st) {
+  Params P = P_in;
   const Lay L(P.d.T_max, P.d.S);
   const bool resident = block_tier_resident(P.d);
   const size_t smem = L.floats(resident) * sizeof(float);
@@ -1089,18 +1415,49 @@ cudaError_t launch_kp(const Params& P, bool backward, cudaStream_t st) {
   } else {
     grid = npairs < kBlockSlots ? npairs : kBlockSlots;  // one workspace slot per CTA
   }
-  const bool dual = POST == GPKL_POST_GP && L.dual(resident);
+  // Shared-prior path (records in the workspace): served for the resident and GEMM-path sizes.  Its kernels run the
+  // single K_q chain on all threads, so the non-DUAL instantiation is launched; if the device then finds ell_p
+  // non-uniform that instantiation runs the per-pair prior chain too (just without the two-chain overlap).
+  const bool share = POST == GPKL_POST_GP && P_in.prior != nullptr && (resident || L.gemm(false));
+  if (!share) { P.prior = nullptr; P.prior_flag = nullptr; }
+  const bool dual = POST == GPKL_POST_GP && L.dual(resident) && !share;
   void (*kern)(Params, int);
   if (!resident) kern = backward ? bwd_block<KERNEL, POST, false, true> : fwd_block<KERNEL, POST, false, true>;
   else if (!backward) kern = dual ? fwd_block<KERNEL, POST, true, false> : fwd_block<KERNEL, POST, false, false>;
   else kern = dual ? bwd_block<KERNEL, POST, true, false> : bwd_block<KERNEL, POST, false, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  // (the profiling events bracket pre-pass + per-pair kernel: an event between them would break the programmatic
+  //  dependency and serialise them)
   prof_begin(backward, st);
-  kern<<<grid, nt, smem, st>>>(P, resident ? 0 : 1);
+  bool pdl = false;
+  if (share) {
+    void (*pk)(Params, int);
+    if (!resident) pk = backward ? prior_block<KERNEL, true, true> : prior_block<KERNEL, true, false>;
+    else pk = backward ? prior_block<KERNEL, false, true> : prior_block<KERNEL, false, false>;
+    e = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int pgrid = resident ? P.d.B : (P.d.B < kBlockSlots ? P.d.B : kBlockSlots);
+    pk<<<pgrid, 256, smem, st>>>(P, resident ? 0 : 1);
+    note_launch();
+    // the pre-pass of the slot path works in the same workspace slots as the per-pair kernel: no overlap there
+    pdl = resident && pdl_enabled();
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(nt);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, kern, P, resident ? 0 : 1);
   prof_end(backward, st);
   note_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace
