@@ -117,13 +117,6 @@ constexpr int NBL = 64;                               // large-T panel width (co
 constexpr int GEMM_TMAX = 512;                        // the shared-memory panel fits up to this T
 constexpr int GEMM_TMIN = 144;                        // below this the per-panel overheads outweigh the GEMM phase
 
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct Lay {  // shared-memory carve-up (floats), identical on host and device
   int TP, ld, nP, S;

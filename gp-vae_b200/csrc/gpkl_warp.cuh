@@ -325,45 +325,53 @@ __device__ __forceinline__ float contract_cols(const float (&x)[R][LP * R], cons
   float al[R];
 #pragma unroll
   for (int jj = 0; jj < R; ++jj) al[jj] = 0.0f;
-  for (int l = 0; l < T; ++l) {
-    float kin[R];
-    if (KINV) {
+  // Rows of M are grouped by capacity: rows ip = 4q .. 4q+3 (l = TM-1-ip) hold q+1 four-groups.  The q loop is
+  // unrolled (compile-time trip counts and offsets, no per-group guards), the four rows of a group are a real loop
+  // (the same code four times: instruction-cache hits instead of straight-line fetch).
 #pragma unroll
-      for (int jj = 0; jj < R; ++jj) kin[jj] = __ldg(kinv + (size_t)(lig + LP * jj) * TM + l);
-    }
-    const int ip = TM - 1 - l;
-    const float* row = M + poff_dyn(ip);
-    float dot[R], dot1[R];
+  for (int q = TM / 4 - 1; q >= 0; --q) {
+    const float* base = M + 8 * q * (q + 1);  // poff(4q)
+#pragma unroll 1
+    for (int r = 3; r >= 0; --r) {
+      const int l = TM - 1 - (4 * q + r);
+      if (l < T) {
+        float kin[R];
+        if (KINV) {
 #pragma unroll
-    for (int jj = 0; jj < R; ++jj) dot[jj] = dot1[jj] = 0.0f;
+          for (int jj = 0; jj < R; ++jj) kin[jj] = __ldg(kinv + (size_t)(lig + LP * jj) * TM + l);
+        }
+        const float* row = base + 4 * r * (q + 1);
+        float dot[R], dot1[R];
 #pragma unroll
-    for (int g = 0; g < TM / 4; ++g) {
-      if (4 * g <= ip) {
-        const float4 q = *reinterpret_cast<const float4*>(row + 4 * g);
+        for (int jj = 0; jj < R; ++jj) dot[jj] = dot1[jj] = 0.0f;
+#pragma unroll
+        for (int g = 0; g <= q; ++g) {
+          const float4 qv = *reinterpret_cast<const float4*>(row + 4 * g);
+#pragma unroll
+          for (int jj = 0; jj < R; ++jj) {
+            fma2<Geo<LP, R>::PACK>(dot[jj], dot1[jj], qv.x, qv.y, x[jj][TM - 2 - 4 * g], x[jj][TM - 1 - 4 * g]);
+            fma2<Geo<LP, R>::PACK>(dot[jj], dot1[jj], qv.z, qv.w, x[jj][TM - 4 - 4 * g], x[jj][TM - 3 - 4 * g]);
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) dot[jj] += dot1[jj];
+        const float tl = ts[l];
+        if (KINV) {
+          const float ml = mvec[l];
+#pragma unroll
+          for (int jj = 0; jj < R; ++jj) {
+            dot[jj] = fmaf(hg, kin[jj], dot[jj]);
+            al[jj] = fmaf(kin[jj], ml, al[jj]);
+          }
+        }
 #pragma unroll
         for (int jj = 0; jj < R; ++jj) {
-          fma2<Geo<LP, R>::PACK>(dot[jj], dot1[jj], q.x, q.y, x[jj][TM - 2 - 4 * g], x[jj][TM - 1 - 4 * g]);
-          fma2<Geo<LP, R>::PACK>(dot[jj], dot1[jj], q.z, q.w, x[jj][TM - 4 - 4 * g], x[jj][TM - 3 - 4 * g]);
+          const int c = lig + LP * jj;
+          const float dt = tcol[jj] - tl;
+          const float dk = kc.dell(dt, kc.val_fast(dt));
+          if (c != l && c < T) acc = fmaf(dot[jj], dk, acc);
         }
       }
-    }
-#pragma unroll
-    for (int jj = 0; jj < R; ++jj) dot[jj] += dot1[jj];
-    const float tl = ts[l];
-    if (KINV) {
-      const float ml = mvec[l];
-#pragma unroll
-      for (int jj = 0; jj < R; ++jj) {
-        dot[jj] = fmaf(hg, kin[jj], dot[jj]);
-        al[jj] = fmaf(kin[jj], ml, al[jj]);
-      }
-    }
-#pragma unroll
-    for (int jj = 0; jj < R; ++jj) {
-      const int c = lig + LP * jj;
-      const float dt = tcol[jj] - tl;
-      const float dk = kc.dell(dt, kc.val_fast(dt));
-      if (c != l && c < T) acc = fmaf(dot[jj], dk, acc);
     }
   }
   if (KINV) {
@@ -598,6 +606,18 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
     const float lq = pi.active ? P.ell_q[pi.d] : 1.0f;
     build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise, nl);
     chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad, nl);
+    float dgp_rec[R] = {};
+    if (shared) {
+      // The record is first needed after the K_q chain, so the pre-pass overlaps it (griddep_wait); its packed
+      // L_p^-1 rows stream into bufA asynchronously while z, the transposition and a = L_p^-1 m's operands are done.
+      griddep_wait();
+      using Rec = PriorRec<LP, R>;
+      const float* __restrict__ rec = P.prior + (size_t)pi.b * P.prior_stride;
+      for (int q = lig; q < Rec::PK / 4; q += LP) cp_async16(sm.bufA + 4 * q, rec + Rec::XP + 4 * q, 16);
+      cp_async_commit();
+#pragma unroll
+      for (int j = 0; j < R; ++j) dgp_rec[j] = __ldg(rec + Rec::DG + lig + LP * j);
+    }
     // z_s = m + L_q eps_s from the register rows
     for (int s = 0; s < S; ++s) {
       float zz[R], zz1[R];
@@ -637,16 +657,12 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
           ssq = fmaf(v, v, ssq);
         }
     } else {
-      // (the record is first needed here, after the whole K_q chain: the pre-pass overlaps it, see griddep_wait)
-      griddep_wait();
-      // bufA <- L_p^-1 packed rows, dgp <- diag L_p (this sequence's record), a = L_p^-1 m by row dot products
+      // bufA <- L_p^-1 packed rows (asynchronous copy issued above), dgp <- diag L_p, a = L_p^-1 m by row dot products
       using Rec = PriorRec<LP, R>;
-      const float* __restrict__ rec = P.prior + (size_t)pi.b * P.prior_stride;
-      for (int q = lig; q < Rec::PK / 4; q += LP)
-        reinterpret_cast<float4*>(sm.bufA)[q] = __ldg(reinterpret_cast<const float4*>(rec + Rec::XP) + q);
+      cp_async_wait<0>();
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-        sm.dgp[lig + LP * j] = __ldg(rec + Rec::DG + lig + LP * j);
+        sm.dgp[lig + LP * j] = dgp_rec[j];
         sm.col[lig + LP * j] = mrow[j];
       }
       __syncwarp();
@@ -677,8 +693,10 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
         const double lpd = (double)sm.dgp[r], lqd = (double)sm.dgq[r];
         const double av = (double)sm.as[r];
         part += diag_term(lqd / lpd) + av * av;
-        ldp += 2.0 * log(lpd);
-        ldq += 2.0 * log(lqd);
+        if (P.logdets) {  // (float64 logarithms: only when the caller asked for the log-determinants)
+          ldp += 2.0 * log(lpd);
+          ldq += 2.0 * log(lqd);
+        }
       }
     }
   } else {  // diagonal posterior: X = L_p^-1 columns, h_c = |X[:,c]|^2

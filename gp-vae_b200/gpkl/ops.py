@@ -174,10 +174,10 @@ class HostStep:
     holding CPU tensors makes.  Owns the device staging area and pinned result buffers."""
 
     def __init__(self, B, D, T_max, S, total_T, *, kernel="rbf", posterior="gp", noise=1e-3, grad_ell_p=False,
-                 tier="auto", device="cuda:0"):
+                 tier="auto", device="cuda:0", shared_prior=True):
         self.device = torch.device(device)
         self.desc = _make_desc(B, D, T_max, S, total_T, kernel, posterior, noise,
-                               FLAG_GRAD_ELL_P if grad_ell_p else 0, tier)
+                               (FLAG_GRAD_ELL_P if grad_ell_p else 0) | (0 if shared_prior else FLAG_PER_PAIR_PRIOR), tier)
         n = _lib.lib().gpkl_step_host_bytes(ctypes.byref(self.desc))
         if n == 0:
             raise RuntimeError("gpkl: bad descriptor")
