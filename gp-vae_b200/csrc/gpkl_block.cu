@@ -447,33 +447,42 @@ __device__ __forceinline__ void gemm_tile_128x64(float (&acc)[8][4], const float
                                                  int bcol_lim, int k0, int k1, float* __restrict__ stg) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int nch = (k1 - k0 + GM_KC - 1) / GM_KC;
-  auto issue = [&](int c) {
-    float* buf = stg + (c % GM_NS) * (GM_KC * GM_SLD);
+  // Each thread copies the same three 16-byte slots of every stage (16 steps x 48 float4 = 768 slots / 256 threads):
+  // their stage offset, global pointer, contraction step and limits are set up ONCE per call and advanced by one
+  // stage per issue, so a stage costs ~10 instructions per slot instead of the full index arithmetic.
+  const float* gp[3];
+  int kq[3], klim[3], rce[3], so[3], gstep[3];
+#pragma unroll
+  for (int rnd = 0; rnd < 3; ++rnd) {
+    const int q = tid + 256 * rnd;
+    const int kk = q / 48, e = q - kk * 48;
+    const bool isA = e < 32;
+    const int rc = isA ? arow0 + 4 * e : bcol0 + 4 * (e - 32);
+    const bool inb = rc < (isA ? arow_lim : bcol_lim);
+    const bool tri = isA ? A_TRI : B_TRI;
+    const int ldx = isA ? lda : ldb;
+    klim[rnd] = inb ? k1 : -0x40000000;        // out-of-range rows / columns: never valid (zero-filled)
+    rce[rnd] = tri ? rc : -0x20000000;         // triangular operand: elements rc .. rc+3 exist while <= k
+    so[rnd] = kk * GM_SLD + (isA ? 4 * e : 128 + 4 * (e - 32));
+    kq[rnd] = k0 + kk;
+    gstep[rnd] = GM_KC * ldx;
+    gp[rnd] = (isA ? Ag : Bg) + (size_t)kq[rnd] * ldx + rc;
+  }
+  int issued = 0;
+  auto issue = [&](int c) {  // called with c = 0, 1, 2, ... in order
+    float* buf = stg + (issued & (GM_NS - 1)) * (GM_KC * GM_SLD);
     if (c < nch) {
 #pragma unroll
       for (int rnd = 0; rnd < 3; ++rnd) {
-        const int q = tid + 256 * rnd;  // 16 steps x 48 float4
-        const int kk = q / 48, e = q - kk * 48;
-        const int k = k0 + c * GM_KC + kk;
-        if (e < 32) {
-          const int row = arow0 + 4 * e;
-          int valid = (k < k1 && row < arow_lim) ? 4 : 0;
-          if (A_TRI && valid) {
-            const int v = k - row + 1;
-            valid = v < 0 ? 0 : (v > 4 ? 4 : v);
-          }
-          cp_async16(buf + kk * GM_SLD + 4 * e, valid ? Ag + (size_t)k * lda + row : Ag, 4 * valid);
-        } else {
-          const int col = bcol0 + 4 * (e - 32);
-          int valid = (k < k1 && col < bcol_lim) ? 4 : 0;
-          if (B_TRI && valid) {
-            const int v = k - col + 1;
-            valid = v < 0 ? 0 : (v > 4 ? 4 : v);
-          }
-          cp_async16(buf + kk * GM_SLD + 128 + 4 * (e - 32), valid ? Bg + (size_t)k * ldb + col : Bg, 4 * valid);
-        }
+        int v = kq[rnd] - rce[rnd] + 1;
+        v = v > 4 ? 4 : v;
+        const int valid = (kq[rnd] < klim[rnd] && v > 0) ? v : 0;
+        cp_async16(buf + so[rnd], valid ? gp[rnd] : Ag, 4 * valid);
+        gp[rnd] += gstep[rnd];
+        kq[rnd] += GM_KC;
       }
     }
+    ++issued;
     cp_async_commit();  // (possibly empty) group: keeps the group count uniform
   };
   // GM_NS-deep pipeline, one barrier per stage: the barrier of iteration c publishes stage c and also guarantees
@@ -1108,12 +1117,20 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
       // ---- shared-prior path: only K_q is factored here (all threads); L_p^-1 and diag L_p come from the record
       if (gm) chol_gemm<KERNEL, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
       else chol_block<KERNEL, false, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.dgq, s.rdq, &bad, G.all);
-      for (int i = threadIdx.x; i < T; i += blockDim.x) {  // z_s = m + L_q eps_s
+      for (int i = threadIdx.x; i < T; i += blockDim.x) {  // z_s = m + L_q eps_s (loads batched 8 ahead: L_q may be global)
         for (int sx = 0; sx < S; ++sx) {
           const float* ev = s.v + (size_t)sx * TP;
-          float acc = s.mm[i];
-          for (int k = 0; k <= i; ++k) acc = fmaf(s.B2[(size_t)k * ld + i], ev[k], acc);
-          P.z[((size_t)S * r0 + (size_t)sx * T + i) * d.D + dd] = acc;
+          float acc = s.mm[i], acc1 = 0.0f;
+          int k = 0;
+          for (; k + 8 <= i + 1; k += 8) {
+            float lv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) lv[e] = s.B2[(size_t)(k + e) * ld + i];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) { acc = fmaf(lv[e], ev[k + e], acc); acc1 = fmaf(lv[e + 1], ev[k + e + 1], acc1); }
+          }
+          for (; k <= i; ++k) acc = fmaf(s.B2[(size_t)k * ld + i], ev[k], acc);
+          P.z[((size_t)S * r0 + (size_t)sx * T + i) * d.D + dd] = acc + acc1;
         }
       }
       phase_mark(P, 4);
