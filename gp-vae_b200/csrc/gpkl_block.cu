@@ -751,6 +751,20 @@ __device__ __noinline__ double contract_gemm(const float* __restrict__ Ub, const
     for (int r = 0; r < 8; ++r) tk[r] = (kb0 + 8 * ty + r < T) ? ts[kb0 + 8 * ty + r] : 0.0f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) tl[c] = (lb0 + 4 * tx + c < T) ? ts[lb0 + 4 * tx + c] : 0.0f;
+    if (!SYM && kinv) {  // prior-side term: acc += hg * K_p^-1 block (eight independent 16-byte loads, issued together)
+      float4 kq[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int k = kb0 + 8 * ty + r, l = lb0 + 4 * tx;
+        kq[r] = (k < L.TP && l < L.TP) ? __ldg(reinterpret_cast<const float4*>(kinv + (size_t)k * ld + l))
+                                       : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        acc[r][0] = fmaf(hg, kq[r].x, acc[r][0]); acc[r][1] = fmaf(hg, kq[r].y, acc[r][1]);
+        acc[r][2] = fmaf(hg, kq[r].z, acc[r][2]); acc[r][3] = fmaf(hg, kq[r].w, acc[r][3]);
+      }
+    }
     float part = 0.0f;
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -760,9 +774,7 @@ __device__ __noinline__ double contract_gemm(const float* __restrict__ Ub, const
         const float dt = tk[r] - tl[c];
         const float dk = kc.dell(dt, kc.val_fast(dt));
         const bool on = SYM ? (k < T && l < k) : (k < T && l < T && k != l);
-        float w = acc[r][c];
-        if (!SYM && kinv && on) w = fmaf(hg, __ldg(kinv + (size_t)k * ld + l), w);
-        part = fmaf(on ? w : 0.0f, SYM ? 2.0f * dk : dk, part);
+        part = fmaf(on ? acc[r][c] : 0.0f, SYM ? 2.0f * dk : dk, part);
       }
     total += (double)part;
   }
@@ -1315,16 +1327,34 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
           chol_block<KERNEL, DUAL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, G.dual ? s.pan2 : s.pan, s.dgq, s.rdq,
                                    &bad, G.chain);
         phase_mark(P, 22);
-        for (int k = G.chain.tid; k < T; k += G.chain.nt) {
-          float pdk = 0.0f;
-          for (int sx = 0; sx < S; ++sx) {
-            const float* uu = s.u + (size_t)sx * TP;
-            float wk = 0.0f;
-            for (int i = k; i < T; ++i) wk = fmaf(s.B2[(size_t)k * ld + i], uu[i], wk);
-            s.w[(size_t)sx * TP + k] = wk;
-            pdk = fmaf(wk, s.v[(size_t)sx * TP + k], pdk);
+        if (SLOT) {
+          // L_q lives in global memory: one WARP per column k, lanes stride down the column (coalesced), shuffle-reduce
+          const int lane = G.chain.tid & 31, wid = G.chain.tid >> 5, nw = G.chain.nt >> 5;
+          for (int k = wid; k < T; k += nw) {
+            float pdk = 0.0f;
+            for (int sx = 0; sx < S; ++sx) {
+              const float* uu = s.u + (size_t)sx * TP;
+              const float* __restrict__ colk = s.B2 + (size_t)k * ld;
+              float wk = 0.0f;
+              for (int i = k + lane; i < T; i += 32) wk = fmaf(colk[i], uu[i], wk);
+              wk = warp_sum(wk);
+              if (lane == 0) s.w[(size_t)sx * TP + k] = wk;
+              pdk = fmaf(wk, s.v[(size_t)sx * TP + k], pdk);
+            }
+            if (lane == 0) s.pd[k] = 0.5f * pdk - 0.5f * g;
           }
-          s.pd[k] = 0.5f * pdk - 0.5f * g;
+        } else {
+          for (int k = G.chain.tid; k < T; k += G.chain.nt) {
+            float pdk = 0.0f;
+            for (int sx = 0; sx < S; ++sx) {
+              const float* uu = s.u + (size_t)sx * TP;
+              float wk = 0.0f;
+              for (int i = k; i < T; ++i) wk = fmaf(s.B2[(size_t)k * ld + i], uu[i], wk);
+              s.w[(size_t)sx * TP + k] = wk;
+              pdk = fmaf(wk, s.v[(size_t)sx * TP + k], pdk);
+            }
+            s.pd[k] = 0.5f * pdk - 0.5f * g;
+          }
         }
         phase_mark(P, 23);
         if (gm) (void)solve_gemm<true>(s.B2, s.rdq, nullptr, s.B2, L, T, s.pan, s.wide, s.stg);
