@@ -437,6 +437,157 @@ extern "C" int gpkl_recon_backward(int32_t B, int32_t F, int32_t S, int64_t tota
   return e == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
 }
 
+// ---- GP-recognition sampler ---------------------------------------------------------------
+// z = m + (chol(K(t, ell)) + diag(sqrt(exp(logvar)))) eps  and the per-row standard KL (GP_recog_VAE_prior.py:137-168,
+// :65-70, :274-276).  The chol(K) eps part is the sample of the fused GP op (gpkl_forward with the prior set to the
+// posterior's own lengthscales, whose KL output is discarded into the workspace); recog_fwd/bwd_kernel add the rest.
+namespace {
+struct RecogWs {
+  void* inner;
+  size_t inner_bytes;
+  int64_t* offsets;
+  float* kl_pairs;
+  double* scalars;  // [0] discarded kl_sum, [1] constant 0 (upstream gradient of the discarded KL)
+  size_t total;
+};
+GpklDesc recog_inner_desc(const GpklDesc& d) {
+  GpklDesc in = d;
+  in.posterior = GPKL_POST_GP;
+  in.flags = d.flags & ~GPKL_FLAG_GRAD_ELL_P;
+  return in;
+}
+RecogWs plan_recog(const GpklDesc& d, void* base) {
+  RecogWs w;
+  unsigned char* b = static_cast<unsigned char*>(base);
+  size_t off = 0;
+  const GpklDesc in = recog_inner_desc(d);
+  w.inner = b;
+  w.inner_bytes = plan(in, nullptr).total;
+  off += align_up(w.inner_bytes);
+  w.offsets = reinterpret_cast<int64_t*>(b + off);
+  off += align_up(((size_t)d.B + 1) * sizeof(int64_t));
+  w.kl_pairs = reinterpret_cast<float*>(b + off);
+  off += align_up((size_t)d.B * d.D * sizeof(float));
+  w.scalars = reinterpret_cast<double*>(b + off);
+  off += align_up(2 * sizeof(double));
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t gpkl_recog_workspace_bytes(const GpklDesc* desc) {
+  if (!desc) return 0;
+  const GpklDesc in = recog_inner_desc(*desc);
+  if (check_desc(&in) != GPKL_OK) return 0;
+  return plan_recog(*desc, nullptr).total;
+}
+
+extern "C" int gpkl_recog_forward(const GpklDesc* desc, const float* mean, const float* logvar, const float* times,
+                                  const int32_t* lengths, const float* ell, const float* eps, float* z, float* kl_rows,
+                                  double* kl_sum, int32_t* status, void* workspace, size_t ws_bytes, void* stream) {
+  if (!desc) return GPKL_ERR_NULL;
+  const GpklDesc in = recog_inner_desc(*desc);
+  int rc = check_desc(&in);
+  if (rc != GPKL_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!kl_sum) return GPKL_ERR_NULL;
+  if (in.B == 0 || in.total_T == 0) {
+    cudaMemsetAsync(kl_sum, 0, sizeof(double), st);
+    if (status) cudaMemsetAsync(status, 0, sizeof(int32_t), st);
+    return GPKL_OK;
+  }
+  if (!mean || !logvar || !times || !lengths || !ell || !eps || !z || !kl_rows || !workspace) return GPKL_ERR_NULL;
+  const RecogWs w = plan_recog(*desc, workspace);
+  if (ws_bytes < w.total) return GPKL_ERR_WORKSPACE;
+  rc = gpkl_forward(&in, mean, times, lengths, ell, ell, nullptr, eps, z, w.kl_pairs, w.scalars, nullptr, status, w.inner,
+                    w.inner_bytes, stream);
+  if (rc != GPKL_OK) return rc;
+  offsets_kernel<<<1, 1024, 0, st>>>(lengths, in.B, w.offsets);
+  note_launch();
+  if (launch_recog_fwd(mean, logvar, eps, reinterpret_cast<const long long*>(w.offsets), in.B, in.D, in.S, in.T_max,
+                       in.total_T, z, kl_rows, st) != cudaSuccess)
+    return GPKL_ERR_CUDA;
+  sum_pairs_kernel<<<1, 1024, 0, st>>>(kl_rows, (int)in.total_T, kl_sum);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
+}
+
+extern "C" int gpkl_recog_backward(const GpklDesc* desc, const float* mean, const float* logvar, const float* times,
+                                   const int32_t* lengths, const float* ell, const float* eps, const float* g_z,
+                                   const double* g_kl_sum, const float* g_kl_rows, float* g_mean, float* g_logvar,
+                                   float* g_ell, int32_t* status, void* workspace, size_t ws_bytes, void* stream) {
+  if (!desc) return GPKL_ERR_NULL;
+  const GpklDesc in = recog_inner_desc(*desc);
+  int rc = check_desc(&in);
+  if (rc != GPKL_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (in.B == 0 || in.total_T == 0) {
+    if (g_ell) cudaMemsetAsync(g_ell, 0, sizeof(float) * in.D, st);
+    if (status) cudaMemsetAsync(status, 0, sizeof(int32_t), st);
+    return GPKL_OK;
+  }
+  if (!mean || !logvar || !times || !lengths || !ell || !eps || !g_mean || !g_logvar || !g_ell || !workspace)
+    return GPKL_ERR_NULL;
+  const RecogWs w = plan_recog(*desc, workspace);
+  if (ws_bytes < w.total) return GPKL_ERR_WORKSPACE;
+  cudaMemsetAsync(w.scalars, 0, 2 * sizeof(double), st);
+  // sample path only: the discarded KL gets upstream gradient 0, so g_mean = sum_s g_z and g_ell = <L-bar, dL/d ell>
+  rc = gpkl_backward(&in, mean, times, lengths, ell, ell, nullptr, eps, g_z, w.scalars + 1, nullptr, g_mean, g_ell,
+                     nullptr, nullptr, status, w.inner, w.inner_bytes, stream);
+  if (rc != GPKL_OK) return rc;
+  offsets_kernel<<<1, 1024, 0, st>>>(lengths, in.B, w.offsets);
+  note_launch();
+  if (launch_recog_bwd(mean, logvar, eps, g_z, g_kl_sum, g_kl_rows, reinterpret_cast<const long long*>(w.offsets), in.B,
+                       in.D, in.S, in.T_max, in.total_T, g_mean, g_logvar, st) != cudaSuccess)
+    return GPKL_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
+}
+
+// ---- ragged batch producer ---------------------------------------------------------------
+namespace {
+struct CollateWs {
+  int64_t* offsets;
+  size_t total;
+};
+CollateWs plan_collate(int B, int max_time, void* base) {
+  CollateWs w;
+  unsigned char* b = static_cast<unsigned char*>(base);
+  size_t off = 0;
+  w.offsets = reinterpret_cast<int64_t*>(b + off);
+  off += align_up(((size_t)B + 1) * sizeof(int64_t));
+  (void)max_time;
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t gpkl_collate_workspace_bytes(int32_t B, int32_t max_time) {
+  return (B < 0 || max_time < 0) ? 0 : plan_collate(B, max_time, nullptr).total;
+}
+
+extern "C" int gpkl_collate(int32_t N, int32_t F, int32_t T_full, int32_t B, int32_t max_time, const float* data,
+                            const float* time_grid, const int32_t* index, float* x, float* times, int32_t* lengths,
+                            int64_t* total_T, void* workspace, size_t ws_bytes, void* stream) {
+  if (N < 0 || F <= 0 || T_full < 0 || B < 0 || max_time < 0) return GPKL_ERR_DESC;
+  if (!index && B > N) return GPKL_ERR_DESC;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0) {
+    if (total_T) cudaMemsetAsync(total_T, 0, sizeof(int64_t), st);
+    return GPKL_OK;
+  }
+  if (!data || !time_grid || !x || !times || !lengths || !workspace) return GPKL_ERR_NULL;
+  const CollateWs w = plan_collate(B, max_time, workspace);
+  if (ws_bytes < w.total) return GPKL_ERR_WORKSPACE;
+  if (launch_collate_scan(data, time_grid, index, B, F, T_full, max_time, lengths, times, st) != cudaSuccess)
+    return GPKL_ERR_CUDA;
+  offsets_kernel<<<1, 1024, 0, st>>>(lengths, B, w.offsets);
+  note_launch();
+  if (launch_collate_gather(data, index, reinterpret_cast<const long long*>(w.offsets), B, F, T_full, max_time, x, st) != cudaSuccess)
+    return GPKL_ERR_CUDA;
+  if (total_T) cudaMemcpyAsync(total_T, w.offsets + B, sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
+  return cudaGetLastError() == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
+}
+
 // ---- host-buffer step ---------------------------------------------------------------------------
 namespace {
 struct Staging {

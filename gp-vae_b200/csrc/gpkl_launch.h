@@ -49,4 +49,16 @@ cudaError_t launch_recon_fwd(const float* x, const float* xd, const long long* o
 cudaError_t launch_recon_bwd(const float* x, const float* xd, const long long* off, int B, int F, int S, long long rows,
                              const double* g_recon, float* g_xd, cudaStream_t st);
 
+
+// rows either side of the path (gpkl_adjacent.cu), SURVEY.md S8(f) rows 3 and 4
+cudaError_t launch_recog_fwd(const float* mean, const float* logvar, const float* eps, const long long* off, int B, int D,
+                             int S, int T_max, long long rows, float* z, float* kl_rows, cudaStream_t st);
+cudaError_t launch_recog_bwd(const float* mean, const float* logvar, const float* eps, const float* g_z,
+                             const double* g_kl_sum, const float* g_kl_rows, const long long* off, int B, int D, int S,
+                             int T_max, long long rows, float* g_mean, float* g_logvar, cudaStream_t st);
+cudaError_t launch_collate_scan(const float* data, const float* grid, const int32_t* index, int B, int F, int T_full,
+                                int max_time, int32_t* lengths, float* times, cudaStream_t st);
+cudaError_t launch_collate_gather(const float* data, const int32_t* index, const long long* off, int B, int F, int T_full,
+                                  int max_time, float* x, cudaStream_t st);
+
 }  // namespace gpkl

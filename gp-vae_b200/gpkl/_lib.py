@@ -16,7 +16,8 @@ FLAG_PER_PAIR_PRIOR = 2
 SYMBOLS = ("gpkl_version", "gpkl_strerror", "gpkl_workspace_bytes", "gpkl_forward", "gpkl_backward",
            "gpkl_step_host_bytes", "gpkl_step_host", "gpkl_launch_count", "gpkl_profile_enable",
            "gpkl_profile_read", "gpkl_fp32_peak_launch", "gpkl_recon_workspace_bytes", "gpkl_recon_forward",
-           "gpkl_recon_backward")
+           "gpkl_recon_backward", "gpkl_recog_workspace_bytes", "gpkl_recog_forward", "gpkl_recog_backward",
+           "gpkl_collate_workspace_bytes", "gpkl_collate")
 
 
 class GpklDesc(ctypes.Structure):
@@ -69,6 +70,16 @@ def lib():
     L.gpkl_recon_forward.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, i64, vp, vp, vp, vp, vp, sz, vp]
     L.gpkl_recon_backward.restype = i32
     L.gpkl_recon_backward.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, i64, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.gpkl_recog_workspace_bytes.restype = sz
+    L.gpkl_recog_workspace_bytes.argtypes = [dp]
+    L.gpkl_recog_forward.restype = i32
+    L.gpkl_recog_forward.argtypes = [dp] + [vp] * 10 + [vp, sz, vp]
+    L.gpkl_recog_backward.restype = i32
+    L.gpkl_recog_backward.argtypes = [dp] + [vp] * 13 + [vp, sz, vp]
+    L.gpkl_collate_workspace_bytes.restype = sz
+    L.gpkl_collate_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    L.gpkl_collate.restype = i32
+    L.gpkl_collate.argtypes = [ctypes.c_int32] * 5 + [vp] * 7 + [vp, sz, vp]
     _lib = L
     return L
 

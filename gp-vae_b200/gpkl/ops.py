@@ -268,3 +268,103 @@ def bernoulli_recon(x, x_decode, lengths, S=1):
 def elbo_loss(x, x_decode, lengths, kl_sum, beta=1.0, S=1):
     """loss = recon + beta * KL  (Full_GP_VAE_dynamic_time.py:358-360; beta warm-up: syndata/GP_VAE_syn_data.py:361-364)."""
     return bernoulli_recon(x, x_decode, lengths, S) + beta * kl_sum
+
+
+# ---- GP-recognition sampler (SURVEY.md S8(f) row 3) ----------------------------------------------------------------
+def _named_ws(name, n, device):
+    key = (name, device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 1 << 16), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def _recog_setup(mean, logvar, times, lengths, ell, eps, kernel, noise, S, tier):
+    if not mean.is_cuda:
+        raise RuntimeError("gpkl: tensors must live on a CUDA device (there is no CPU implementation)")
+    B, T_max = times.shape
+    total_T, D = mean.shape
+    assert logvar.shape == (total_T, D) and ell.shape == (D,) and eps.shape == (B, D, S, T_max)
+    assert lengths.shape == (B,) and lengths.dtype == torch.int32
+    for t in (mean, logvar, times, ell, eps):
+        assert t.dtype == torch.float32 and t.is_contiguous(), "float32 contiguous tensors required"
+    desc = _make_desc(B, D, T_max, S, total_T, kernel, "gp", noise, 0, tier)
+    n = _lib.lib().gpkl_recog_workspace_bytes(ctypes.byref(desc))
+    if n == 0:
+        raise RuntimeError("gpkl: inconsistent descriptor")
+    return desc, _named_ws("recog", n, mean.device), n
+
+
+class GpRecogSample(torch.autograd.Function):
+    """(mean, logvar, times, lengths, ell, eps) -> (z, kl_sum, kl_rows): the sampler and KL of GP_recog_VAE_prior.py
+    (:65-70, :137-168, :170-191), differentiable in mean, logvar and ell (approx_time_chars, :81)."""
+
+    @staticmethod
+    def forward(ctx, mean, logvar, times, lengths, ell, eps, kernel, noise, S, tier):
+        desc, ws, n = _recog_setup(mean, logvar, times, lengths, ell, eps, kernel, noise, S, tier)
+        dev = mean.device
+        z = torch.empty(S * mean.shape[0], mean.shape[1], dtype=torch.float32, device=dev)
+        kl_rows = torch.empty(mean.shape[0], dtype=torch.float32, device=dev)
+        kl_sum = torch.empty((), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().gpkl_recog_forward(ctypes.byref(desc), _ptr(mean), _ptr(logvar), _ptr(times), _ptr(lengths),
+                                                 _ptr(ell), _ptr(eps), _ptr(z), _ptr(kl_rows), _ptr(kl_sum), None,
+                                                 _ptr(ws), n, _stream(dev)))
+        ctx.save_for_backward(mean, logvar, times, lengths, ell, eps)
+        ctx.cfg = (kernel, noise, S, tier)
+        return z, kl_sum, kl_rows
+
+    @staticmethod
+    def backward(ctx, g_z, g_kl_sum, g_kl_rows):
+        mean, logvar, times, lengths, ell, eps = ctx.saved_tensors
+        kernel, noise, S, tier = ctx.cfg
+        desc, ws, n = _recog_setup(mean, logvar, times, lengths, ell, eps, kernel, noise, S, tier)
+        dev = mean.device
+        if g_kl_sum is None:
+            g_kl_sum = torch.zeros((), dtype=torch.float64, device=dev)
+        g_kl_sum = g_kl_sum.to(torch.float64).reshape(()).contiguous()
+        g_z = None if g_z is None else g_z.contiguous()
+        g_kl_rows = None if g_kl_rows is None else g_kl_rows.contiguous()
+        g_mean, g_logvar = torch.empty_like(mean), torch.empty_like(logvar)
+        g_ell = torch.empty_like(ell)
+        _lib.check(_lib.lib().gpkl_recog_backward(ctypes.byref(desc), _ptr(mean), _ptr(logvar), _ptr(times), _ptr(lengths),
+                                                  _ptr(ell), _ptr(eps), _ptr(g_z), _ptr(g_kl_sum), _ptr(g_kl_rows),
+                                                  _ptr(g_mean), _ptr(g_logvar), _ptr(g_ell), None, _ptr(ws), n,
+                                                  _stream(dev)))
+        return g_mean, g_logvar, None, None, g_ell, None, None, None, None, None
+
+
+def gp_recog_sample(mean, logvar, times, lengths, ell, eps=None, *, kernel="rbf", noise=1e-3, S=1, tier="auto",
+                    generator=None):
+    """GP-recognition sampler: z = mean + (chol(K(times, ell)) + diag(sqrt(exp(logvar)))) eps and the standard KL of the
+    rows (GP_recog_VAE_prior.py:274-284).  Returns (z [S*sum_T, D] f32, kl_sum f64 scalar, kl_rows [sum_T] f32)."""
+    if eps is None:
+        B, T_max = times.shape
+        eps = torch.randn(B, mean.shape[1], S, T_max, device=mean.device, dtype=torch.float32, generator=generator)
+    return GpRecogSample.apply(mean, logvar, times, lengths, ell, eps, kernel, float(noise), int(S), tier)
+
+
+# ---- ragged batch producer (SURVEY.md S8(f) row 4) -----------------------------------------------------------------
+def collate_batch(data, time_grid, index=None, max_time=None, batch_size=None):
+    """GPU-side SyntheticDataHandler._prep_dataset + data_batch (DataHandler.py:111-156) for one batch.
+    data [N, F, T_full] f32 CUDA with -1 at missing time points, time_grid [T_full], index [B] int32 (None: the first
+    batch_size sequences).  Returns (x [sum_T, F], times [B, max_time], lengths [B] int32) -- the feed of
+    Full_GP_VAE_dynamic_time.py:377-378.  One host read (sum_T) sizes the returned view of x."""
+    if not data.is_cuda:
+        raise RuntimeError("gpkl: tensors must live on a CUDA device (there is no CPU implementation)")
+    N, F, T_full = data.shape
+    max_time = T_full if max_time is None else int(max_time)
+    B = int(index.shape[0]) if index is not None else int(N if batch_size is None else batch_size)
+    assert data.dtype == torch.float32 and data.is_contiguous() and time_grid.shape == (T_full,)
+    assert time_grid.dtype == torch.float32 and time_grid.is_contiguous()
+    assert index is None or (index.dtype == torch.int32 and index.is_contiguous())
+    dev = data.device
+    x = torch.empty(B * min(T_full, max_time), F, dtype=torch.float32, device=dev)
+    times = torch.empty(B, max_time, dtype=torch.float32, device=dev)
+    lengths = torch.empty(B, dtype=torch.int32, device=dev)
+    total = torch.zeros((), dtype=torch.int64, device=dev)
+    n = _lib.lib().gpkl_collate_workspace_bytes(B, max_time)
+    ws = _named_ws("collate", n, dev)
+    _lib.check(_lib.lib().gpkl_collate(N, F, T_full, B, max_time, _ptr(data), _ptr(time_grid), _ptr(index), _ptr(x),
+                                       _ptr(times), _ptr(lengths), _ptr(total), _ptr(ws), n, _stream(dev)))
+    return x[: int(total.item())], times, lengths

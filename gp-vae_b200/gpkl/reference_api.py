@@ -74,3 +74,76 @@ class GPPriorPath:
         assert isinstance(approx_linear_kernel, KernelHandle) and isinstance(prior_kernel, KernelHandle)
         _, kl_sum, kl_pairs = self._run(mean)
         return kl_sum, kl_pairs
+
+
+class GPRecogPath:
+    """The GP-recognition model's call sites (src/Models/GP_recog_VAE_prior.py:274-284) over gp_recog_sample:
+
+        kl                                   = standard_vae_kl(latent_mean, latent_log_var, latent_size)
+        approx_kernel, chol_noise, time_chars = approx_kernels(sequences, sizes, latent_size, batch_size, S, latent_log_var)
+        latent_sample                        = gp_vae_sample(latent_mean, chol_noise, sizes, batch_size, S, latent_size)
+
+    approx_kernels records what to build; gp_vae_sample launches the fused op; standard_vae_kl returns the reference's
+    value (+1/2 sum(1 + log(1e-10+var) - mean^2 - var) per row, i.e. MINUS the KL, :69) from the same launch when the
+    sample has already been drawn for this (mean, log_var), else from a launch of its own."""
+
+    def __init__(self, latent_size, *, kernel="rbf", noise=1e-3, approx_lengthscale=1.0, device="cuda:0", tier="auto"):
+        dev = torch.device(device)
+        # tf.Variable(tf.constant(1.0, shape=[latent_size,1]), name='approx_time_chars')   (:81)
+        self.approx_time_chars = torch.nn.Parameter(torch.full((latent_size,), float(approx_lengthscale), device=dev))
+        self.latent_size, self.kernel, self.noise, self.tier = latent_size, kernel, noise, tier
+        self._seq = None
+        self._cache = None
+
+    def parameters(self):
+        return [self.approx_time_chars]
+
+    def approx_kernels(self, sequences, sequence_sizes, latent_size, batch_size, number_samples, encode_log_var, eps=None):
+        assert latent_size == self.latent_size and sequences.shape[0] == batch_size
+        self._seq = (sequences.contiguous().float(), sequence_sizes.to(torch.int32).contiguous())
+        self._logvar, self.number_samples, self._eps = encode_log_var, number_samples, eps
+        self._cache = None
+        h = KernelHandle(self, "approx", self.approx_time_chars)
+        return h, h, self.approx_time_chars
+
+    def _run(self, mean, logvar):
+        from .ops import gp_recog_sample
+        if self._cache is None or self._cache[0] is not mean or self._cache[1] is not logvar:
+            times, lengths = self._seq
+            out = gp_recog_sample(mean.contiguous(), logvar.contiguous(), times, lengths, self.approx_time_chars, self._eps,
+                                  kernel=self.kernel, noise=self.noise, S=self.number_samples, tier=self.tier)
+            self._cache = (mean, logvar, out)
+        return self._cache[2]
+
+    def gp_vae_sample(self, mean, noise_chol_full_time, sequence_sizes, batch_size, number_samples, latent_size):
+        assert isinstance(noise_chol_full_time, KernelHandle) and number_samples == self.number_samples
+        return self._run(mean, self._logvar)[0]
+
+    def standard_vae_kl(self, mean, log_var, latent_size):
+        assert self._seq is not None, "call approx_kernels first (it records the time stamps the fused op needs)"
+        return -self._run(mean, log_var)[2]
+
+
+class SyntheticDataHandlerGPU:
+    """SyntheticDataHandler.data_batch (src/Models/DataHandler.py:111-127) with the array resident on the GPU: the
+    -1-masked data [N, F, T_full] and data['time'] are uploaded once; every data_batch() collates the next batch_size
+    sequences on the device (gpkl.collate_batch) and returns (batch_xs, batch_time_steps, batch_lengths) as CUDA tensors.
+    Reshuffling at the end of an epoch permutes an index vector instead of the data (:116-117, :137)."""
+
+    def __init__(self, data, max_time, batch_size=5, device="cuda:0", generator=None):
+        dev = torch.device(device)
+        self.x = torch.as_tensor(data["x"], dtype=torch.float32).to(dev).contiguous()
+        self.time = torch.as_tensor(data["time"], dtype=torch.float32).to(dev).contiguous()
+        self.max_time, self.batch_size, self.generator = max_time, batch_size, generator
+        self.order = torch.arange(self.x.shape[0], dtype=torch.int32, device=dev)
+        self.counter = 0
+
+    def data_batch(self, data_name="train"):
+        from .ops import collate_batch
+        n = self.x.shape[0]
+        if self.counter + self.batch_size > n:
+            self.order = torch.randperm(n, generator=self.generator).to(torch.int32).to(self.x.device)
+            self.counter = 0
+        index = self.order[self.counter:self.counter + self.batch_size].contiguous()
+        self.counter += self.batch_size
+        return collate_batch(self.x, self.time, index, self.max_time)

@@ -131,6 +131,37 @@ int gpkl_recon_backward(int32_t B, int32_t F, int32_t S, int64_t total_T, const 
                         const int32_t* lengths, const double* g_recon, float* g_x_decode, void* workspace,
                         size_t ws_bytes, void* stream);
 
+/* ---- GP-recognition sampler ------------------------------------------------------------
+ * Replaces approx_kernels / tf_kernel_approx / gp_vae_sample / standard_vae_kl of src/Models/GP_recog_VAE_prior.py
+ * (:72-117, :137-168, :170-191, :65-70; call sites :274-284):
+ *   z_s  = m + (chol(K(t, ell)) + diag(sqrt(exp(logvar)))) eps_s        per (sequence, latent-dim) pair
+ *   kl_rows[r] = -1/2 sum_d (1 + log(1e-10 + exp(logvar)) - mean^2 - exp(logvar))   per row r of mean (:69, :276)
+ *   kl_sum = sum_r kl_rows[r]  (:277)
+ * desc: B, D, T_max, S, total_T, kernel, noise, tier as for gpkl_forward; `posterior` is ignored.  logvar [total_T, D],
+ * ell [D] = approx_time_chars (:81), eps [B, D, S, T_max], z [S*total_T, D] in the layout of gpkl_forward.
+ * Backward of  Loss = g_kl_sum*kl_sum + <g_kl_rows, kl_rows> + <g_z, z>  (g_kl_sum DEVICE f64, NULL == 1; g_kl_rows,
+ * g_z may be NULL == 0): g_mean, g_logvar [total_T, D], g_ell [D]. */
+size_t gpkl_recog_workspace_bytes(const GpklDesc* desc);
+int gpkl_recog_forward(const GpklDesc* desc, const float* mean, const float* logvar, const float* times,
+                       const int32_t* lengths, const float* ell, const float* eps, float* z, float* kl_rows,
+                       double* kl_sum, int32_t* status, void* workspace, size_t ws_bytes, void* stream);
+int gpkl_recog_backward(const GpklDesc* desc, const float* mean, const float* logvar, const float* times,
+                        const int32_t* lengths, const float* ell, const float* eps, const float* g_z,
+                        const double* g_kl_sum, const float* g_kl_rows, float* g_mean, float* g_logvar, float* g_ell,
+                        int32_t* status, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- ragged batch producer ----------------------------------------------------------------
+ * Replaces SyntheticDataHandler._prep_dataset + data_batch (src/Models/DataHandler.py:129-156, :111-127) for one batch:
+ * data [N, F, T_full] f32 with -1 marking missing time points (:143-145; validity is read from feature 0, the reference
+ * requires the mask to be the same for every feature), time_grid [T_full] f32 (data['time']), index [B] i32 = the
+ * sequences of this batch (NULL == 0..B-1).  Outputs: x [sum_T, F] rows sequence-major then time (capacity
+ * B*min(T_full, max_time) rows), times [B, max_time] zero padded on the right (:149-151), lengths [B], *total_T (device
+ * int64, may be NULL).  Sequences longer than max_time are truncated (the reference's np.pad raises there). */
+size_t gpkl_collate_workspace_bytes(int32_t B, int32_t max_time);
+int gpkl_collate(int32_t N, int32_t F, int32_t T_full, int32_t B, int32_t max_time, const float* data,
+                 const float* time_grid, const int32_t* index, float* x, float* times, int32_t* lengths,
+                 int64_t* total_T, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- measurement hooks (bench.py; not part of the data path) ------------------------------------
  * These are the only process-global state in the library and are not thread safe.
  * gpkl_launch_count: kernels this library has launched since load (bench.py's gpu_launches).

@@ -30,6 +30,8 @@ tf = tf1_stub.install()
 import Full_GP_VAE_dynamic_time as dyn  # noqa: E402  (reference, unmodified)
 import Full_GP_VAE_fixed_for_MovMnist as fixed  # noqa: E402
 import VAE_GPprior_diag_cov as diagcov  # noqa: E402
+import GP_recog_VAE_prior as recog  # noqa: E402
+import DataHandler as datahandler  # noqa: E402
 
 
 class _Vars:
@@ -165,6 +167,59 @@ def run_recon(name):
           recon=ns["sum_recon_loss"], loss=ns["loss"], beta=0.7, kl=12.5, g_x_decode=x_decode.grad)
 
 
+def run_recog(name, times, lengths, mean, logvar, ell, S, seed):
+    """GP-recognition sampler: the calls of GP_recog_VAE_prior.main() (:274-284) -- standard_vae_kl, approx_kernels
+    (tf_kernel_approx: float64 Cholesky + diag sqrt(var)), gp_vae_sample -- and autograd through them (:305)."""
+    B, T_max = times.shape
+    D = mean.shape[1]
+    lengths_t = torch.tensor(lengths, dtype=torch.int32)
+    mean = mean.clone().requires_grad_(True)
+    logvar = logvar.clone().requires_grad_(True)
+    lq = ell.clone().reshape(D, 1).requires_grad_(True)
+    _seeded_noise(seed)
+    kl = recog.standard_vae_kl(mean, logvar, D)
+    kl = tf.scalar_mul(-1.0, tf.cast(kl, tf.float64))                      # :275-276
+    sum_kl = tf.reduce_sum(kl)                                              # :277
+    n0 = len(tf1_stub.RANDOM_LOG)
+    with _Vars(lq):
+        approx_kernel, chol_noise, chars = recog.approx_kernels(times, lengths_t, D, B, S, logvar)
+    draws = tf1_stub.RANDOM_LOG[n0:]
+    assert len(draws) == B * D
+    eps = torch.zeros(B, D, S, T_max)
+    for b in range(B):
+        for d in range(D):
+            r = draws[b * D + d]            # [T_b, S]   (tf_kernel_approx :159)
+            eps[b, d, :, : r.shape[0]] = r.t()
+    z = recog.gp_vae_sample(mean, chol_noise, lengths_t, B, S, D)
+    g = torch.Generator().manual_seed(seed + 1)
+    g_z = torch.randn(z.shape, generator=g, dtype=torch.float32)
+    g_rows = torch.randn(kl.shape, generator=g, dtype=torch.float32)
+    loss = 0.7 * sum_kl + (g_rows.to(torch.float64) * kl).sum() + (g_z.to(torch.float64) * z.to(torch.float64)).sum()
+    loss.backward()
+    _save(name, variant="recog", kernel="rbf", noise=1e-3, S=S, times=times, lengths=np.asarray(lengths, np.int32),
+          mean=mean, logvar=logvar, ell=lq.reshape(-1), eps=eps, g_z=g_z, g_kl_rows=g_rows, g_kl_sum=0.7, z=z,
+          kl_rows=kl.reshape(-1), kl_sum=sum_kl, g_mean=mean.grad, g_logvar=logvar.grad, g_ell=lq.grad.reshape(-1))
+
+
+def run_collate(name):
+    """Ragged batch producer: SyntheticDataHandler (DataHandler.py:96-162) on a synthetic -1-masked array with the
+    reference's hard-coded 15 features (:145); two consecutive data_batch('train') calls."""
+    rng = np.random.RandomState(31)
+    N, F, T_full, max_time, bs = 8, 15, 45, 45, 3
+    grid = np.linspace(0.0, 60.0, T_full).astype(np.float32)
+    x = rng.rand(N, F, T_full).astype(np.float32)
+    for i in range(N):
+        drop = rng.rand(T_full) < 0.35
+        x[i][:, drop] = -1.0
+    h = datahandler.SyntheticDataHandler({"x": x.copy(), "time": grid}, max_time, batch_size=bs, train_fraction=0.75)
+    out = {}
+    for k in range(2):
+        bx, bt, bl = h.data_batch("train")
+        out["x%d" % k], out["times%d" % k], out["lengths%d" % k] = bx, bt, np.asarray(bl, np.int32)
+        out["index%d" % k] = np.arange(k * bs, (k + 1) * bs, dtype=np.int32)
+    _save(name, variant="collate", data=x, time_grid=grid, max_time=max_time, **out)
+
+
 def main():
     torch.manual_seed(0)
     # G1 -- SURVEY.md Appendix B golden case (regular grid, B=3 D=4 T=6)
@@ -201,6 +256,22 @@ def main():
     run_diag("g2_v2_diag")
     # G6 -- reconstruction term and beta-weighted loss (next row after the path)
     run_recon("g6_recon_loss")
+    # G7 -- GP-recognition sampler (S8(f) row 3): ragged, irregular, S=2
+    g = torch.Generator().manual_seed(8)
+    lengths = [8, 5, 11]
+    B, D, T_max = 3, 4, 11
+    times = torch.cumsum(torch.rand(B, T_max, generator=g) + 0.5, 1).float()
+    for b, L in enumerate(lengths):
+        times[b, L:] = 0
+    run_recog("g7_recog_ragged_s2", times, lengths, torch.randn(sum(lengths), D, generator=g),
+              0.5 * torch.randn(sum(lengths), D, generator=g) - 0.5, torch.tensor([1.0, 0.6, 1.8, 2.5]), S=2, seed=15)
+    # G8 -- the reference's own configuration of that model: T=20 grid 0..19, ell = 1 (:81), S=1
+    g = torch.Generator().manual_seed(9)
+    B, D, T = 3, 6, 20
+    run_recog("g8_recog_grid", torch.arange(T, dtype=torch.float32).repeat(B, 1), [T] * B,
+              torch.randn(B * T, D, generator=g), 0.3 * torch.randn(B * T, D, generator=g) - 1.0, torch.ones(D), S=1, seed=16)
+    # G9 -- ragged batch producer (S8(f) row 4)
+    run_collate("g9_collate")
 
 
 if __name__ == "__main__":

@@ -233,6 +233,67 @@ def bernoulli_recon(x, x_decode, lengths, S=1):
     return rec.to(torch.float64).sum() / S   # mean over the S samples of every (sequence, time) row, then the sum
 
 
+def gp_recog_sample(mean, logvar, times, lengths, ell, eps, *, kernel=RBF, noise=1e-3, S=1, build_dtype=torch.float32):
+    """GP-recognition sampler + standard KL (src/Models/GP_recog_VAE_prior.py): tf_kernel_approx builds K in float32, casts
+    to float64, L = chol(K) + diag(sqrt(exp(logvar))) (:150-158), noise = L eps (:160-162); gp_vae_sample adds it to the
+    mean (:170-191); standard_vae_kl (:65-70) per row of mean, cast to float64 and negated (:274-277).
+    Returns dict z [S*sum_T, D] f64 (layout of gp_prior_kl), kl_rows [sum_T] f64, kl_sum."""
+    lengths_l = [int(x) for x in (lengths.tolist() if hasattr(lengths, "tolist") else lengths)]
+    B, D = len(lengths_l), mean.shape[1]
+    offs = np.concatenate([[0], np.cumsum(lengths_l)]).astype(np.int64)
+    mean64, lv64 = mean.to(torch.float64), logvar.to(torch.float64)
+    var = torch.exp(lv64)
+    kl_rows = -0.5 * (1.0 + torch.log(1e-10 + var) - mean64 ** 2 - var).sum(1)
+    z_rows = []
+    for b, T in enumerate(lengths_l):
+        if T == 0:
+            z_rows.append(torch.zeros(0, D, dtype=torch.float64))
+            continue
+        rows = slice(int(offs[b]), int(offs[b]) + T)
+        t = times[b, :T].unsqueeze(0).expand(D, T)
+        K = kernel_matrix(t, ell, kernel, noise, build_dtype)               # [D, T, T] float64 values of a float32 build
+        L = torch.linalg.cholesky(K) + torch.diag_embed(torch.sqrt(var[rows].t()))
+        e = eps[b][..., :T].to(torch.float64)                               # [D, S, T]
+        zz = mean64[rows].t().unsqueeze(1) + (L.unsqueeze(1) @ e.unsqueeze(-1)).squeeze(-1)   # [D, S, T]
+        z_rows.append(zz.permute(1, 2, 0).reshape(S * T, D))
+    return {"z": torch.cat(z_rows, 0) if B else torch.zeros(0, D, dtype=torch.float64), "kl_rows": kl_rows,
+            "kl_sum": kl_rows.sum()}
+
+
+def gp_recog_grads(mean, logvar, times, lengths, ell, eps, g_z, g_kl_sum=1.0, g_kl_rows=None, **kw):
+    """Forward + autograd backward of L = g_kl_sum*kl_sum + <g_kl_rows, kl_rows> + <g_z, z> (TF autodiff, :305)."""
+    mean = mean.detach().clone().requires_grad_(True)
+    logvar = logvar.detach().clone().requires_grad_(True)
+    ell = ell.detach().clone().requires_grad_(True)
+    out = gp_recog_sample(mean, logvar, times, lengths, ell, eps, **kw)
+    loss = g_kl_sum * out["kl_sum"]
+    if g_kl_rows is not None:
+        loss = loss + (g_kl_rows.to(torch.float64) * out["kl_rows"]).sum()
+    if g_z is not None:
+        loss = loss + (g_z.to(torch.float64) * out["z"]).sum()
+    loss.backward()
+    grads = {"mean": mean.grad.detach(), "logvar": logvar.grad.detach(),
+             "ell": torch.zeros_like(ell) if ell.grad is None else ell.grad.detach()}
+    return {k: v.detach() for k, v in out.items()}, grads
+
+
+def collate_batch(data, time_grid, index, max_time):
+    """Ragged batch producer: numpy restatement of SyntheticDataHandler._prep_dataset (src/Models/DataHandler.py:129-156)
+    for the sequences `index` (data_batch :111-127 slices consecutive ones): valid time points are those whose feature-0
+    value is > -1 (:143), the kept values are packed [T_b, F] (:145), the time stamps zero padded to max_time (:149-151).
+    data [N, F, T_full], time_grid [T_full].  Returns x [sum_T, F], times [B, max_time], lengths [B] int32."""
+    xs, ts, ls = [], [], []
+    for i in index:
+        keep = np.where(data[i, 0, :] > -1)[0][:max_time]
+        xs.append(data[i][:, keep].T)
+        ts.append(np.pad(time_grid[keep], (0, max_time - len(keep)), "constant", constant_values=0))
+        ls.append(len(keep))
+    F = data.shape[1]
+    x = np.concatenate(xs, 0) if xs else np.zeros((0, F), data.dtype)
+    return x.astype(np.float32), np.stack(ts).astype(np.float32) if ts else np.zeros((0, max_time), np.float32), \
+        np.asarray(ls, np.int32)
+
+
 def gp_kl_div_numpy(m, Kq, Kp):
     """Single-pair numpy float64 transcription of gp_kl_div (Full_GP_VAE_dynamic_time.py:242-260),
     independent of torch -- second opinion for the golden tests."""

@@ -118,3 +118,28 @@ def test_recon_loss_matches_reference_lines():
     assert abs(float(rec) - float(g["recon"])) < 1e-12 * abs(float(g["recon"]))
     assert abs(float(rec) + g["beta"] * g["kl"] - float(g["loss"])) < 1e-12 * abs(float(g["loss"]))
     assert rel_err(xd.grad, g["g_x_decode"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["g7_recog_ragged_s2", "g8_recog_grid"])
+def test_recog_oracle_matches_reference(name):
+    """G7/G8: GP_recog_VAE_prior.{standard_vae_kl, approx_kernels, gp_vae_sample} executed under the stub (S8(f) row 3)."""
+    g = load_golden(name)
+    out, grads = orc.gp_recog_grads(g["mean"], g["logvar"], g["times"], g["lengths"], g["ell"], g["eps"], g["g_z"],
+                                    float(g["g_kl_sum"]), g["g_kl_rows"], S=g["S"])
+    assert rel_err(out["kl_rows"], g["kl_rows"]) < 1e-6      # the reference sums the row in float32 (:69)
+    assert abs(float(out["kl_sum"]) - float(g["kl_sum"])) < 1e-6 * abs(float(g["kl_sum"]))
+    assert rel_err(out["z"], g["z"]) < 1e-6                  # float32 matmul L eps in the reference (:158-160)
+    assert rel_err(grads["mean"], g["g_mean"]) < 2e-6
+    assert rel_err(grads["logvar"], g["g_logvar"]) < 2e-6
+    assert rel_err(grads["ell"], g["g_ell"]) < 2e-5
+
+
+def test_collate_oracle_matches_reference():
+    """G9: SyntheticDataHandler._prep_dataset + data_batch (DataHandler.py:111-156) on a -1-masked array (S8(f) row 4)."""
+    g = load_golden("g9_collate")
+    data, grid, mt = g["data"].numpy(), g["time_grid"].numpy(), int(g["max_time"])
+    for k in range(2):
+        x, times, lengths = orc.collate_batch(data, grid, g["index%d" % k].numpy(), mt)
+        assert (x == g["x%d" % k].numpy()).all() and x.shape == tuple(g["x%d" % k].shape)
+        assert (times == g["times%d" % k].numpy()).all()
+        assert (lengths == g["lengths%d" % k].numpy()).all()
