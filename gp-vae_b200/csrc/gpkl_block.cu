@@ -59,21 +59,23 @@ __device__ __forceinline__ void tile_fma(float (&acc)[4][4], const float4& u4, c
 
 // acc (+/-)= sum_{j in [ja, jb)} U[j*ldu + 0..3] (x) V[j*ldv + 0..3].  Main loop in groups of 8 steps with all
 // 16 operand loads issued before the FMAs (memory-level parallelism when the operands come from L1/L2).
-template <int SGN>
+// VNEG: V is walked with stride -ldv (the row-reversed C' of the one-buffer backward).
+template <int SGN, bool VNEG = false>
 __device__ __forceinline__ void tile_update(float (&acc)[4][4], const float* __restrict__ U, int ldu,
                                             const float* __restrict__ V, int ldv, int ja, int jb) {
+  const ptrdiff_t sv = VNEG ? -(ptrdiff_t)ldv : (ptrdiff_t)ldv;
   const float* up = U + (size_t)ja * ldu;
-  const float* vp = V + (size_t)ja * ldv;
+  const float* vp = V + (ptrdiff_t)ja * sv;
   int j = ja;
   for (; j + 8 <= jb; j += 8) {
     float4 u4[8], v4[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       u4[e] = *reinterpret_cast<const float4*>(up + (size_t)e * ldu);
-      v4[e] = *reinterpret_cast<const float4*>(vp + (size_t)e * ldv);
+      v4[e] = *reinterpret_cast<const float4*>(vp + (ptrdiff_t)e * sv);
     }
     up += (size_t)8 * ldu;
-    vp += (size_t)8 * ldv;
+    vp += (ptrdiff_t)8 * sv;
 #pragma unroll
     for (int e = 0; e < 8; ++e) tile_fma<SGN>(acc, u4[e], v4[e]);
   }
@@ -81,7 +83,7 @@ __device__ __forceinline__ void tile_update(float (&acc)[4][4], const float* __r
     const float4 u4 = *reinterpret_cast<const float4*>(up);
     const float4 v4 = *reinterpret_cast<const float4*>(vp);
     up += ldu;
-    vp += ldv;
+    vp += sv;
     tile_fma<SGN>(acc, u4, v4);
   }
 }
@@ -132,16 +134,18 @@ struct Lay {  // shared-memory carve-up (floats), identical on host and device
   __host__ __device__ bool dual(bool resident) const { return resident && TP > 64; }
   // gemm: workspace path whose 64-wide panels live in shared memory and are updated by the staged GEMM tile
   __host__ __device__ bool gemm(bool resident) const { return !resident && TP > GEMM_TMIN && TP <= GEMM_TMAX; }
-  __host__ __device__ size_t floats(bool resident) const {
-    return 64 + (resident ? 2 * buf() : (size_t)STG_FLOATS) + (gemm(resident) ? (size_t)NBL * ld : 0) +
-           (dual(resident) ? 2 : 1) * (size_t)NB * ld + ld + 9 * (size_t)TP + 3 * (size_t)S * TP;
+  // onebuf: the resident shared-prior kernels need ONE work matrix (B2: L_q / X_q, and in backward the row-reversed
+  // C' in the triangle L_q vacates; the prior record is read from global memory through L1), single chain
+  __host__ __device__ size_t floats(bool resident, bool onebuf = false) const {
+    return 64 + (resident ? (onebuf ? 1 : 2) * buf() : (size_t)STG_FLOATS) + (gemm(resident) ? (size_t)NBL * ld : 0) +
+           ((dual(resident) && !onebuf) ? 2 : 1) * (size_t)NB * ld + ld + 9 * (size_t)TP + 3 * (size_t)S * TP;
   }
 };
 
 struct Sm {
   double* red;
   float *B1, *B2, *stg, *wide, *pan, *pan2, *rdp, *rdq, *ts, *dgp, *dgq, *aa, *al, *pd, *gzs, *mm, *u, *v, *w;
-  __device__ Sm(float* base, const Lay& L, float* slot) {
+  __device__ Sm(float* base, const Lay& L, float* slot, bool onebuf = false) {
     red = reinterpret_cast<double*>(base); base += 64;
     stg = nullptr;
     wide = nullptr;
@@ -151,13 +155,16 @@ struct Sm {
       wide = base;  // 64-wide panel (Cholesky) / 64-row block (solve) of the GEMM path
       if (L.gemm(false)) base += (size_t)NBL * L.ld;
       stg = base; base += STG_FLOATS;  // immediately followed by pan: GEMM phases stage through stg + pan
+    } else if (onebuf) {
+      B1 = nullptr;
+      B2 = base; base += L.buf();
     } else {
       B1 = base; base += L.buf();
       B2 = base; base += L.buf();
     }
     pan = base; base += (size_t)NB * L.ld;
     pan2 = base;
-    if (L.dual(slot == nullptr)) base += (size_t)NB * L.ld;
+    if (L.dual(slot == nullptr) && !onebuf) base += (size_t)NB * L.ld;
     ts = base; base += L.ld;
     rdp = base; base += L.TP;
     rdq = base; base += L.TP;
@@ -667,12 +674,15 @@ __device__ __noinline__ float solve_gemm(const float* __restrict__ Lb, const flo
 // sum_{k != l, k,l < T} dK(k,l)/d ell * sum_{i} XU[i][k] XV[i][l]   (XR triangles of Ub / Vb); thread partial.
 // kinv != NULL (shared-prior path): the weight of dK(k,l) becomes hg * kinv[k*ld + l] + (U^T V)_kl, i.e. the prior-side
 // term g/2 <K_p^-1, dK_q/d ell> rides along in the same epilogue (kinv = this sequence's K_p^-1 record, row stride ld).
-template <int KERNEL>
+// VREV (one-buffer backward): V = C' is stored row- and column-reversed in the triangle of Vb that L_q vacated,
+// C'(i,l) at Vb[(TP-1-i)*ld + (TP-1-l)] (l <= i), so that a row of C' is still one aligned float4 per 4 columns; the
+// tile then holds its columns in reverse order (acc[r][c] <-> l = lb + 3 - c).
+template <int KERNEL, bool VREV = false>
 __device__ __noinline__ double contract_block(const float* __restrict__ Ub, const float* __restrict__ Vb, const Lay& L, int T,
                                  const float* __restrict__ ts, float ell, float sig, Grp g,
                                  const float* __restrict__ kinv = nullptr, float hg = 0.0f) {
   const int tid = g.tid, NT = g.nt;
-  const int ld = L.ld;
+  const int ld = L.ld, TP = L.TP;
   const int nk = (T + 3) / 4;
   const KernC<KERNEL> kc(ell, sig);
   double total = 0.0;
@@ -686,34 +696,47 @@ __device__ __noinline__ double contract_block(const float* __restrict__ Ub, cons
       for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
     int i = kb > lb ? kb : lb;
     const int ihead = (i + 3 < T) ? i + 3 : T;
+    // row i of V: VREV ? Vb + (TP-1-i)*ld + (TP-4-lb) (components l = lb+3 .. lb) : Vb + (i+1)*ld + lb
+    const float* __restrict__ v0 = VREV ? Vb + (size_t)(TP - 1) * ld + (TP - 4 - lb) : Vb + ld + lb;
     for (; i < ihead; ++i) {
       const float4 u4 = *reinterpret_cast<const float4*>(Ub + (size_t)(i + 1) * ld + kb);
-      const float4 v4 = *reinterpret_cast<const float4*>(Vb + (size_t)(i + 1) * ld + lb);
+      const float4 v4 = *reinterpret_cast<const float4*>(VREV ? v0 - (size_t)i * ld : v0 + (size_t)i * ld);
       const float u[4] = {kb <= i ? u4.x : 0.0f, kb + 1 <= i ? u4.y : 0.0f, kb + 2 <= i ? u4.z : 0.0f, kb + 3 <= i ? u4.w : 0.0f};
-      const float v[4] = {lb <= i ? v4.x : 0.0f, lb + 1 <= i ? v4.y : 0.0f, lb + 2 <= i ? v4.z : 0.0f, lb + 3 <= i ? v4.w : 0.0f};
+      float v[4];
+      if (VREV) {
+        v[0] = lb + 3 <= i ? v4.x : 0.0f; v[1] = lb + 2 <= i ? v4.y : 0.0f; v[2] = lb + 1 <= i ? v4.z : 0.0f; v[3] = lb <= i ? v4.w : 0.0f;
+      } else {
+        v[0] = lb <= i ? v4.x : 0.0f; v[1] = lb + 1 <= i ? v4.y : 0.0f; v[2] = lb + 2 <= i ? v4.z : 0.0f; v[3] = lb + 3 <= i ? v4.w : 0.0f;
+      }
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(u[r], v[c], acc[r][c]);
     }
-    tile_update<1>(acc, Ub + ld + kb, ld, Vb + ld + lb, ld, i, T);
+    tile_update<1, VREV>(acc, Ub + ld + kb, ld, v0, ld, i, T);
     if (kinv) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const float4 q = __ldg(reinterpret_cast<const float4*>(kinv + (size_t)(kb + r) * ld + lb));
-        acc[r][0] = fmaf(hg, q.x, acc[r][0]); acc[r][1] = fmaf(hg, q.y, acc[r][1]);
-        acc[r][2] = fmaf(hg, q.z, acc[r][2]); acc[r][3] = fmaf(hg, q.w, acc[r][3]);
+        if (VREV) {
+          acc[r][0] = fmaf(hg, q.w, acc[r][0]); acc[r][1] = fmaf(hg, q.z, acc[r][1]);
+          acc[r][2] = fmaf(hg, q.y, acc[r][2]); acc[r][3] = fmaf(hg, q.x, acc[r][3]);
+        } else {
+          acc[r][0] = fmaf(hg, q.x, acc[r][0]); acc[r][1] = fmaf(hg, q.y, acc[r][1]);
+          acc[r][2] = fmaf(hg, q.z, acc[r][2]); acc[r][3] = fmaf(hg, q.w, acc[r][3]);
+        }
       }
     }
     const float4 tk4 = *reinterpret_cast<const float4*>(ts + kb);
     const float4 tl4 = *reinterpret_cast<const float4*>(ts + lb);
-    const float tk[4] = {tk4.x, tk4.y, tk4.z, tk4.w}, tl[4] = {tl4.x, tl4.y, tl4.z, tl4.w};
+    const float tk[4] = {tk4.x, tk4.y, tk4.z, tk4.w};
+    const float tl[4] = {VREV ? tl4.w : tl4.x, VREV ? tl4.z : tl4.y, VREV ? tl4.y : tl4.z, VREV ? tl4.x : tl4.w};
     float part = 0.0f;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int k = kb + r, l = lb + c;
+        const int k = kb + r, l = lb + (VREV ? 3 - c : c);
         const float dt = tk[r] - tl[c];
         const float dk = kc.dell(dt, kc.val_fast(dt));
         part = fmaf((k < T && l < T && k != l) ? acc[r][c] : 0.0f, dk, part);  // branch-free
@@ -1089,18 +1112,23 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) prior_block(Params P, int u
   }
 }
 
-template <int KERNEL, int POST, bool DUAL, bool SLOT>
+// SH (resident sizes only): the shared-prior kernel proper.  It holds ONE work matrix in shared memory (two CTAs per
+// SM up to T = 144) and reads the prior record from global memory; it returns at once when the device flag says the
+// prior is not shared, and the ordinary kernel launched behind it (P.skip_if_shared) returns at once when it is.
+template <int KERNEL, int POST, bool DUAL, bool SLOT, bool SH = false>
 __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use_slot) {
   extern __shared__ __align__(16) float smem_f[];
   __shared__ int bad;
   const GpklDesc& d = P.d;
+  if (SH && *P.prior_flag == 0) return;
+  if (!SH && P.skip_if_shared && *P.prior_flag != 0) return;
   const Lay L(d.T_max, d.S);
-  Sm s(smem_f, L, use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr);
+  Sm s(smem_f, L, use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr, SH);
   const int S = d.S, TP = L.TP, ld = L.ld;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
   const Groups G(DUAL);
   // shared-prior fast path: the pre-pass found one ell_p for all latent dims and left per-sequence records
-  const bool shared = (POST == GPKL_POST_GP) && !DUAL && P.prior != nullptr && *P.prior_flag != 0;
+  const bool shared = SH || ((POST == GPKL_POST_GP) && !DUAL && SLOT && P.prior != nullptr && *P.prior_flag != 0);
   for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
     const int T = P.lengths[b];
@@ -1166,15 +1194,21 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
         }
         ssq = product_ssq_gemm(rec, s.B2, L, T, s.stg);
       } else {
-        for (int q = threadIdx.x; q < TP * ld / 4; q += blockDim.x)
-          reinterpret_cast<float4*>(s.B1)[q] = __ldg(reinterpret_cast<const float4*>(rec) + q);
-        __syncthreads();
+        // the record (this sequence's L_p^-1, shared by its D pairs) is read in place: L1/L2 resident, no staging copy
         for (int i = threadIdx.x; i < T; i += blockDim.x) {
-          float a0 = 0.0f;
-          for (int k = 0; k <= i; ++k) a0 = fmaf(s.B1[(size_t)k * ld + i], s.mm[k], a0);
-          s.aa[i] = a0;
+          float a0 = 0.0f, a1 = 0.0f;
+          int k = 0;
+          for (; k + 8 <= i + 1; k += 8) {
+            float xv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xv[e] = __ldg(rec + (size_t)(k + e) * ld + i);
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) { a0 = fmaf(xv[e], s.mm[k + e], a0); a1 = fmaf(xv[e + 1], s.mm[k + e + 1], a1); }
+          }
+          for (; k <= i; ++k) a0 = fmaf(__ldg(rec + (size_t)k * ld + i), s.mm[k], a0);
+          s.aa[i] = a0 + a1;
         }
-        ssq = product_ssq_block(s.B1, ld, s.B2, L, T, G.all);
+        ssq = product_ssq_block(rec, ld, s.B2, L, T, G.all);
       }
       __syncthreads();
       phase_mark(P, 5);
@@ -1248,19 +1282,21 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
   }
 }
 
-template <int KERNEL, int POST, bool DUAL, bool SLOT>
+template <int KERNEL, int POST, bool DUAL, bool SLOT, bool SH = false>
 __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use_slot) {
   extern __shared__ __align__(16) float smem_f[];
   __shared__ int bad;
   const GpklDesc& d = P.d;
+  if (SH && *P.prior_flag == 0) return;
+  if (!SH && P.skip_if_shared && *P.prior_flag != 0) return;
   const Lay L(d.T_max, d.S);
-  Sm s(smem_f, L, use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr);
+  Sm s(smem_f, L, use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr, SH);
   const int S = d.S, TP = L.TP, ld = L.ld;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
   const double g_sum = P.g_kl_sum ? *P.g_kl_sum : 1.0;
   const Groups G(DUAL);
   // shared-prior fast path: the pre-pass found one ell_p for all latent dims and left per-sequence records
-  const bool shared = (POST == GPKL_POST_GP) && !DUAL && P.prior != nullptr && *P.prior_flag != 0;
+  const bool shared = SH || ((POST == GPKL_POST_GP) && !DUAL && SLOT && P.prior != nullptr && *P.prior_flag != 0);
   for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
     const int T = P.lengths[b];
@@ -1366,7 +1402,10 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
       // issued 8 rows ahead of the dependent prefix arithmetic (the matrices may live in global memory).
       for (int l = threadIdx.x; l < T; l += blockDim.x) {
         const float* __restrict__ xq = s.B2 + ld + l;  // X_q(i, l) at xq[i*ld]
-        float* __restrict__ cp = s.B1 + ld + l;        // C'(i, l) at cp[i*ld]
+        // C'(i, l) at cp[i*cs]: the XR triangle of B1, or (SH, one buffer) row/column-reversed in the triangle of B2
+        // that L_q vacated once w and X_q were formed
+        float* __restrict__ cp = SH ? s.B2 + (size_t)(TP - 1) * ld + (TP - 1 - l) : s.B1 + ld + l;
+        const ptrdiff_t cs = SH ? -(ptrdiff_t)ld : (ptrdiff_t)ld;
         for (int sx0 = 0; sx0 < S; sx0 += 4) {
           const int ns = (S - sx0 < 4) ? S - sx0 : 4;
           float cum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -1376,7 +1415,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
             for (int e = 0; e < 8; ++e) {
               const int i = i0 + e;
               xv[e] = (i < T) ? xq[(size_t)i * ld] : 0.0f;
-              base[e] = (sx0 == 0) ? 0.0f : ((i < T) ? cp[(size_t)i * ld] : 0.0f);
+              base[e] = (sx0 == 0) ? 0.0f : ((i < T) ? cp[(ptrdiff_t)i * cs] : 0.0f);
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -1390,7 +1429,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
                     cum[q] = fmaf(s.v[(size_t)(sx0 + q) * TP + i], xv[e], cum[q]);
                   }
                 }
-                cp[(size_t)i * ld] = cv;
+                cp[(ptrdiff_t)i * cs] = cv;
               }
             }
           }
@@ -1421,7 +1460,8 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
       const float hg = 0.5f * g;
       const double t2 = gm ? contract_gemm<KERNEL, false>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg, kinv, hg)
                         : SLOT ? contract_block_staged<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg, kinv, hg)
-                                 : contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, G.all, kinv, hg);
+                        : SH ? contract_block<KERNEL, true>(s.B2, s.B2, L, T, s.ts, lq, sig, G.all, kinv, hg)
+                             : contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, G.all, kinv, hg);
       phase_mark(P, 26);
       const double gq = block_sum(0.5 * (double)g * t1 + t2, s.red);
       phase_mark(P, 27);
@@ -1455,12 +1495,14 @@ cudaError_t launch_kp(const Params& P_in, bool backward, cudaStream_t st) {
   } else {
     grid = npairs < kBlockSlots ? npairs : kBlockSlots;  // one workspace slot per CTA
   }
-  // Shared-prior path (records in the workspace): served for the resident and GEMM-path sizes.  Its kernels run the
-  // single K_q chain on all threads, so the non-DUAL instantiation is launched; if the device then finds ell_p
-  // non-uniform that instantiation runs the per-pair prior chain too (just without the two-chain overlap).
+  // Shared-prior path (records in the workspace): served for the resident and GEMM-path sizes.
+  //  * GEMM path: one kernel decides on the device (flag) between the shared and the per-pair prior.
+  //  * resident sizes: the shared-prior kernel proper (SH: one work matrix in shared memory, two CTAs per SM up to
+  //    T = 144) is launched behind the pre-pass and returns at once if the device flag says "not shared"; the ordinary
+  //    per-pair kernel is launched behind it and returns at once if the flag says "shared" (no host read of ell_p).
   const bool share = POST == GPKL_POST_GP && P_in.prior != nullptr && (resident || L.gemm(false));
   if (!share) { P.prior = nullptr; P.prior_flag = nullptr; }
-  const bool dual = POST == GPKL_POST_GP && L.dual(resident) && !share;
+  const bool dual = POST == GPKL_POST_GP && L.dual(resident);
   void (*kern)(Params, int);
   if (!resident) kern = backward ? bwd_block<KERNEL, POST, false, true> : fwd_block<KERNEL, POST, false, true>;
   else if (!backward) kern = dual ? fwd_block<KERNEL, POST, true, false> : fwd_block<KERNEL, POST, false, false>;
@@ -1470,7 +1512,15 @@ cudaError_t launch_kp(const Params& P_in, bool backward, cudaStream_t st) {
   // (the profiling events bracket pre-pass + per-pair kernel: an event between them would break the programmatic
   //  dependency and serialise them)
   prof_begin(backward, st);
-  bool pdl = false;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(nt);
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 0;
   if (share) {
     void (*pk)(Params, int);
     if (!resident) pk = backward ? prior_block<KERNEL, true, true> : prior_block<KERNEL, true, false>;
@@ -1480,20 +1530,33 @@ cudaError_t launch_kp(const Params& P_in, bool backward, cudaStream_t st) {
     const int pgrid = resident ? P.d.B : (P.d.B < kBlockSlots ? P.d.B : kBlockSlots);
     pk<<<pgrid, 256, smem, st>>>(P, resident ? 0 : 1);
     note_launch();
-    // the pre-pass of the slot path works in the same workspace slots as the per-pair kernel: no overlap there
-    pdl = resident && pdl_enabled();
+    if (resident) {
+      if (POST == GPKL_POST_GP) {  // (the SH instantiations exist for the GP posterior only)
+        void (*sk)(Params, int) = backward ? bwd_block<KERNEL, GPKL_POST_GP, false, false, true>
+                                           : fwd_block<KERNEL, GPKL_POST_GP, false, false, true>;
+        const size_t smem1 = L.floats(true, true) * sizeof(float);
+        e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e != cudaSuccess) return e;
+        int per_sm = (int)(kMaxDynSmem / (smem1 + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 2048 / nt) per_sm = 2048 / nt;
+        const int cap = kNumSMs * per_sm * 4;
+        cfg.gridDim = dim3(npairs < cap ? npairs : cap);
+        cfg.dynamicSmemBytes = smem1;
+        // the pre-pass overlaps the K_q chain of the per-pair kernel (programmatic dependent launch)
+        cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        e = cudaLaunchKernelEx(&cfg, sk, P, 0);
+        note_launch();
+        if (e != cudaSuccess) return e;
+      }
+      // per-pair fallback behind it: no records, returns at once when the flag says "shared"
+      P.prior = nullptr;
+      P.skip_if_shared = 1;
+    }
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(nt);
   cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr.val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = 0;
   e = cudaLaunchKernelEx(&cfg, kern, P, resident ? 0 : 1);
   prof_end(backward, st);
   note_launch();
