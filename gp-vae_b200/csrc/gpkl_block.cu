@@ -106,6 +106,14 @@ __device__ __forceinline__ void grp_sync(const Grp& g) {
   }
 }
 
+// Work items sorted by decreasing cost are dealt to the warps of a group in chunks of 32, boustrophedon (round r goes
+// w = 0..nw-1, round r+1 back): every warp gets the same total and the lanes of a warp the same trip count.  Phases
+// end at a barrier, so the slowest warp is the phase time.  Returns the item index of this thread in round r.
+__device__ __forceinline__ int dealt_index(int r, const Grp& g) {
+  const int w = g.tid >> 5, nw = g.nt >> 5;
+  return (r * nw + ((r & 1) ? nw - 1 - w : w)) * 32 + (g.tid & 31);
+}
+
 // Workspace variant (T > ~144): operand slabs are staged global -> shared with cp.async, double buffered.
 // staging floats: >= 2*32*128 for the 64x64 staged contraction, and stg + pan (16*(TP+4) floats, TP >= 160 on the
 // GEMM path) must hold the GM_NS stages of the GEMM tile: 9728 + 16*164 = 12352 >= 4*16*192 = 12288
@@ -681,13 +689,20 @@ template <int KERNEL, bool VREV = false>
 __device__ __noinline__ double contract_block(const float* __restrict__ Ub, const float* __restrict__ Vb, const Lay& L, int T,
                                  const float* __restrict__ ts, float ell, float sig, Grp g,
                                  const float* __restrict__ kinv = nullptr, float hg = 0.0f) {
-  const int tid = g.tid, NT = g.nt;
+  const int NT = g.nt;
   const int ld = L.ld, TP = L.TP;
   const int nk = (T + 3) / 4;
   const KernC<KERNEL> kc(ell, sig);
   double total = 0.0;
-  for (int id = tid; id < nk * nk; id += NT) {
-    const int kt = id % nk, lt = id / nk;
+  // tiles enumerated by shell m = max(kt, lt) (2m+1 tiles, all with the contraction range [4m, T)), longest first
+  for (int rr = 0; rr * NT < nk * nk; ++rr) {
+    const int n = dealt_index(rr, g);
+    if (n >= nk * nk) continue;
+    int m = (int)sqrtf((float)n);
+    while ((m + 1) * (m + 1) <= n) ++m;
+    while (m * m > n) --m;
+    const int pos = n - m * m;
+    const int kt = pos <= m ? m : pos - m - 1, lt = pos <= m ? pos : m;
     const int kb = 4 * kt, lb = 4 * lt;
     float acc[4][4];
 #pragma unroll
@@ -897,10 +912,16 @@ __device__ __noinline__ float product_ssq_block(const float* __restrict__ Xc, in
                                                 const Lay& L, int T, Grp g) {
   const int ld = L.ld;
   const int nt = (T + 3) / 4;
+  const int ntri = nt * (nt + 1) / 2;
   float ssq = 0.0f;
-  for (int id = g.tid; id < nt * nt; id += g.nt) {
-    const int it = id % nt, ct = id / nt;
-    if (ct > it) continue;
+  // lower tiles (it >= ct) enumerated by diagonal, longest contraction first: diagonal it - ct = nt-1-q holds q+1 tiles
+  for (int rr = 0; rr * g.nt < ntri; ++rr) {
+    const int n = dealt_index(rr, g);
+    if (n >= ntri) continue;
+    int q = (int)((sqrtf(8.0f * (float)n + 1.0f) - 1.0f) * 0.5f);
+    while ((q + 1) * (q + 2) / 2 <= n) ++q;
+    while (q * (q + 1) / 2 > n) --q;
+    const int ct = n - q * (q + 1) / 2, it = ct + nt - 1 - q;
     const int rb = 4 * it, cb = 4 * ct;
     float acc[4][4];
 #pragma unroll
@@ -1157,6 +1178,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
       // ---- shared-prior path: only K_q is factored here (all threads); L_p^-1 and diag L_p come from the record
       if (gm) chol_gemm<KERNEL, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
       else chol_block<KERNEL, false, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.dgq, s.rdq, &bad, G.all);
+      phase_mark(P, 3);
       for (int i = threadIdx.x; i < T; i += blockDim.x) {  // z_s = m + L_q eps_s (loads batched 8 ahead: L_q may be global)
         for (int sx = 0; sx < S; ++sx) {
           const float* ev = s.v + (size_t)sx * TP;
@@ -1177,6 +1199,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
       griddep_wait();  // the record is first needed here: the pre-pass overlaps the K_q factorisation
       const float* __restrict__ rec = P.prior + (size_t)b * P.prior_stride;
       for (int i = threadIdx.x; i < TP; i += blockDim.x) s.dgp[i] = __ldg(rec + rec_dg_offset(L) + i);
+      phase_mark(P, 7);
       float ssq;
       if (gm) {
         for (int i = threadIdx.x; i < T; i += blockDim.x) {  // a = L_p^-1 m from the record (coalesced over i)
@@ -1208,6 +1231,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
           for (; k <= i; ++k) a0 = fmaf(__ldg(rec + (size_t)k * ld + i), s.mm[k], a0);
           s.aa[i] = a0 + a1;
         }
+        phase_mark(P, 8);
         ssq = product_ssq_block(rec, ld, s.B2, L, T, G.all);
       }
       __syncthreads();
