@@ -143,10 +143,11 @@ struct Lay {  // shared-memory carve-up (floats), identical on host and device
   // gemm: workspace path whose 64-wide panels live in shared memory and are updated by the staged GEMM tile
   __host__ __device__ bool gemm(bool resident) const { return !resident && TP > GEMM_TMIN && TP <= GEMM_TMAX; }
   // onebuf: the resident shared-prior kernels need ONE work matrix (B2: L_q / X_q, and in backward the row-reversed
-  // C' in the triangle L_q vacates; the prior record is read from global memory through L1), single chain
+  // C' in the triangle L_q vacates; the prior record is read from global memory through L1), single chain; their
+  // second staging panel is the look-ahead panel of the factorisation
   __host__ __device__ size_t floats(bool resident, bool onebuf = false) const {
     return 64 + (resident ? (onebuf ? 1 : 2) * buf() : (size_t)STG_FLOATS) + (gemm(resident) ? (size_t)NBL * ld : 0) +
-           ((dual(resident) && !onebuf) ? 2 : 1) * (size_t)NB * ld + ld + 9 * (size_t)TP + 3 * (size_t)S * TP;
+           ((dual(resident) || onebuf) ? 2 : 1) * (size_t)NB * ld + ld + 9 * (size_t)TP + 3 * (size_t)S * TP;
   }
 };
 
@@ -172,7 +173,7 @@ struct Sm {
     }
     pan = base; base += (size_t)NB * L.ld;
     pan2 = base;
-    if (L.dual(slot == nullptr) && !onebuf) base += (size_t)NB * L.ld;
+    if (L.dual(slot == nullptr) || onebuf) base += (size_t)NB * L.ld;
     ts = base; base += L.ld;
     rdp = base; base += L.TP;
     rdq = base; base += L.TP;
@@ -257,72 +258,108 @@ __device__ __forceinline__ void diag_solve16(float (&b)[16], const float* __rest
 // GEMM phase of the large-T path left them there) instead of being generated.
 // XRC (resident buffers only): the factor is ALSO written row-major into the XR triangle of the same buffer
 // (element (i,k) at Bm[(i+1)*ldm + k]) -- the k-major operand of the shared-prior product A = L_p^-1 L_q.
+// Tile phase of one 16-column panel at j0: every (4-row x 4-column) tile of rows >= j0 is initialised (INIT 0: kernel
+// entries generated on the fly / the extra m^T row / identity padding; INIT 1: read from the view Bm; INIT 2: read from the
+// staging panel `src`, a partial result of this same phase), updated with  acc -= sum_{k in [ka,kb)} L[rows,k] L[cols,k]
+// and parked in the staging panel `dst` (column-major, stride ld).  (tid, NT): the threads that share the phase.
+template <int KERNEL, int INIT>
+__device__ __forceinline__ void panel_tiles(const float* __restrict__ Bm, int ldm, int j0, int ka, int kb, const Lay& L, int T,
+                                            bool extra, const float* __restrict__ ts, const float* __restrict__ mm,
+                                            const KernC<KERNEL>& kc, float noise, const float* __restrict__ src,
+                                            float* __restrict__ dst, int tid, int NT) {
+  const int cg = tid & 3, rg = tid >> 2, NRG = NT >> 2;
+  const int ld = L.ld, TP = L.TP;
+  const int Tact = (T + NB - 1) / NB * NB;
+  const int rows_end = extra ? TP + 4 : Tact;
+  const int cb = j0 + 4 * cg;
+  for (int rb = j0 + 4 * rg; rb < rows_end; rb += 4 * NRG) {
+    if (rb >= Tact && rb < TP) continue;  // identity padding rows
+    float acc[4][4];
+    if (INIT == 2) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 a4 = *reinterpret_cast<const float4*>(src + (size_t)(4 * cg + c) * ld + rb);
+        acc[0][c] = a4.x; acc[1][c] = a4.y; acc[2][c] = a4.z; acc[3][c] = a4.w;
+      }
+    } else if (INIT == 1) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 a4 = *reinterpret_cast<const float4*>(Bm + (size_t)(cb + c) * ldm + rb);
+        acc[0][c] = a4.x; acc[1][c] = a4.y; acc[2][c] = a4.z; acc[3][c] = a4.w;
+      }
+    } else if (rb + 3 < T && cb + 3 < T) {  // all-real tile: no padding logic
+      const float4 tr4 = *reinterpret_cast<const float4*>(ts + rb);
+      const float4 tc4 = *reinterpret_cast<const float4*>(ts + cb);
+      const float tr[4] = {tr4.x, tr4.y, tr4.z, tr4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = kc.val(tr[r] - tc[c]);
+      if (rb == cb) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r][r] += noise;
+      }
+    } else if (rb == TP) {  // the extra row block: row TP carries m^T, rows TP+1..TP+3 are zero
+      const float4 m4 = *reinterpret_cast<const float4*>(mm + cb);
+      const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc[0][c] = (cb + c < T) ? mv[c] : 0.0f;
+        acc[1][c] = acc[2][c] = acc[3][c] = 0.0f;
+      }
+    } else {  // tile touching the identity padding: branch-free selects (divergent branches cost ~20 cycles each)
+      const float4 tr4 = *reinterpret_cast<const float4*>(ts + rb);
+      const float4 tc4 = *reinterpret_cast<const float4*>(ts + cb);
+      const float tr[4] = {tr4.x, tr4.y, tr4.z, tr4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = rb + r, k = cb + c;
+          const float v = kc.val(tr[r] - tc[c]) + (i == k ? noise : 0.0f);
+          acc[r][c] = (i < T && k < T) ? v : (i == k ? 1.0f : 0.0f);
+        }
+    }
+    tile_update<-1>(acc, Bm + rb, ldm, Bm + cb, ldm, ka, kb);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<float4*>(dst + (size_t)(4 * cg + c) * ld + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+  }
+}
+
+// Left-looking panel Cholesky with fused kernel-matrix generation.  Result: LC triangle of Bm, diag(L) in dg, 1/diag(L)
+// in rdg.  extra: also carry row TP = m^T (gives L^-1 m).
+// Bm is a VIEW: element (i,k) at Bm[k*ldm + i].  Columns [c_begin, c_end) are factored; contributions of columns
+// < kstart are assumed applied already, and with FROM_VIEW the starting values are read from the view (the
+// GEMM phase of the large-T path left them there) instead of being generated.
+// XRC (resident buffers only): the factor is ALSO written row-major into the XR triangle of the same buffer
+// (element (i,k) at Bm[(i+1)*ldm + k]) -- the k-major operand of the shared-prior product A = L_p^-1 L_q.
+// pan2 != NULL: LOOK-AHEAD.  The serial 16x16 diagonal factor (one warp, ~3 K cycles) used to idle the other warps at a
+// barrier; now, while warp 0 factors the diagonal block of panel j, the other warps already apply the finished columns
+// [kstart, j0) to panel j+1 (into pan2), and only the 16 columns of panel j itself are applied after its rows are solved.
 template <int KERNEL, bool DUAL, bool FROM_VIEW, bool XRC = false>
 __device__ __noinline__ void chol_panels(float* __restrict__ Bm, int ldm, int c_begin, int c_end, int kstart, const Lay& L,
                                          int T, bool extra, const float* __restrict__ ts, const float* __restrict__ mm,
                                          float ell, float sig, float noise, float* __restrict__ pan,
-                                         float* __restrict__ dg, float* __restrict__ rdg, int* bad, Grp g) {
+                                         float* __restrict__ dg, float* __restrict__ rdg, int* bad, Grp g,
+                                         float* __restrict__ pan2 = nullptr) {
   const int tid = g.tid, NT = g.nt;
-  const int cg = tid & 3, rg = tid >> 2, NRG = NT >> 2;
   const int ld = L.ld, TP = L.TP;  // ld: stride of the staging panel `pan`
   const KernC<KERNEL> kc(ell, sig);
   // rows beyond the last real row are identity padding and decouple: only panels that contain real rows matter
   const int Tact = (T + NB - 1) / NB * NB;
-  const int rows_end = extra ? TP + 4 : Tact;
+  const bool ahead = pan2 != nullptr && NT > 32;
   PT_DECL;
+  if (ahead) panel_tiles<KERNEL, FROM_VIEW ? 1 : 0>(Bm, ldm, c_begin, kstart, c_begin, L, T, extra, ts, mm, kc, noise, nullptr, pan, tid, NT);
   for (int j0 = c_begin; j0 < c_end; j0 += NB) {
-    const int cb = j0 + 4 * cg;
-    for (int rb = j0 + 4 * rg; rb < rows_end; rb += 4 * NRG) {
-      if (rb >= Tact && rb < TP) continue;  // identity padding rows
-      float acc[4][4];
-      if (FROM_VIEW) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 a4 = *reinterpret_cast<const float4*>(Bm + (size_t)(cb + c) * ldm + rb);
-          acc[0][c] = a4.x; acc[1][c] = a4.y; acc[2][c] = a4.z; acc[3][c] = a4.w;
-        }
-      } else if (rb + 3 < T && cb + 3 < T) {  // all-real tile: no padding logic
-        const float4 tr4 = *reinterpret_cast<const float4*>(ts + rb);
-        const float4 tc4 = *reinterpret_cast<const float4*>(ts + cb);
-        const float tr[4] = {tr4.x, tr4.y, tr4.z, tr4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = kc.val(tr[r] - tc[c]);
-        if (rb == cb) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) acc[r][r] += noise;
-        }
-      } else if (rb == TP) {  // the extra row block: row TP carries m^T, rows TP+1..TP+3 are zero
-        const float4 m4 = *reinterpret_cast<const float4*>(mm + cb);
-        const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          acc[0][c] = (cb + c < T) ? mv[c] : 0.0f;
-          acc[1][c] = acc[2][c] = acc[3][c] = 0.0f;
-        }
-      } else {  // tile touching the identity padding: branch-free selects (divergent branches cost ~20 cycles each)
-        const float4 tr4 = *reinterpret_cast<const float4*>(ts + rb);
-        const float4 tc4 = *reinterpret_cast<const float4*>(ts + cb);
-        const float tr[4] = {tr4.x, tr4.y, tr4.z, tr4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int i = rb + r, k = cb + c;
-            const float v = kc.val(tr[r] - tc[c]) + (i == k ? noise : 0.0f);
-            acc[r][c] = (i < T && k < T) ? v : (i == k ? 1.0f : 0.0f);
-          }
-      }
-      tile_update<-1>(acc, Bm + rb, ldm, Bm + cb, ldm, kstart, j0);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<float4*>(pan + (size_t)(4 * cg + c) * ld + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
-    }
+    const bool more = j0 + NB < c_end;
+    if (!ahead) panel_tiles<KERNEL, FROM_VIEW ? 1 : 0>(Bm, ldm, j0, kstart, j0, L, T, extra, ts, mm, kc, noise, nullptr, pan, tid, NT);
     PT_ADD(0);
     grp_sync<DUAL>(g);
     PT_ADD(1);
     if (tid < 32) diag_factor<XRC>(Bm, ldm, j0, T, pan, ld, dg, rdg, bad);
+    else if (ahead && more)
+      panel_tiles<KERNEL, FROM_VIEW ? 1 : 0>(Bm, ldm, j0 + NB, kstart, j0, L, T, extra, ts, mm, kc, noise, nullptr, pan2, tid - 32, NT - 32);
     PT_ADD(2);
     grp_sync<DUAL>(g);
     PT_ADD(1);
@@ -346,6 +383,8 @@ __device__ __noinline__ void chol_panels(float* __restrict__ Bm, int ldm, int c_
     PT_ADD(3);
     grp_sync<DUAL>(g);
     PT_ADD(1);
+    if (ahead && more)  // the 16 columns just finished, applied to the partial panel j+1
+      panel_tiles<KERNEL, 2>(Bm, ldm, j0 + NB, j0, j0 + NB, L, T, extra, ts, mm, kc, noise, pan2, pan, tid, NT);
   }
   PT_FLUSH;
   // identity padding: diag entries for rows in [Tact, TP) (only dg / rdg are consulted for them)
@@ -360,9 +399,9 @@ template <int KERNEL, bool DUAL, bool XRC = false>
 __device__ __forceinline__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool extra, const float* __restrict__ ts,
                                            const float* __restrict__ mm, float ell, float sig, float noise,
                                            float* __restrict__ pan, float* __restrict__ dg, float* __restrict__ rdg, int* bad,
-                                           Grp g) {
+                                           Grp g, float* __restrict__ pan2 = nullptr) {
   const int Tact = (T + NB - 1) / NB * NB;
-  chol_panels<KERNEL, DUAL, false, XRC>(Bm, L.ld, 0, Tact, 0, L, T, extra, ts, mm, ell, sig, noise, pan, dg, rdg, bad, g);
+  chol_panels<KERNEL, DUAL, false, XRC>(Bm, L.ld, 0, Tact, 0, L, T, extra, ts, mm, ell, sig, noise, pan, dg, rdg, bad, g, pan2);
 }
 
 // X = L^-1 B by 16-row blocks into the XR triangle of Xb.  L: LC triangle of Lb with inverse diagonal
@@ -1061,7 +1100,8 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) prior_block(Params P, int u
         chol_gemm<KERNEL>(s.B1, L, T, false, s.ts, s.mm, lp, sig, noise, s.pan, s.wide, s.stg, s.dgp, s.rdp, &bad);
         (void)solve_gemm<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, s.wide, s.stg);
       } else {
-        chol_block<KERNEL, false>(s.B1, L, T, false, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, all);
+        chol_block<KERNEL, false>(s.B1, L, T, false, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, all,
+                                  (!use_slot && L.dual(true)) ? s.pan2 : nullptr);
         (void)solve_block<true, false>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, all);
       }
       __syncthreads();
@@ -1177,7 +1217,8 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
     if (POST == GPKL_POST_GP && shared) {
       // ---- shared-prior path: only K_q is factored here (all threads); L_p^-1 and diag L_p come from the record
       if (gm) chol_gemm<KERNEL, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
-      else chol_block<KERNEL, false, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.dgq, s.rdq, &bad, G.all);
+      else chol_block<KERNEL, false, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.dgq, s.rdq, &bad, G.all,
+                                           SH ? s.pan2 : nullptr);
       phase_mark(P, 3);
       for (int i = threadIdx.x; i < T; i += blockDim.x) {  // z_s = m + L_q eps_s (loads batched 8 ahead: L_q may be global)
         for (int sx = 0; sx < S; ++sx) {
@@ -1385,7 +1426,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
         if (gm) chol_gemm<KERNEL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
         else
           chol_block<KERNEL, DUAL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, G.dual ? s.pan2 : s.pan, s.dgq, s.rdq,
-                                   &bad, G.chain);
+                                   &bad, G.chain, SH ? s.pan2 : nullptr);
         phase_mark(P, 22);
         if (SLOT) {
           // L_q lives in global memory: one WARP per column k, lanes stride down the column (coalesced), shuffle-reduce
