@@ -24,6 +24,8 @@
 // :242-260 (+ TF autodiff :361); V2 src/Models/VAE_GPprior_diag_cov.py:64-71, :100-119.
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "gpkl_common.cuh"
 #include "gpkl_launch.h"
 
@@ -1463,6 +1465,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
         phase_mark(P, 24);
       }
       __syncthreads();  // join: X_p (dead after t1), X_q, w, pd are complete
+      phase_mark(P, 28);
       // C' = (Phi(sum_s w_s eps_s^T) - g/2 I) X_q by running prefix sums down each column, into XR1.  Loads are
       // issued 8 rows ahead of the dependent prefix arithmetic (the matrices may live in global memory).
       for (int l = threadIdx.x; l < T; l += blockDim.x) {
@@ -1471,6 +1474,32 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
         // that L_q vacated once w and X_q were formed
         float* __restrict__ cp = SH ? s.B2 + (size_t)(TP - 1) * ld + (TP - 1 - l) : s.B1 + ld + l;
         const ptrdiff_t cs = SH ? -(ptrdiff_t)ld : (ptrdiff_t)ld;
+        if (S == 1) {
+          // one sample (the reference's default, :318): every operand of the 8-row batch is loaded before the dependent
+          // prefix chain (the per-row loads of pd / w / eps inside the chain cost a shared-memory round trip per row)
+          float cum = 0.0f;
+          for (int i0 = l; i0 < T; i0 += 8) {
+            float xv[8], pv[8], wv[8], ev[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int i = i0 + e;
+              const bool ok = i < T;
+              const int ii = ok ? i : l;
+              xv[e] = ok ? xq[(size_t)i * ld] : 0.0f;
+              pv[e] = s.pd[ii];
+              wv[e] = s.w[ii];
+              ev[e] = s.v[ii];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int i = i0 + e;
+              const float cv = fmaf(wv[e], cum, pv[e] * xv[e]);
+              cum = fmaf(ev[e], xv[e], cum);
+              if (i < T) cp[(ptrdiff_t)i * cs] = cv;
+            }
+          }
+          continue;
+        }
         for (int sx0 = 0; sx0 < S; sx0 += 4) {
           const int ns = (S - sx0 < 4) ? S - sx0 : 4;
           float cum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -1500,6 +1529,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
           }
         }
       }
+      phase_mark(P, 29);
       __syncthreads();
       phase_mark(P, 25);
       // shared-prior path: alpha = K_p^-1 m from the record (K_p^-1 symmetric: coalesced over k), and the prior term
@@ -1602,11 +1632,19 @@ cudaError_t launch_kp(const Params& P_in, bool backward, cudaStream_t st) {
         const size_t smem1 = L.floats(true, true) * sizeof(float);
         e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) return e;
+        static const int env_nt = [] { const char* e = getenv("GPKL_SH_NT"); return e ? atoi(e) : 0; }();
+        // CTA size of the one-buffer kernels: what counts is pairs in flight per SM (latency-bound phases), so fewer
+        // threads per pair where shared memory admits a third CTA (measured, T=96: forward 3.22 -> 2.50 ms with 128
+        // threads; T=128: 192 threads best for both directions); GPKL_SH_NT overrides (experiments)
+        const int def_nt = nt != 256 ? nt : ((!backward && L.TP <= 112) ? 128 : 192);
+        const int snt = (env_nt >= 64 && env_nt <= 256 && env_nt % 32 == 0 && nt == 256) ? env_nt : def_nt;
         int per_sm = (int)(kMaxDynSmem / (smem1 + 1024));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm > 2048 / nt) per_sm = 2048 / nt;
+        if (per_sm > 2048 / snt) per_sm = 2048 / snt;
+        if (per_sm > 65536 / (snt * 128)) per_sm = 65536 / (snt * 128);
         const int cap = kNumSMs * per_sm * 4;
         cfg.gridDim = dim3(npairs < cap ? npairs : cap);
+        cfg.blockDim = dim3(snt);
         cfg.dynamicSmemBytes = smem1;
         // the pre-pass overlaps the K_q chain of the per-pair kernel (programmatic dependent launch)
         cfg.numAttrs = pdl_enabled() ? 1 : 0;
@@ -1620,6 +1658,7 @@ cudaError_t launch_kp(const Params& P_in, bool backward, cudaStream_t st) {
     }
   }
   cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(nt);
   cfg.dynamicSmemBytes = smem;
   cfg.numAttrs = 0;
   e = cudaLaunchKernelEx(&cfg, kern, P, resident ? 0 : 1);

@@ -24,6 +24,8 @@ for T in [int(a) for a in sys.argv[1:]] or [48, 128]:
             T, t[1] - t[0], t[3] - t[1], t[4] - t[3], t[7] - t[4], t[8] - t[7], t[5] - t[8], t[6] - t[5]))
     print('T=%d bwd cycles: load %d chol_p %d inv_p %d alpha %d t1 %d chol_q %d w %d inv_q %d Cprime %d t2 %d red %d | total %d'
           % tuple([T] + b + [t[27] - t[16]]))
+    if t[28] and t[29]:
+        print('T=%d bwd C-prime phase: join barrier %d, thread 0 loop %d, end barrier %d' % (T, t[28] - t[24], t[29] - t[28], t[25] - t[29]))
     if any(t[32:48]):
         names = ['chol.tiles', 'chol.sync', 'chol.diag', 'chol.rows', 'solve.tiles', 'solve.sync', 'solve.diag', 'diag.loop']
         print('   panel loops (GPKL_PANEL_TRACE build): fwd ' + ' '.join('%s %d' % (n, v) for n, v in zip(names, t[32:40])))
