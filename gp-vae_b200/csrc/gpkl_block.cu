@@ -1081,7 +1081,11 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) prior_block(Params P, int u
   if (*P.prior_flag == 0) return;  // ell_p differs between latent dims (offsets_kernel checked): per-pair path
   const GpklDesc& d = P.d;
   const Lay L(d.T_max, d.S);
-  Sm s(smem_f, L, use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr);
+  // use_slot: 0 = resident two-buffer carve-up, 1 = workspace slot, 2 = resident ONE-buffer carve-up (sizes whose two-buffer
+  // layout does not fit shared memory but whose one-buffer shared-prior kernels do: 145 <= T <= 208)
+  const bool onebuf = use_slot == 2;
+  Sm s(smem_f, L, use_slot == 1 ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr, onebuf);
+  float* const W = onebuf ? s.B2 : s.B1;  // the work matrix of the pre-pass
   const int TP = L.TP, ld = L.ld;
   const int tid = threadIdx.x, nt = blockDim.x;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
@@ -1099,12 +1103,12 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) prior_block(Params P, int u
     __syncthreads();
     if (T > 0) {
       if (gm) {
-        chol_gemm<KERNEL>(s.B1, L, T, false, s.ts, s.mm, lp, sig, noise, s.pan, s.wide, s.stg, s.dgp, s.rdp, &bad);
-        (void)solve_gemm<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, s.wide, s.stg);
+        chol_gemm<KERNEL>(W, L, T, false, s.ts, s.mm, lp, sig, noise, s.pan, s.wide, s.stg, s.dgp, s.rdp, &bad);
+        (void)solve_gemm<true>(W, s.rdp, nullptr, W, L, T, s.pan, s.wide, s.stg);
       } else {
-        chol_block<KERNEL, false>(s.B1, L, T, false, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, all,
-                                  (!use_slot && L.dual(true)) ? s.pan2 : nullptr);
-        (void)solve_block<true, false>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, all);
+        chol_block<KERNEL, false>(W, L, T, false, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, all,
+                                  (onebuf || (!use_slot && L.dual(true))) ? s.pan2 : nullptr);
+        (void)solve_block<true, false>(W, s.rdp, nullptr, W, L, T, s.pan, all);
       }
       __syncthreads();
     }
@@ -1112,7 +1116,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) prior_block(Params P, int u
       for (int idx = tid; idx < TP * ld; idx += nt) {
         const int k = idx / ld, i = idx - k * ld;
         float v;
-        if (i < Tact && k < Tact) v = (i >= k) ? s.B1[(size_t)(i + 1) * ld + k] : 0.0f;
+        if (i < Tact && k < Tact) v = (i >= k) ? W[(size_t)(i + 1) * ld + k] : 0.0f;
         else v = (i == k) ? 1.0f : 0.0f;
         rec[idx] = v;
       }
@@ -1134,7 +1138,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) prior_block(Params P, int u
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
           const int i0 = (kb0 > lb0 ? kb0 : lb0) / GM_KC * GM_KC;
-          gemm_tile_128x64<1, true, true>(acc, s.B1 + ld, ld, kb0, ld, s.B1 + ld, ld, lb0, ld, i0, Tact, s.stg);
+          gemm_tile_128x64<1, true, true>(acc, W + ld, ld, kb0, ld, W + ld, ld, lb0, ld, i0, Tact, s.stg);
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             const int k = kb0 + 8 * ty + r, l = lb0 + 4 * tx;
@@ -1155,8 +1159,8 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) prior_block(Params P, int u
           int i = kb > lb ? kb : lb;
           const int ihead = (i + 3 < Tact) ? i + 3 : Tact;
           for (; i < ihead; ++i) {
-            const float4 u4 = *reinterpret_cast<const float4*>(s.B1 + (size_t)(i + 1) * ld + kb);
-            const float4 v4 = *reinterpret_cast<const float4*>(s.B1 + (size_t)(i + 1) * ld + lb);
+            const float4 u4 = *reinterpret_cast<const float4*>(W + (size_t)(i + 1) * ld + kb);
+            const float4 v4 = *reinterpret_cast<const float4*>(W + (size_t)(i + 1) * ld + lb);
             const float u[4] = {kb <= i ? u4.x : 0.0f, kb + 1 <= i ? u4.y : 0.0f, kb + 2 <= i ? u4.z : 0.0f, kb + 3 <= i ? u4.w : 0.0f};
             const float v[4] = {lb <= i ? v4.x : 0.0f, lb + 1 <= i ? v4.y : 0.0f, lb + 2 <= i ? v4.z : 0.0f, lb + 3 <= i ? v4.w : 0.0f};
 #pragma unroll
@@ -1164,7 +1168,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) prior_block(Params P, int u
 #pragma unroll
               for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(u[r], v[c], acc[r][c]);
           }
-          tile_update<1>(acc, s.B1 + ld + kb, ld, s.B1 + ld + lb, ld, i, Tact);
+          tile_update<1>(acc, W + ld + kb, ld, W + ld + lb, ld, i, Tact);
 #pragma unroll
           for (int r = 0; r < 4; ++r)
             *reinterpret_cast<float4*>(rec + (size_t)(kb + r) * ld + lb) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
@@ -1597,6 +1601,12 @@ cudaError_t launch_kp(const Params& P_in, bool backward, cudaStream_t st) {
   //    per-pair kernel is launched behind it and returns at once if the flag says "shared" (no host read of ell_p).
   const bool share = POST == GPKL_POST_GP && P_in.prior != nullptr && (resident || L.gemm(false));
   if (!share) { P.prior = nullptr; P.prior_flag = nullptr; }
+  // one-buffer residency: the shared-prior kernels of sizes whose TWO work matrices do not fit shared memory but whose
+  // ONE does (145 <= T <= 208) still run shared-memory resident (one CTA per SM); only their per-pair fallback uses the
+  // workspace path.  GPKL_ONEBUF_TMAX (experiments) lowers the limit; 0 switches the extension off.
+  static const int env_tmax = [] { const char* e = getenv("GPKL_ONEBUF_TMAX"); return e ? atoi(e) : 1 << 30; }();
+  const size_t smem1 = L.floats(true, true) * sizeof(float);
+  const bool sh_resident = share && nt == 256 ? (resident || (smem1 <= kMaxDynSmem && L.TP <= env_tmax)) : (share && resident);
   const bool dual = POST == GPKL_POST_GP && L.dual(resident);
   void (*kern)(Params, int);
   if (!resident) kern = backward ? bwd_block<KERNEL, POST, false, true> : fwd_block<KERNEL, POST, false, true>;
@@ -1618,26 +1628,27 @@ cudaError_t launch_kp(const Params& P_in, bool backward, cudaStream_t st) {
   cfg.numAttrs = 0;
   if (share) {
     void (*pk)(Params, int);
-    if (!resident) pk = backward ? prior_block<KERNEL, true, true> : prior_block<KERNEL, true, false>;
+    if (!sh_resident) pk = backward ? prior_block<KERNEL, true, true> : prior_block<KERNEL, true, false>;
     else pk = backward ? prior_block<KERNEL, false, true> : prior_block<KERNEL, false, false>;
-    e = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // pre-pass carve-up: two buffers where they fit (its own look-ahead panel included), else the one-buffer layout
+    const size_t psmem = !sh_resident ? smem : (resident ? smem : smem1);
+    e = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
     if (e != cudaSuccess) return e;
-    const int pgrid = resident ? P.d.B : (P.d.B < kBlockSlots ? P.d.B : kBlockSlots);
-    pk<<<pgrid, 256, smem, st>>>(P, resident ? 0 : 1);
+    const int pgrid = sh_resident ? P.d.B : (P.d.B < kBlockSlots ? P.d.B : kBlockSlots);
+    pk<<<pgrid, 256, psmem, st>>>(P, !sh_resident ? 1 : (resident ? 0 : 2));
     note_launch();
-    if (resident) {
+    if (sh_resident) {
       if (POST == GPKL_POST_GP) {  // (the SH instantiations exist for the GP posterior only)
         void (*sk)(Params, int) = backward ? bwd_block<KERNEL, GPKL_POST_GP, false, false, true>
                                            : fwd_block<KERNEL, GPKL_POST_GP, false, false, true>;
-        const size_t smem1 = L.floats(true, true) * sizeof(float);
         e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) return e;
         static const int env_nt = [] { const char* e = getenv("GPKL_SH_NT"); return e ? atoi(e) : 0; }();
         // CTA size of the one-buffer kernels: what counts is pairs in flight per SM (latency-bound phases), so fewer
         // threads per pair where shared memory admits a third CTA (measured, T=96: forward 3.22 -> 2.50 ms with 128
         // threads; T=128: 192 threads best for both directions); GPKL_SH_NT overrides (experiments)
-        const int def_nt = nt != 256 ? nt : ((!backward && L.TP <= 112) ? 128 : 192);
-        const int snt = (env_nt >= 64 && env_nt <= 256 && env_nt % 32 == 0 && nt == 256) ? env_nt : def_nt;
+        const int def_nt = nt != 256 ? nt : ((!backward && L.TP <= 112) ? 128 : (resident ? 192 : 256));
+        const int snt = (env_nt >= 32 && env_nt <= 256 && env_nt % 32 == 0) ? env_nt : def_nt;
         int per_sm = (int)(kMaxDynSmem / (smem1 + 1024));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 2048 / snt) per_sm = 2048 / snt;

@@ -24,3 +24,29 @@ out = gpkl.bernoulli_recon(x, xd, torch.tensor([4, 2, 5], dtype=torch.int32, dev
 out.backward()
 torch.cuda.synchronize()
 print("ok recon", float(out))
+# rows either side of the path: GP-recognition sampler and ragged batch producer
+for B, D, T, S in ((3, 5, 9, 2), (2, 3, 100, 1)):
+    g = torch.Generator().manual_seed(T)
+    lengths = torch.randint((T + 1) // 2, T + 1, (B,), generator=g, dtype=torch.int32)
+    total = int(lengths.sum())
+    times = torch.arange(T, dtype=torch.float32).repeat(B, 1)
+    for b in range(B):
+        times[b, int(lengths[b]):] = 0
+    mean = torch.randn(total, D, generator=g).to(dev).requires_grad_(True)
+    logvar = (0.3 * torch.randn(total, D, generator=g) - 0.5).to(dev).requires_grad_(True)
+    ell = torch.ones(D, device=dev, requires_grad=True)
+    z, kl_sum, kl_rows = gpkl.gp_recog_sample(mean, logvar, times.to(dev), lengths.to(dev), ell,
+                                              torch.randn(B, D, S, T, generator=g).to(dev), S=S)
+    (kl_sum + z.double().sum()).backward()
+    torch.cuda.synchronize()
+    print("ok recog", B, D, T, S, float(kl_sum))
+import numpy as np
+rng = np.random.RandomState(3)
+for N, F, Tf, mt in ((5, 15, 45, 45), (4, 70, 33, 20), (3, 3, 100, 100)):
+    data = rng.rand(N, F, Tf).astype(np.float32)
+    for i in range(N):
+        data[i][:, rng.rand(Tf) < 0.4] = -1.0
+    x, times, lengths = gpkl.collate_batch(torch.from_numpy(data).to(dev), torch.arange(Tf, dtype=torch.float32, device=dev),
+                                           torch.arange(N, dtype=torch.int32, device=dev), mt)
+    torch.cuda.synchronize()
+    print("ok collate", N, F, Tf, mt, tuple(x.shape))
