@@ -135,6 +135,31 @@ def test_shared_prior_matches_per_pair(cuda_device):
         assert rel_err(b1["g_mean"], b0["g_mean"]) < 2e-5 and rel_err(b1["g_ell_q"], b0["g_ell_q"]) < 2e-5
 
 
+@pytest.mark.parametrize("T,S,ragged", [(145, 1, False), (176, 2, True), (200, 1, True), (208, 2, False), (209, 1, True)])
+def test_v1_one_buffer_residency_range(cuda_device, T, S, ragged):
+    """145 <= T <= 208: the shared-prior kernels run shared-memory resident with ONE work matrix (one CTA per SM) while the
+    per-pair fallback of the same sizes uses the workspace path; T = 209 is the first size back on the GEMM path.  Both
+    prior paths against the oracle, and against each other."""
+    case = orc.synthetic_batch(2, 3, T, S, ragged=ragged, seed=700 + T, grid=True)
+    for shared in (True, False):
+        errs = compare(case, cuda_device, S=S, tier="block", grad_ell_p=False, shared_prior=shared)
+        assert_parity(errs, "V1 one-buffer range T=%d shared=%s" % (T, shared))
+    f1, b1 = run_cuda(case, cuda_device, S=S, tier="auto", grad_ell_p=False, shared_prior=True)
+    f0, b0 = run_cuda(case, cuda_device, S=S, tier="auto", grad_ell_p=False, shared_prior=False)
+    assert rel_err(f1["kl_pairs"], f0["kl_pairs"]) < 2e-6 and rel_err(f1["z"], f0["z"]) < 1e-6
+    assert rel_err(b1["g_mean"], b0["g_mean"]) < 2e-5 and rel_err(b1["g_ell_q"], b0["g_ell_q"]) < 2e-5
+
+
+def test_v1_one_buffer_nonuniform_prior_falls_back(cuda_device):
+    """ell_p differs between latent dims: the device flag sends every size to the per-pair kernels (the one-buffer
+    kernels and the pre-pass return at once)."""
+    for T in (100, 160):
+        case = orc.synthetic_batch(2, 3, T, 1, ragged=True, seed=800 + T, grid=True)
+        case["ell_p"] = torch.tensor([1.0, 1.2, 0.9])
+        errs = compare(case, cuda_device, floor=True, S=1, tier="block", grad_ell_p=False)
+        assert_parity(errs, "V1 non-uniform prior T=%d" % T)
+
+
 V2_GRID = [g for g in GRID if g[2] in (1, 7, 10, 20, 33, 48, 100, 160)]
 
 
