@@ -47,6 +47,12 @@ __device__ long long g_ptrace[8];
 #define PT_FLUSH
 #endif
 
+// Address-space hint.  The resident kernels keep their work matrices in shared memory, but the phase functions below are
+// shared with the workspace (global memory) paths and are not inlined, so without the hint every operand access is a
+// generic LD.E / ST.E (64-bit address arithmetic, longer latency) instead of LDS / STS: 1186 of the 1721 128-bit loads
+// of the one-buffer backward kernel were generic (cuobjdump -sass).  SM = "the matrix operands are in shared memory".
+#define GPKL_SHARED_HINT(p) __builtin_assume(__isShared(p))
+
 template <int SGN>
 __device__ __forceinline__ void tile_fma(float (&acc)[4][4], const float4& u4, const float4& v4) {
   const float u[4] = {SGN > 0 ? u4.x : -u4.x, SGN > 0 ? u4.y : -u4.y, SGN > 0 ? u4.z : -u4.z, SGN > 0 ? u4.w : -u4.w};
@@ -339,12 +345,17 @@ __device__ __forceinline__ void panel_tiles(const float* __restrict__ Bm, int ld
 // pan2 != NULL: LOOK-AHEAD.  The serial 16x16 diagonal factor (one warp, ~3 K cycles) used to idle the other warps at a
 // barrier; now, while warp 0 factors the diagonal block of panel j, the other warps already apply the finished columns
 // [kstart, j0) to panel j+1 (into pan2), and only the 16 columns of panel j itself are applied after its rows are solved.
-template <int KERNEL, bool DUAL, bool FROM_VIEW, bool XRC = false>
+template <int KERNEL, bool DUAL, bool FROM_VIEW, bool XRC = false, bool SM = false>
 __device__ __noinline__ void chol_panels(float* __restrict__ Bm, int ldm, int c_begin, int c_end, int kstart, const Lay& L,
                                          int T, bool extra, const float* __restrict__ ts, const float* __restrict__ mm,
                                          float ell, float sig, float noise, float* __restrict__ pan,
                                          float* __restrict__ dg, float* __restrict__ rdg, int* bad, Grp g,
                                          float* __restrict__ pan2 = nullptr) {
+  if (SM) {
+    GPKL_SHARED_HINT(Bm); GPKL_SHARED_HINT(pan); GPKL_SHARED_HINT(dg); GPKL_SHARED_HINT(rdg); GPKL_SHARED_HINT(ts);
+    GPKL_SHARED_HINT(mm);
+    if (pan2) GPKL_SHARED_HINT(pan2);
+  }
   const int tid = g.tid, NT = g.nt;
   const int ld = L.ld, TP = L.TP;  // ld: stride of the staging panel `pan`
   const KernC<KERNEL> kc(ell, sig);
@@ -397,13 +408,13 @@ __device__ __noinline__ void chol_panels(float* __restrict__ Bm, int ldm, int c_
 }
 
 // Resident path: the whole factorisation, kernel entries generated on the fly.
-template <int KERNEL, bool DUAL, bool XRC = false>
+template <int KERNEL, bool DUAL, bool XRC = false, bool SM = false>
 __device__ __forceinline__ void chol_block(float* __restrict__ Bm, const Lay& L, int T, bool extra, const float* __restrict__ ts,
                                            const float* __restrict__ mm, float ell, float sig, float noise,
                                            float* __restrict__ pan, float* __restrict__ dg, float* __restrict__ rdg, int* bad,
                                            Grp g, float* __restrict__ pan2 = nullptr) {
   const int Tact = (T + NB - 1) / NB * NB;
-  chol_panels<KERNEL, DUAL, false, XRC>(Bm, L.ld, 0, Tact, 0, L, T, extra, ts, mm, ell, sig, noise, pan, dg, rdg, bad, g, pan2);
+  chol_panels<KERNEL, DUAL, false, XRC, SM>(Bm, L.ld, 0, Tact, 0, L, T, extra, ts, mm, ell, sig, noise, pan, dg, rdg, bad, g, pan2);
 }
 
 // X = L^-1 B by 16-row blocks into the XR triangle of Xb.  L: LC triangle of Lb with inverse diagonal
@@ -412,10 +423,14 @@ __device__ __forceinline__ void chol_block(float* __restrict__ Bm, const Lay& L,
 // Xb is a VIEW of the solution: X(i,k) at Xb[(i+1)*ldx + k].  Rows [r_begin, r_end) are solved; contributions of
 // rows < kstart are assumed applied already and with FROM_VIEW the starting values are read from the view (the GEMM
 // phase of the large-T path left them there) instead of the right-hand side.
-template <bool IDENT, bool DUAL, bool FROM_VIEW>
+template <bool IDENT, bool DUAL, bool FROM_VIEW, bool SM = false>
 __device__ __noinline__ float solve_rows(const float* __restrict__ Lb, const float* __restrict__ rdgL, const float* __restrict__ Bb,
                                          float* __restrict__ Xb, int ldx, int r_begin, int r_end, int kstart, const Lay& L,
                                          int T, float* __restrict__ pan, Grp g) {
+  if (SM) {
+    GPKL_SHARED_HINT(Lb); GPKL_SHARED_HINT(rdgL); GPKL_SHARED_HINT(Xb); GPKL_SHARED_HINT(pan);
+    if (!IDENT) GPKL_SHARED_HINT(Bb);
+  }
   const int tid = g.tid, NT = g.nt;
   const int ld = L.ld;
   float ssq = 0.0f;
@@ -483,12 +498,12 @@ __device__ __noinline__ float solve_rows(const float* __restrict__ Lb, const flo
 }
 
 // Resident path: X = L^-1 B over all rows.
-template <bool IDENT, bool DUAL>
+template <bool IDENT, bool DUAL, bool SM = false>
 __device__ __forceinline__ float solve_block(const float* __restrict__ Lb, const float* __restrict__ rdgL,
                                              const float* __restrict__ Bb, float* __restrict__ Xb, const Lay& L, int T,
                                              float* __restrict__ pan, Grp g) {
   const int Tact = (T + NB - 1) / NB * NB;
-  return solve_rows<IDENT, DUAL, false>(Lb, rdgL, Bb, Xb, L.ld, 0, Tact, 0, L, T, pan, g);
+  return solve_rows<IDENT, DUAL, false, SM>(Lb, rdgL, Bb, Xb, L.ld, 0, Tact, 0, L, T, pan, g);
 }
 
 // ---- GEMM-structured phases of the workspace path (144 < T <= 512, 256 threads) -------------------------------
@@ -726,10 +741,11 @@ __device__ __noinline__ float solve_gemm(const float* __restrict__ Lb, const flo
 // VREV (one-buffer backward): V = C' is stored row- and column-reversed in the triangle of Vb that L_q vacated,
 // C'(i,l) at Vb[(TP-1-i)*ld + (TP-1-l)] (l <= i), so that a row of C' is still one aligned float4 per 4 columns; the
 // tile then holds its columns in reverse order (acc[r][c] <-> l = lb + 3 - c).
-template <int KERNEL, bool VREV = false>
+template <int KERNEL, bool VREV = false, bool SM = false>
 __device__ __noinline__ double contract_block(const float* __restrict__ Ub, const float* __restrict__ Vb, const Lay& L, int T,
                                  const float* __restrict__ ts, float ell, float sig, Grp g,
                                  const float* __restrict__ kinv = nullptr, float hg = 0.0f) {
+  if (SM) { GPKL_SHARED_HINT(Ub); GPKL_SHARED_HINT(Vb); GPKL_SHARED_HINT(ts); }
   const int NT = g.nt;
   const int ld = L.ld, TP = L.TP;
   const int nk = (T + 3) / 4;
@@ -949,8 +965,10 @@ __host__ __device__ inline size_t rec_dg_offset(const Lay& L) { return (size_t)L
 
 // sum_{c < i < T} A(i,c)^2, A = X L:  Xc column-major with explicit zeros above the diagonal (X(i,k) at Xc[k*ldx+i]),
 // Lq's row-major copy in the XR triangle of Lb (L(k,c) at Lb[(k+1)*ld + c], garbage above the diagonal).  Thread partial.
+template <bool SM = false>
 __device__ __noinline__ float product_ssq_block(const float* __restrict__ Xc, int ldx, const float* __restrict__ Lb,
                                                 const Lay& L, int T, Grp g) {
+  if (SM) GPKL_SHARED_HINT(Lb);
   const int ld = L.ld;
   const int nt = (T + 3) / 4;
   const int ntri = nt * (nt + 1) / 2;
@@ -1084,7 +1102,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) prior_block(Params P, int u
   // use_slot: 0 = resident two-buffer carve-up, 1 = workspace slot, 2 = resident ONE-buffer carve-up (sizes whose two-buffer
   // layout does not fit shared memory but whose one-buffer shared-prior kernels do: 145 <= T <= 208)
   const bool onebuf = use_slot == 2;
-  Sm s(smem_f, L, use_slot == 1 ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr, onebuf);
+  Sm s(smem_f, L, SLOT ? (use_slot == 1 ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr) : nullptr, onebuf);
   float* const W = onebuf ? s.B2 : s.B1;  // the work matrix of the pre-pass
   const int TP = L.TP, ld = L.ld;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -1106,9 +1124,9 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) prior_block(Params P, int u
         chol_gemm<KERNEL>(W, L, T, false, s.ts, s.mm, lp, sig, noise, s.pan, s.wide, s.stg, s.dgp, s.rdp, &bad);
         (void)solve_gemm<true>(W, s.rdp, nullptr, W, L, T, s.pan, s.wide, s.stg);
       } else {
-        chol_block<KERNEL, false>(W, L, T, false, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, all,
+        chol_block<KERNEL, false, false, !SLOT>(W, L, T, false, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, all,
                                   (onebuf || (!use_slot && L.dual(true))) ? s.pan2 : nullptr);
-        (void)solve_block<true, false>(W, s.rdp, nullptr, W, L, T, s.pan, all);
+        (void)solve_block<true, false, !SLOT>(W, s.rdp, nullptr, W, L, T, s.pan, all);
       }
       __syncthreads();
     }
@@ -1190,7 +1208,8 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
   if (SH && *P.prior_flag == 0) return;
   if (!SH && P.skip_if_shared && *P.prior_flag != 0) return;
   const Lay L(d.T_max, d.S);
-  Sm s(smem_f, L, use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr, SH);
+  // (resident instantiations pass a literal NULL slot: the work-matrix pointers are then provably shared-memory addresses)
+  Sm s(smem_f, L, SLOT ? (use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr) : nullptr, SH);
   const int S = d.S, TP = L.TP, ld = L.ld;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
   const Groups G(DUAL);
@@ -1216,14 +1235,14 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
     const bool gm = SLOT && L.gemm(false);  // large T: GEMM-structured phases on shared-memory panels
     if (!shared) {
       if (gm) chol_gemm<KERNEL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.wide, s.stg, s.dgp, s.rdp, &bad);
-      else if (G.g0) chol_block<KERNEL, DUAL>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
+      else if (G.g0) chol_block<KERNEL, DUAL, false, !SLOT>(s.B1, L, T, true, s.ts, s.mm, P.ell_p[dd], sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
     }
     phase_mark(P, 2);
     double part = 0.0, ldp = 0.0, ldq = 0.0;
     if (POST == GPKL_POST_GP && shared) {
       // ---- shared-prior path: only K_q is factored here (all threads); L_p^-1 and diag L_p come from the record
       if (gm) chol_gemm<KERNEL, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
-      else chol_block<KERNEL, false, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.dgq, s.rdq, &bad, G.all,
+      else chol_block<KERNEL, false, true, !SLOT>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.dgq, s.rdq, &bad, G.all,
                                            SH ? s.pan2 : nullptr);
       phase_mark(P, 3);
       for (int i = threadIdx.x; i < T; i += blockDim.x) {  // z_s = m + L_q eps_s (loads batched 8 ahead: L_q may be global)
@@ -1279,7 +1298,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
           s.aa[i] = a0 + a1;
         }
         phase_mark(P, 8);
-        ssq = product_ssq_block(rec, ld, s.B2, L, T, G.all);
+        ssq = product_ssq_block<!SLOT>(rec, ld, s.B2, L, T, G.all);
       }
       __syncthreads();
       phase_mark(P, 5);
@@ -1295,7 +1314,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
       if (gm) chol_gemm<KERNEL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
       if (G.g1) {
         if (!gm)
-          chol_block<KERNEL, DUAL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, G.dual ? s.pan2 : s.pan, s.dgq,
+          chol_block<KERNEL, DUAL, false, !SLOT>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, G.dual ? s.pan2 : s.pan, s.dgq,
                                    s.rdq, &bad, G.chain);
         for (int i = G.chain.tid; i < T; i += G.chain.nt) {  // z_s = m + L_q eps_s
           for (int sx = 0; sx < S; ++sx) {
@@ -1309,7 +1328,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
       if (G.dual) __syncthreads();  // join the two chains
       phase_mark(P, 4);
       const float ssq = gm ? solve_gemm<false>(s.B1, s.rdp, s.B2, s.B1, L, T, s.pan, s.wide, s.stg)
-                           : solve_block<false, DUAL>(s.B1, s.rdp, s.B2, s.B1, L, T, s.pan, G.all);
+                           : solve_block<false, DUAL, !SLOT>(s.B1, s.rdp, s.B2, s.B1, L, T, s.pan, G.all);
       phase_mark(P, 5);
       part = (double)ssq;
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
@@ -1321,7 +1340,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
       }
     } else {
       if (gm) (void)solve_gemm<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, s.wide, s.stg);
-      else (void)solve_block<true, DUAL>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, G.all);
+      else (void)solve_block<true, DUAL, !SLOT>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, G.all);
       for (int i = threadIdx.x; i < T; i += blockDim.x) {
         float h = 0.0f;
         for (int k = i; k < T; ++k) { const float x = s.B1[(size_t)(k + 1) * ld + i]; h = fmaf(x, x, h); }
@@ -1361,7 +1380,8 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
   if (SH && *P.prior_flag == 0) return;
   if (!SH && P.skip_if_shared && *P.prior_flag != 0) return;
   const Lay L(d.T_max, d.S);
-  Sm s(smem_f, L, use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr, SH);
+  // (resident instantiations pass a literal NULL slot: the work-matrix pointers are then provably shared-memory addresses)
+  Sm s(smem_f, L, SLOT ? (use_slot ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr) : nullptr, SH);
   const int S = d.S, TP = L.TP, ld = L.ld;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
   const double g_sum = P.g_kl_sum ? *P.g_kl_sum : 1.0;
@@ -1389,10 +1409,10 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
     double t1 = 0.0;
     if (!shared && G.g0) {  // ---- prior chain: L_p, X_p = L_p^-1, alpha = K_p^-1 m, t1 = <K_p^-1, dK_q/d ell>
       if (gm) chol_gemm<KERNEL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.wide, s.stg, s.dgp, s.rdp, &bad);
-      else chol_block<KERNEL, DUAL>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
+      else chol_block<KERNEL, DUAL, false, !SLOT>(s.B1, L, T, true, s.ts, s.mm, lp, sig, noise, s.pan, s.dgp, s.rdp, &bad, G.chain);
       phase_mark(P, 18);
       if (gm) (void)solve_gemm<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, s.wide, s.stg);
-      else (void)solve_block<true, DUAL>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, G.chain);
+      else (void)solve_block<true, DUAL, !SLOT>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, G.chain);
       phase_mark(P, 19);
       // a = L_p^-1 m (the extra row of the factor) into shared memory once, then alpha = X_p^T a with the
       // column loads issued 8 rows ahead
@@ -1414,7 +1434,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
       if (POST == GPKL_POST_GP)
         t1 = gm ? contract_gemm<KERNEL, true>(s.B1, s.B1, L, T, s.ts, lq, sig, s.stg)
            : SLOT ? contract_block_staged<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, s.stg)
-                      : contract_block<KERNEL>(s.B1, s.B1, L, T, s.ts, lq, sig, G.chain);
+                      : contract_block<KERNEL, false, !SLOT>(s.B1, s.B1, L, T, s.ts, lq, sig, G.chain);
       phase_mark(P, 21);
     }
     if (POST == GPKL_POST_DIAG) {
@@ -1431,7 +1451,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
       if (G.g1) {  // ---- posterior chain: L_q, w = L_q^T g_z, X_q = L_q^-1
         if (gm) chol_gemm<KERNEL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
         else
-          chol_block<KERNEL, DUAL>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, G.dual ? s.pan2 : s.pan, s.dgq, s.rdq,
+          chol_block<KERNEL, DUAL, false, !SLOT>(s.B2, L, T, false, s.ts, s.mm, lq, sig, noise, G.dual ? s.pan2 : s.pan, s.dgq, s.rdq,
                                    &bad, G.chain, SH ? s.pan2 : nullptr);
         phase_mark(P, 22);
         if (SLOT) {
@@ -1465,7 +1485,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
         }
         phase_mark(P, 23);
         if (gm) (void)solve_gemm<true>(s.B2, s.rdq, nullptr, s.B2, L, T, s.pan, s.wide, s.stg);
-        else (void)solve_block<true, DUAL>(s.B2, s.rdq, nullptr, s.B2, L, T, G.dual ? s.pan2 : s.pan, G.chain);
+        else (void)solve_block<true, DUAL, !SLOT>(s.B2, s.rdq, nullptr, s.B2, L, T, G.dual ? s.pan2 : s.pan, G.chain);
         phase_mark(P, 24);
       }
       __syncthreads();  // join: X_p (dead after t1), X_q, w, pd are complete
@@ -1559,8 +1579,8 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) bwd_block(Params P, int use
       const float hg = 0.5f * g;
       const double t2 = gm ? contract_gemm<KERNEL, false>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg, kinv, hg)
                         : SLOT ? contract_block_staged<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, s.stg, kinv, hg)
-                        : SH ? contract_block<KERNEL, true>(s.B2, s.B2, L, T, s.ts, lq, sig, G.all, kinv, hg)
-                             : contract_block<KERNEL>(s.B2, s.B1, L, T, s.ts, lq, sig, G.all, kinv, hg);
+                        : SH ? contract_block<KERNEL, true, true>(s.B2, s.B2, L, T, s.ts, lq, sig, G.all, kinv, hg)
+                             : contract_block<KERNEL, false, !SLOT>(s.B2, s.B1, L, T, s.ts, lq, sig, G.all, kinv, hg);
       phase_mark(P, 26);
       const double gq = block_sum(0.5 * (double)g * t1 + t2, s.red);
       phase_mark(P, 27);
