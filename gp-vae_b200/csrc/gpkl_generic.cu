@@ -194,8 +194,11 @@ __device__ SmemPlan carve(unsigned char* base, int T, int S, bool mats_in_smem, 
   return s;
 }
 
-template <int KERNEL>
-__global__ void __launch_bounds__(NT) fwd_generic(Params P, int Tcap, int ld_cap, int mats_in_smem) {
+// INSMEM: the two work matrices live in shared memory (a compile-time fact, so that their accesses are LDS / STS and not
+// generic loads -- the run-time selection between a shared and a global carve-up made every matrix access generic).
+template <int KERNEL, bool INSMEM>
+__global__ void __launch_bounds__(NT) fwd_generic(Params P, int Tcap, int ld_cap, int) {
+  constexpr bool mats_in_smem = INSMEM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int bad;
   const GpklDesc& d = P.d;
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(NT) fwd_generic(Params P, int Tcap, int ld_cap
   const int S = d.S;
   const float noise = d.noise;
   const float sig = (float)(1.0 - (double)noise);
-  float* slot = (!mats_in_smem && P.scratch) ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr;
+  float* slot = mats_in_smem ? nullptr : (P.scratch ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr);
   for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
     const int T = P.lengths[b];
@@ -321,8 +324,9 @@ __global__ void __launch_bounds__(NT) fwd_generic(Params P, int Tcap, int ld_cap
   }
 }
 
-template <int KERNEL>
-__global__ void __launch_bounds__(NT) bwd_generic(Params P, int Tcap, int ld_cap, int mats_in_smem) {
+template <int KERNEL, bool INSMEM>
+__global__ void __launch_bounds__(NT) bwd_generic(Params P, int Tcap, int ld_cap, int) {
+  constexpr bool mats_in_smem = INSMEM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int bad;
   const GpklDesc& d = P.d;
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(NT) bwd_generic(Params P, int Tcap, int ld_cap
   const float noise = d.noise;
   const float sig = (float)(1.0 - (double)noise);
   const bool want_lp = (d.flags & GPKL_FLAG_GRAD_ELL_P) != 0;
-  float* slot = (!mats_in_smem && P.scratch) ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr;
+  float* slot = mats_in_smem ? nullptr : (P.scratch ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr);
   const double g_sum = P.g_kl_sum ? *P.g_kl_sum : 1.0;
   for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
@@ -603,11 +607,17 @@ cudaError_t launch_generic(const Params& P, bool backward, cudaStream_t st) {
   if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
   const int grid = in_smem ? generic_grid(d, true, smem) : min(148, max(1, d.B * d.D));
   if (!backward) {
-    return d.kernel == GPKL_KERNEL_RBF ? launch(fwd_generic<GPKL_KERNEL_RBF>, P, grid, smem, in_smem, st)
-                                       : launch(fwd_generic<GPKL_KERNEL_CAUCHY>, P, grid, smem, in_smem, st);
+    if (in_smem)
+      return d.kernel == GPKL_KERNEL_RBF ? launch(fwd_generic<GPKL_KERNEL_RBF, true>, P, grid, smem, in_smem, st)
+                                         : launch(fwd_generic<GPKL_KERNEL_CAUCHY, true>, P, grid, smem, in_smem, st);
+    return d.kernel == GPKL_KERNEL_RBF ? launch(fwd_generic<GPKL_KERNEL_RBF, false>, P, grid, smem, in_smem, st)
+                                       : launch(fwd_generic<GPKL_KERNEL_CAUCHY, false>, P, grid, smem, in_smem, st);
   }
-  return d.kernel == GPKL_KERNEL_RBF ? launch(bwd_generic<GPKL_KERNEL_RBF>, P, grid, smem, in_smem, st)
-                                     : launch(bwd_generic<GPKL_KERNEL_CAUCHY>, P, grid, smem, in_smem, st);
+  if (in_smem)
+    return d.kernel == GPKL_KERNEL_RBF ? launch(bwd_generic<GPKL_KERNEL_RBF, true>, P, grid, smem, in_smem, st)
+                                       : launch(bwd_generic<GPKL_KERNEL_CAUCHY, true>, P, grid, smem, in_smem, st);
+  return d.kernel == GPKL_KERNEL_RBF ? launch(bwd_generic<GPKL_KERNEL_RBF, false>, P, grid, smem, in_smem, st)
+                                     : launch(bwd_generic<GPKL_KERNEL_CAUCHY, false>, P, grid, smem, in_smem, st);
 }
 
 }  // namespace gpkl
