@@ -150,6 +150,26 @@ def test_v1_one_buffer_residency_range(cuda_device, T, S, ragged):
     assert rel_err(b1["g_mean"], b0["g_mean"]) < 2e-5 and rel_err(b1["g_ell_q"], b0["g_ell_q"]) < 2e-5
 
 
+@pytest.mark.parametrize("T_max,lengths", [(100, [100, 1, 0, 17, 64]), (160, [3, 160, 0, 33]), (130, [16, 15, 130])])
+def test_v1_block_tier_extreme_raggedness(cuda_device, T_max, lengths):
+    """One-buffer kernels with sequences far shorter than T_max in the same batch (lengths 0, 1, < one panel)."""
+    B, D, S = len(lengths), 3, 2
+    case = orc.synthetic_batch(B, D, T_max, S, ragged=False, seed=900 + T_max, grid=True)
+    off = [0]
+    for b in range(B):
+        off.append(off[-1] + T_max)
+    keep = torch.cat([torch.arange(off[b], off[b] + lengths[b]) for b in range(B)])
+    keepz = torch.cat([torch.arange(S * off[b] + s * T_max, S * off[b] + s * T_max + lengths[b]) for b in range(B) for s in range(S)])
+    case["mean"] = case["mean"][keep].contiguous()
+    case["g_z"] = case["g_z"][keepz].contiguous()
+    case["lengths"] = torch.tensor(lengths, dtype=torch.int32)
+    for b in range(B):
+        case["times"][b, lengths[b]:] = 0
+    for shared in (True, False):
+        errs = compare(case, cuda_device, S=S, tier="block", grad_ell_p=False, shared_prior=shared)
+        assert_parity(errs, "ragged T_max=%d shared=%s" % (T_max, shared))
+
+
 def test_v1_one_buffer_nonuniform_prior_falls_back(cuda_device):
     """ell_p differs between latent dims: the device flag sends every size to the per-pair kernels (the one-buffer
     kernels and the pre-pass return at once)."""
