@@ -170,6 +170,25 @@ def test_v1_block_tier_extreme_raggedness(cuda_device, T_max, lengths):
         assert_parity(errs, "ragged T_max=%d shared=%s" % (T_max, shared))
 
 
+def test_v1_block_tier_fuzz_shared_vs_per_pair(cuda_device):
+    """Random (T, D, S, raggedness, kernel) over the block tier's resident range: the one-buffer shared-prior kernels and the
+    two-chain per-pair kernels are independent code paths for the same numbers."""
+    rng = torch.Generator().manual_seed(2024)
+    for it in range(14):
+        T = int(torch.randint(65, 209, (1,), generator=rng))
+        D = int(torch.randint(1, 6, (1,), generator=rng))
+        S = int(torch.randint(1, 4, (1,), generator=rng))
+        B = int(torch.randint(1, 4, (1,), generator=rng))
+        kernel = "rbf" if it % 3 else "cauchy"
+        case = orc.synthetic_batch(B, D, T, S, ragged=bool(it % 2), seed=1000 + it, grid=True)
+        f1, b1 = run_cuda(case, cuda_device, kernel=kernel, S=S, tier="block", grad_ell_p=False, shared_prior=True)
+        f0, b0 = run_cuda(case, cuda_device, kernel=kernel, S=S, tier="block", grad_ell_p=False, shared_prior=False)
+        tag = "T=%d D=%d S=%d B=%d %s" % (T, D, S, B, kernel)
+        assert int(f1["status"]) == 0 and int(f0["status"]) == 0, tag
+        assert rel_err(f1["kl_pairs"], f0["kl_pairs"]) < 4e-6 and rel_err(f1["z"], f0["z"]) < 1e-6, tag
+        assert rel_err(b1["g_mean"], b0["g_mean"]) < 3e-5 and rel_err(b1["g_ell_q"], b0["g_ell_q"]) < 3e-5, tag
+
+
 def test_v1_one_buffer_nonuniform_prior_falls_back(cuda_device):
     """ell_p differs between latent dims: the device flag sends every size to the per-pair kernels (the one-buffer
     kernels and the pre-pass return at once)."""
