@@ -1307,8 +1307,10 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
         const double lpd = (double)s.dgp[i], lqd = (double)s.dgq[i];
         const double av = (double)s.aa[i];
         part += diag_term(lqd / lpd) + av * av;
-        ldp += 2.0 * log(lpd);
-        ldq += 2.0 * log(lqd);
+        if (P.logdets) {  // float64 logs only when the log-determinants are requested (they are not part of the KL form used)
+          ldp += 2.0 * log(lpd);
+          ldq += 2.0 * log(lqd);
+        }
       }
     } else if (POST == GPKL_POST_GP) {
       if (gm) chol_gemm<KERNEL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
@@ -1335,8 +1337,10 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
         const double lpd = (double)s.dgp[i], lqd = (double)s.dgq[i];
         const double av = (double)s.B1[(size_t)i * ld + TP];  // a_i = (L_p^-1 m)_i rides in the extra row
         part += diag_term(lqd / lpd) + av * av;
-        ldp += 2.0 * log(lpd);
-        ldq += 2.0 * log(lqd);
+        if (P.logdets) {  // float64 logs only when the log-determinants are requested (they are not part of the KL form used)
+          ldp += 2.0 * log(lpd);
+          ldq += 2.0 * log(lqd);
+        }
       }
     } else {
       if (gm) (void)solve_gemm<true>(s.B1, s.rdp, nullptr, s.B1, L, T, s.pan, s.wide, s.stg);
