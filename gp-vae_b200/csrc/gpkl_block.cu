@@ -1669,9 +1669,10 @@ cudaError_t launch_kp(const Params& P_in, bool backward, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         static const int env_nt = [] { const char* e = getenv("GPKL_SH_NT"); return e ? atoi(e) : 0; }();
         // CTA size of the one-buffer kernels: what counts is pairs in flight per SM (latency-bound phases), so fewer
-        // threads per pair where shared memory admits a third CTA (measured, T=96: forward 3.22 -> 2.50 ms with 128
-        // threads; T=128: 192 threads best for both directions); GPKL_SH_NT overrides (experiments)
-        const int def_nt = nt != 256 ? nt : ((!backward && L.TP <= 112) ? 128 : (resident ? 192 : 256));
+        // threads per pair where shared memory admits a third CTA (measured at the end of session 3, fwd | bwd ms at
+        // 128 / 192 / 256 threads: T=96 2.33|4.06, 2.75|4.53, 2.88|4.80; T=128 2.61|4.32, 2.43|4.06, 2.55|4.13;
+        // T=160 (one CTA per SM) 3.84|6.30, 3.31|5.80, 3.17|5.59); GPKL_SH_NT overrides (experiments)
+        const int def_nt = nt != 256 ? nt : (L.TP <= 112 ? 128 : (resident ? 192 : 256));
         const int snt = (env_nt >= 32 && env_nt <= 256 && env_nt % 32 == 0) ? env_nt : def_nt;
         int per_sm = (int)(kMaxDynSmem / (smem1 + 1024));
         if (per_sm < 1) per_sm = 1;
