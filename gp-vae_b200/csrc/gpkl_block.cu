@@ -1,4 +1,9 @@
-// Block tier: one CTA per (sequence, latent-dim) pair, 32 < T <= ~160, matrices resident in shared memory.
+// Block tier: one CTA per (sequence, latent-dim) pair, T > 64.  Three regimes (launch_kp):
+//   resident    both work matrices in shared memory (T <= 144); prior and posterior chains on two half-CTA groups
+//   one-buffer  the shared-prior kernels (SH): K_p factored once per sequence by a pre-pass, ONE work matrix per pair
+//               (T <= 208), 1-3 CTAs per SM, look-ahead panel Cholesky, tiles dealt by contraction length
+//   GEMM path   work matrices in per-CTA workspace slots (T <= 512), 64-wide panels in shared memory updated by a staged
+//               128x64 cp.async GEMM tile; beyond 512 the resident code reading the slots through L1/L2
 //
 // Loop-based by design (the register-resident warp tier is instruction-fetch bound beyond T ~ 32, see
 // profiles/r01_c2_warp_tier_unrolled_ncu_summary.txt): every O(T^3) phase is the same inner loop,
@@ -22,9 +27,8 @@
 //              derivative evaluated in the epilogue (never stored).
 // Math: SURVEY.md Appendix A; reference replaced: src/Models/Full_GP_VAE_dynamic_time.py:149-172, :174-195,
 // :242-260 (+ TF autodiff :361); V2 src/Models/VAE_GPprior_diag_cov.py:64-71, :100-119.
-#include <string.h>
-
 #include <stdlib.h>
+#include <string.h>
 
 #include "gpkl_common.cuh"
 #include "gpkl_launch.h"
