@@ -20,7 +20,8 @@ bool pdl_enabled();  // programmatic dependent launch of the per-pair kernels be
 // Shared-prior records (Params::prior): floats per sequence, an upper bound over the tiers' layouts
 // (warp tier: packed L_p^-1 rows + diag + K_p^-1, gpkl_warp.cuh PriorRec; block tier: gpkl_block.cu).
 inline size_t prior_record_floats(int T_max) {
-  const size_t TP = ((size_t)(T_max < 1 ? 1 : T_max) + 15) / 16 * 16;
+  const size_t al = T_max > 208 ? 64 : 16;  // as Lay (gpkl_block.cu): 64 x 64 tiles beyond the resident sizes
+  const size_t TP = ((size_t)(T_max < 1 ? 1 : T_max) + al - 1) / al * al;
   return 2 * (TP + 1) * (TP + 4);
 }
 
@@ -41,6 +42,13 @@ bool block_tier_supports(const GpklDesc& d, bool backward);
 bool block_tier_resident(const GpklDesc& d);
 size_t block_slot_floats(const GpklDesc& d);  // 0 when resident
 cudaError_t launch_block(const Params& P, bool backward, cudaStream_t st);
+
+// tile tier (gpkl_tile.cu): the shared-prior GP posterior for 208 < T <= 512 -- one tile-packed, L2-resident triangle per
+// CTA, operands streamed by bulk asynchronous copies; launched by the block tier between its pre-pass and its per-pair
+// kernel (it uses the block tier's workspace slots and prior records)
+bool tile_tier_supports(const GpklDesc& d, bool backward);
+size_t tile_slot_floats(const GpklDesc& d);
+cudaError_t launch_tile(const Params& P, bool backward, cudaStream_t st);
 
 // reconstruction term (gpkl_recon.cu), SURVEY.md S8(f) row 1
 int recon_grid(long long rows);

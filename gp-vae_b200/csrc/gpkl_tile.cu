@@ -1,0 +1,839 @@
+// Tile tier: the shared-prior GP posterior for 208 < T <= 512 (BASELINE config C4: T = 512), one CTA (256 threads) per
+// (sequence, latent-dim) pair, one pair in flight per SM.
+//
+// Why a tier of its own.  A T = 512 factor is 0.5 MB packed: it fits neither the registers of a warp nor the shared
+// memory of an SM, and the block tier's GEMM path kept TWO padded squares per pair in 2 x 148 workspace slots (627 MB,
+// five times the L2) -- 300-580x the algorithmic DRAM bytes (profiles/traffic.json, round 1).  Here a pair owns ONE
+// tile-packed lower triangle (nT (nT+1)/2 tiles of 64 x 64 floats, 576 KB at T = 512; 148 CTAs -> 85 MB < 126 MB L2;
+// the backward adds the triangle of C') that stays L2-resident while it is reused pair after pair, and every O(T^3)
+// phase streams 4 KB operand chunks L2 -> shared memory with bulk asynchronous copies (cp.async.bulk, the TMA engine;
+// SASS: UBLKCP) completing on mbarriers, two stages per thread group.  Distributed shared memory was weighed and not
+// used: a 4-CTA cluster would hold the triangle, but the measured DSMEM bandwidth (17-21 B/clk/SM,
+// B300_MICROARCH.md) is half of what L2 delivers per SM (~42 B/clk) and every panel would have to be broadcast to
+// three peers, whereas from L2 each chunk is read once by the one CTA that needs it.
+//
+// Micro-kernel.  A GROUP of 64 threads (two warps) owns a 64 x 64 output tile, 8 x 8 per thread (two 4-row blocks x two
+// 4-column blocks, 32 apart), operands contraction-major in shared memory ([k][64]): four 128-bit loads (each one
+// wavefront: 8 row-threads are the fast lane index, so a warp reads 128 contiguous bytes of A and 64 of B) feed 32
+// packed FFMA2.  The CTA is four such groups working on DIFFERENT tiles, each with its own 2-stage chunk ring, so the
+// only CTA-wide barriers are at phase boundaries.
+//
+// Tile layouts (all "contraction index major", so any 16 consecutive contraction steps are one contiguous 4 KB chunk):
+//     L  tile (I,K):  [k][i]   (column-major)   operand of the panel update  raw(I,J) = K(I,J) - sum_K L(I,K) L(J,K)^T
+//     X  tile (I,K):  [i][k]   (row-major)      X = L^-1, operand of the inverse and of the contraction
+//     C' tile (I,L):  [i][l]   (row-major)
+// Diagonal tiles carry explicit zeros in their other half and the rows / columns beyond a sequence's length are the
+// identity, so no phase masks operands.
+//
+// Phases per pair (S = samples, T_b <= T_max ragged; nTb = ceil(T_b / 64)):
+//   forward   for each 64-column panel J:  raw panel (split-K over the groups, partials reduced in shared memory with the
+//             kernel matrix GENERATED in the same pass) -> 64 x 64 diagonal block factored + inverted in shared memory
+//             -> rows below = raw x L_JJ^-T (micro-kernel, operands resident) -> the finished panel, row-major in shared
+//             memory, is at once the B operand of  A(:,J) = X_p(:,J:) L_q(J:,J)  (A operand: the prior record,
+//             streamed) and of z = m + L_q eps.  Nothing of L_q is ever stored row-major in global memory.
+//   backward  the same factorisation (+ w = L_q^T g_z per panel), then X_q = L_q^-1 IN PLACE by 64-row blocks
+//             (GEMM against the rows already inverted, then L_II^-1 from the left), C' by column prefix sums, and the
+//             contraction  sum_kl dK_kl (g/2 K_p^-1 + X_q^T C')_kl  with the kernel derivative in the epilogue.
+// The per-sequence prior records (L_p^-1, diag L_p, K_p^-1) come from the block tier's pre-pass, unchanged.
+// Reference replaced: tf.cholesky / tf.matrix_inverse / tf.linalg.logdet / tf.matmul of
+// src/Models/Full_GP_VAE_dynamic_time.py:165, :250-254 and TF autodiff through them (:361).
+#include <stdlib.h>
+#include <string.h>
+
+#include "gpkl_common.cuh"
+#include "gpkl_diag.cuh"
+#include "gpkl_launch.h"
+
+namespace gpkl {
+namespace {
+
+constexpr int TS = 64;             // tile edge
+constexpr int TF = TS * TS;        // floats per tile (16 KB)
+constexpr int KC = 16;             // contraction steps per staged chunk
+constexpr int CH = KC * TS;        // floats per operand chunk (4 KB)
+constexpr int STAGE_F = 2 * CH;    // one stage: A chunk | B chunk
+constexpr int GSTG_F = 2 * STAGE_F;  // two stages per group == one tile (doubles as the group's partial-tile buffer)
+constexpr int NGRP = 4;            // thread groups per CTA
+constexpr int NTHR = 256;
+constexpr int NVEC = 8;            // per-pair vectors of TP floats besides the per-sample ones
+
+// ---- shared-memory carve-up (floats), identical on host and device ------------------------------------------------
+struct TLay {
+  int TP, nT, S;
+  __host__ __device__ TLay(int Tmax, int S_) : S(S_) {
+    TP = (Tmax + TS - 1) / TS * TS;
+    if (TP < TS) TP = TS;
+    nT = TP / TS;
+  }
+  __host__ __device__ int ntri() const { return nT * (nT + 1) / 2; }
+  __host__ __device__ size_t nvec() const { return (size_t)NVEC + 2 * (size_t)(S > 1 ? S - 1 : 0); }
+  __host__ __device__ size_t floats() const {
+    return 64 /*red*/ + 16 /*mbarriers*/ + 64 /*rdl*/ + (size_t)nT * TF + (size_t)NGRP * GSTG_F + TF + nvec() * TP;
+  }
+};
+
+__host__ __device__ inline int tri(int I, int J) { return I * (I + 1) / 2 + J; }
+
+// ---- mbarrier / bulk-copy (TMA engine) primitives -------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on an mbarrier (16-byte aligned addresses and size)
+__device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global bulk copy (bulk async-group)
+__device__ __forceinline__ void bulk_s2g(float* gdst, const float* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes (st.shared / st.global by threads) ordered before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---- thread group -----------------------------------------------------------------------------------------------------
+struct GCtx {
+  int g, t, ty, tx;     // group, thread within the group, micro-tile coordinates (rows 4ty.., 32+4ty..; cols 4tx.., 32+4tx..)
+  float* stg;           // this group's two stages (GSTG_F floats)
+  uint64_t* bar;        // the two "stage full" barriers
+  unsigned use0, use1;  // fills consumed per stage (phase parity)
+};
+
+// named barrier of one group (ids must be literals: a register id makes ptxas reserve all 16 hardware barriers)
+__device__ __forceinline__ void group_sync(int g) {
+  switch (g) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
+__device__ __forceinline__ void acc_zero(float (&acc)[8][8]) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.0f;
+}
+
+// acc[r][c] += sum_{kk < KC} A[kk][row(r)] * B[kk][col(c)]  (operand rows are 64 floats apart)
+__device__ __forceinline__ void mk_chunk(float (&acc)[8][8], const float* __restrict__ As, const float* __restrict__ Bs, int ty,
+                                         int tx) {
+  const float* ap = As + 4 * ty;
+  const float* bp = Bs + 4 * tx;
+#pragma unroll
+  for (int kk = 0; kk < KC; ++kk) {
+    const float4 a0 = *reinterpret_cast<const float4*>(ap + kk * TS);
+    const float4 a1 = *reinterpret_cast<const float4*>(ap + kk * TS + 32);
+    const float4 b0 = *reinterpret_cast<const float4*>(bp + kk * TS);
+    const float4 b1 = *reinterpret_cast<const float4*>(bp + kk * TS + 32);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) fma2(acc[r][c], acc[r][c + 1], a[r], a[r], b[c], b[c + 1]);
+  }
+}
+
+__device__ __forceinline__ int mrow(int ty, int r) { return 4 * ty + (r & 3) + 32 * (r >> 2); }
+__device__ __forceinline__ int mcol(int tx, int c) { return 4 * tx + (c & 3) + 32 * (c >> 2); }
+
+// tile stores from the micro-kernel's registers.  SGN: +1 / -1.
+template <int SGN>
+__device__ __forceinline__ void store_colmajor(float* __restrict__ dst, const float (&acc)[8][8], int ty, int tx) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float* d = dst + (size_t)mcol(tx, c) * TS + 4 * ty;  // [c][i]: 8 row-threads of a quarter warp -> 128 contiguous bytes
+    *reinterpret_cast<float4*>(d) = make_float4(SGN * acc[0][c], SGN * acc[1][c], SGN * acc[2][c], SGN * acc[3][c]);
+    *reinterpret_cast<float4*>(d + 32) = make_float4(SGN * acc[4][c], SGN * acc[5][c], SGN * acc[6][c], SGN * acc[7][c]);
+  }
+}
+template <int SGN>
+__device__ __forceinline__ void store_rowmajor(float* __restrict__ dst, const float (&acc)[8][8], int ty, int tx) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    float* d = dst + (size_t)mrow(ty, r) * TS + 4 * tx;  // [i][c]
+    *reinterpret_cast<float4*>(d) = make_float4(SGN * acc[r][0], SGN * acc[r][1], SGN * acc[r][2], SGN * acc[r][3]);
+    *reinterpret_cast<float4*>(d + 32) = make_float4(SGN * acc[r][4], SGN * acc[r][5], SGN * acc[r][6], SGN * acc[r][7]);
+  }
+}
+
+// Staged contraction of one job: n chunks; issue(c, stage, bar) is executed by ONE thread of the group and starts the
+// bulk copies of chunk c into `stage` (A chunk at stage, B chunk at stage + CH) after arming `bar` with their byte count.
+// B_RES: the B operand is resident in shared memory, bres(c) returns its chunk.
+template <bool B_RES, class IssueF, class BresF>
+__device__ __forceinline__ void run_chunks(float (&acc)[8][8], GCtx& G, int n, IssueF issue, BresF bres) {
+  if (G.t == 0) {
+    if (n > 0) issue(0, G.stg, &G.bar[0]);
+    if (n > 1) issue(1, G.stg + STAGE_F, &G.bar[1]);
+  }
+  for (int c = 0; c < n; ++c) {
+    const int s = c & 1;
+    if (s) { mbar_wait(&G.bar[1], G.use1 & 1u); ++G.use1; }
+    else { mbar_wait(&G.bar[0], G.use0 & 1u); ++G.use0; }
+    const float* As = G.stg + s * STAGE_F;
+    const float* Bs = B_RES ? bres(c) : As + CH;
+    mk_chunk(acc, As, Bs, G.ty, G.tx);
+    group_sync(G.g);  // both warps are done with stage s
+    if (G.t == 0 && c + 2 < n) issue(c + 2, G.stg + s * STAGE_F, &G.bar[s]);
+  }
+}
+
+// Everything a pair's phases share.
+struct Sm {
+  double* red;
+  uint64_t* bars;
+  float *rdl, *panel, *stg, *linv;
+  float *ts, *mm, *dgq, *v0, *v1, *v2, *v3, *v4, *eps, *zacc;  // v0..v4: direction-specific vectors (see kernels)
+  __device__ Sm(float* base, const TLay& L) {
+    red = reinterpret_cast<double*>(base); base += 64;
+    bars = reinterpret_cast<uint64_t*>(base); base += 16;
+    rdl = base; base += 64;
+    panel = base; base += (size_t)L.nT * TF;
+    stg = base; base += (size_t)NGRP * GSTG_F;
+    linv = base; base += TF;
+    ts = base; base += L.TP;
+    mm = base; base += L.TP;
+    dgq = base; base += L.TP;
+    v0 = base; base += L.TP;
+    v1 = base; base += L.TP;
+    v2 = base; base += L.TP;
+    eps = base; base += (size_t)L.S * L.TP;     // NVEC counts one eps and one zacc/extra vector; S > 1 adds 2 (S-1)
+    zacc = base; base += (size_t)L.S * L.TP;
+    v3 = zacc;  // backward (S == 1): the z accumulator's slot is free
+    v4 = dgq;   // backward: diag L_q is not needed beyond the factorisation's own 64-entry window
+  }
+};
+
+template <int KERNEL>
+struct Pair {
+  int T, nTb, Tact;
+  float noise;
+  KernC<KERNEL> kc;
+  __device__ Pair(int T_, float ell, float sig, float noise_) : T(T_), nTb((T_ + TS - 1) / TS), Tact((T_ + TS - 1) / TS * TS),
+                                                                 noise(noise_), kc(ell, sig) {}
+  // K(i, c..) for four consecutive rows i0..i0+3 at column c (absolute indices); identity beyond the sequence
+  __device__ __forceinline__ float4 kgen4(int c, int i0, const float* __restrict__ ts) const {
+    const float4 t4 = *reinterpret_cast<const float4*>(ts + i0);
+    const float tc = ts[c];
+    const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = i0 + e;
+      const float v = kc.val(tv[e] - tc) + (i == c ? noise : 0.0f);
+      o[e] = (i < T && c < T) ? v : (i == c ? 1.0f : 0.0f);
+    }
+    return make_float4(o[0], o[1], o[2], o[3]);
+  }
+};
+
+// ---- the 64 x 64 diagonal block: Cholesky + inverse in shared memory, all 256 threads ------------------------------------
+// D: the block, column-major (D[c*64 + i], i >= c valid), factored in place.  dgl: diag(L) out (64), rdl: 1/diag(L) out (64).
+// Tl: number of real rows of the block (may exceed 64).  16-column sub-panels: one warp factors the 16 x 16 diagonal block in
+// registers (diag_factor), the rows below are solved one per thread, the trailing columns updated in 4 x 4 tiles.
+__device__ __forceinline__ void factor64(float* __restrict__ D, float* __restrict__ dgl, float* __restrict__ rdl, int Tl, int* bad) {
+  const int tid = threadIdx.x;
+  for (int jl = 0; jl < TS; jl += 16) {
+    if (tid < 32) diag_factor<false>(D, TS, jl, Tl, D + (size_t)jl * TS, TS, dgl, rdl, bad);
+    __syncthreads();
+    const int nbelow = TS - jl - 16;
+    if (tid < nbelow) {
+      const int i = jl + 16 + tid;
+      float b[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) b[c] = D[(size_t)(jl + c) * TS + i];
+      diag_solve16(b, D, TS, jl, rdl);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) D[(size_t)(jl + c) * TS + i] = b[c];
+    }
+    __syncthreads();
+    const int nt4 = nbelow >> 2;
+    for (int id = tid; id < nt4 * nt4; id += NTHR) {
+      const int rt = id / nt4, ct = id - rt * nt4;
+      if (rt < ct) continue;
+      const int rb = jl + 16 + 4 * rt, cb = jl + 16 + 4 * ct;
+      float acc[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 a4 = *reinterpret_cast<const float4*>(D + (size_t)(cb + c) * TS + rb);
+        acc[0][c] = a4.x; acc[1][c] = a4.y; acc[2][c] = a4.z; acc[3][c] = a4.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 u4 = *reinterpret_cast<const float4*>(D + (size_t)(jl + k) * TS + rb);
+        const float4 v4 = *reinterpret_cast<const float4*>(D + (size_t)(jl + k) * TS + cb);
+        const float u[4] = {u4.x, u4.y, u4.z, u4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(-u[r], v[c], acc[r][c]);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(D + (size_t)(cb + c) * TS + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+    }
+    __syncthreads();
+  }
+}
+
+// Inverse of the factored block.  D as above (L column-major), rdl = 1/diag(L).  Output LT[c'][c] = Linv[c][c'] (the
+// contraction-major operand of both uses: rows-below = raw Linv^T and X = Linv Y), zeros where c < c'; optionally also
+// Lrm[r][c] = Linv[r][c] row-major with zeros above the diagonal (the diagonal X tile).  tmp: >= 1024 floats of scratch.
+__device__ __forceinline__ void invert64(const float* __restrict__ D, const float* __restrict__ rdl, float* __restrict__ LT,
+                                         float* __restrict__ Lrm, float* __restrict__ tmp) {
+  const int tid = threadIdx.x;
+  for (int e = tid * 4; e < TF; e += NTHR * 4) {
+    *reinterpret_cast<float4*>(LT + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (Lrm) *reinterpret_cast<float4*>(Lrm + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+  __syncthreads();
+  for (int P = 0; P < 4; ++P) {
+    const int p0 = 16 * P, ncol = p0 + 16;
+    // right-hand side of block row P: R[r][col] = [p0 + r == col] - sum_{k = col}^{p0-1} L[p0+r][k] Linv[k][col]
+    for (int id = tid; id < 16 * ncol; id += NTHR) {
+      const int r = id & 15, col = id >> 4;
+      float acc = (p0 + r == col) ? 1.0f : 0.0f;
+      for (int k = col; k < p0; ++k) acc = fmaf(-D[(size_t)k * TS + p0 + r], LT[(size_t)col * TS + k], acc);
+      tmp[col * 16 + r] = acc;
+    }
+    __syncthreads();
+    if (tid < ncol) {
+      const int col = tid;
+      float b[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) b[r] = tmp[col * 16 + r];
+      diag_solve16(b, D, TS, p0, rdl);
+#pragma unroll
+      for (int r = 0; r < 16; r += 4)
+        *reinterpret_cast<float4*>(LT + (size_t)col * TS + p0 + r) = make_float4(b[r], b[r + 1], b[r + 2], b[r + 3]);
+      if (Lrm) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) Lrm[(size_t)(p0 + r) * TS + col] = b[r];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- the factorisation of K_q by 64-column panels -------------------------------------------------------------------------
+// Lg: this CTA's tile-packed triangle in global memory (L tiles column-major).  After panel J: panel tiles I >= J hold the
+// finished columns of the panel ROW-major (zeros above the diagonal), LinvT = L_JJ^-T operand, dgq[64J..] = diag.  hook(J)
+// runs with the panel in place (all threads; it must end with every thread past its last panel read before returning
+// -- the loop issues the CTA barrier).
+template <int KERNEL, class HookF>
+__device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* __restrict__ Lg, Sm& s, GCtx& G, int* bad,
+                                                 HookF hook) {
+  const int tid = threadIdx.x;
+  const int nTb = pr.nTb;
+  for (int J = 0; J < nTb; ++J) {
+    const int m = nTb - J;  // tiles I = J .. nTb-1 of this panel
+    // ---- (1) raw panel, column-major per tile: K(I,J) - sum_{K<J} L(I,K) L(J,K)^T ------------------------------------
+    if (J == 0) {
+      for (int ti = 0; ti < m; ++ti) {
+        float* dst = s.panel + (size_t)ti * TF;
+        for (int e = tid * 4; e < TF; e += NTHR * 4) {
+          const int c = e >> 6, i = e & 63;
+          *reinterpret_cast<float4*>(dst + e) = pr.kgen4(c, TS * ti + i, s.ts);
+        }
+      }
+      __syncthreads();
+    } else {
+      const int nch = 4 * J;  // chunks per tile
+      // split every tile's contraction over sp groups (1, 2 or 4): the split that needs the fewest chunk-times
+      int sp = 1, best = ((m + 3) / 4) * nch;
+      { const int c2 = ((2 * m + 3) / 4) * (nch / 2); if (c2 < best) { best = c2; sp = 2; } }
+      { const int c4 = m * (nch / 4); if (c4 < best) { best = c4; sp = 4; } }
+      const int per = nch / sp, tpr = NGRP / sp;  // chunks per job, tiles per round
+      const int rounds = (m + tpr - 1) / tpr;
+      for (int rd = 0; rd < rounds; ++rd) {
+        const int ti = rd * tpr + G.g / sp, part = G.g % sp;
+        float acc[8][8];
+        acc_zero(acc);
+        if (ti < m) {
+          const int I = J + ti, c0 = part * per;
+          const float* Arow = Lg + (size_t)tri(I, 0) * TF;
+          const float* Brow = Lg + (size_t)tri(J, 0) * TF;
+          run_chunks<false>(acc, G, per,
+                            [&](int c, float* st, uint64_t* bar) {
+                              const size_t off = (size_t)(c0 + c) * CH;  // chunk (K, q) of a row of tiles is contiguous
+                              mbar_expect_tx(bar, 2 * CH * 4);
+                              bulk_g2s(st, Arow + off, CH * 4, bar);
+                              bulk_g2s(st + CH, Brow + off, CH * 4, bar);
+                            },
+                            [](int) { return (const float*)nullptr; });
+        }
+        // the job's partial tile into the group's own stage area (all its copies have landed and been consumed)
+        store_colmajor<1>(G.stg, acc, G.ty, G.tx);
+        __syncthreads();
+        for (int q = 0; q < tpr; ++q) {
+          const int tq = rd * tpr + q;
+          if (tq >= m) break;
+          float* dst = s.panel + (size_t)(J + tq) * TF;
+          const float* src = s.stg + (size_t)(q * sp) * GSTG_F;
+          for (int e = tid * 4; e < TF; e += NTHR * 4) {
+            const int c = e >> 6, i = e & 63;
+            float4 kv = pr.kgen4(TS * J + c, TS * (J + tq) + i, s.ts);
+            for (int p = 0; p < sp; ++p) {
+              const float4 pv = *reinterpret_cast<const float4*>(src + (size_t)p * GSTG_F + e);
+              kv.x -= pv.x; kv.y -= pv.y; kv.z -= pv.z; kv.w -= pv.w;
+            }
+            *reinterpret_cast<float4*>(dst + e) = kv;
+          }
+        }
+        fence_async();  // the stage areas were written by threads; the next job's bulk copies overwrite them
+        __syncthreads();
+      }
+    }
+    // ---- (2) diagonal block: factor in place (column-major), invert, publish -------------------------------------------
+    float* D = s.panel + (size_t)J * TF;
+    factor64(D, s.dgq + TS * J, s.rdl, pr.T - TS * J, bad);
+    invert64(D, s.rdl, s.linv, nullptr, s.stg);
+    {
+      float* gt = Lg + (size_t)tri(J, J) * TF;
+      float* tmp = s.stg;  // one tile of scratch: the transposed copy, XOR-swizzled so that both passes are conflict-free
+      for (int e = tid * 4; e < TF; e += NTHR * 4) {
+        const int c = e >> 6, i = e & 63;
+        const float4 d4 = *reinterpret_cast<const float4*>(D + e);
+        const float o[4] = {i >= c ? d4.x : 0.0f, i + 1 >= c ? d4.y : 0.0f, i + 2 >= c ? d4.z : 0.0f, i + 3 >= c ? d4.w : 0.0f};
+        *reinterpret_cast<float4*>(gt + e) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      for (int e = tid; e < TF; e += NTHR) {
+        const int c = e >> 6, i = e & 63;
+        tmp[i * TS + (c ^ (i & 31))] = (i >= c) ? D[e] : 0.0f;
+      }
+      __syncthreads();
+      for (int e = tid; e < TF; e += NTHR) {
+        const int i = e >> 6, c = e & 63;
+        D[e] = tmp[i * TS + (c ^ (i & 31))];
+      }
+      __syncthreads();
+    }
+    // ---- (3) rows below: L(I,J) = raw(I,J) L_JJ^-T, one tile per group job, operands resident --------------------------
+    for (int rd = 0; rd * NGRP < m - 1; ++rd) {
+      const int ti = 1 + rd * NGRP + G.g;
+      if (ti < m) {
+        float* tile = s.panel + (size_t)(J + ti) * TF;
+        float acc[8][8];
+        acc_zero(acc);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) mk_chunk(acc, tile + q * CH, s.linv + q * CH, G.ty, G.tx);
+        store_colmajor<1>(Lg + (size_t)tri(J + ti, J) * TF, acc, G.ty, G.tx);
+        group_sync(G.g);  // both warps have read the raw tile
+        store_rowmajor<1>(tile, acc, G.ty, G.tx);
+      }
+    }
+    fence_async();  // the L tiles written above are read by bulk copies from the next panel on
+    __syncthreads();
+    // ---- (4) per-panel consumers of the finished panel -----------------------------------------------------------------
+    hook(J);
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void load_vectors(const Params& P, int p, int b, int dd, int T, long long r0, const TLay& L, Sm& s,
+                                             bool backward) {
+  const GpklDesc& d = P.d;
+  const int S = d.S, TP = L.TP;
+  for (int i = threadIdx.x; i < TP; i += NTHR) {
+    s.ts[i] = (i < T) ? P.times[(size_t)b * d.T_max + i] : 0.0f;
+    s.mm[i] = (i < T) ? P.mean[(size_t)(r0 + i) * d.D + dd] : 0.0f;
+    for (int sx = 0; sx < S; ++sx) {
+      s.eps[(size_t)sx * TP + i] = (i < T) ? P.eps[((size_t)p * S + sx) * d.T_max + i] : 0.0f;
+      if (!backward) s.zacc[(size_t)sx * TP + i] = s.mm[i];
+    }
+    if (backward) {  // S == 1
+      s.v0[i] = (i < T && P.g_z) ? P.g_z[((size_t)r0 + i) * d.D + dd] : 0.0f;  // u = g_z
+      s.v3[i] = 0.0f;                                                         // running column sums of C'
+    }
+  }
+}
+
+// ---- forward ---------------------------------------------------------------------------------------------------------------
+template <int KERNEL>
+__global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ int bad;
+  if (*P.prior_flag == 0) return;  // ell_p differs between latent dims: the per-pair kernel launched behind this one serves
+  const GpklDesc& d = P.d;
+  const TLay L(d.T_max, d.S);
+  Sm s(smem_f, L);
+  const int tid = threadIdx.x;
+  GCtx G;
+  G.g = tid >> 6; G.t = tid & 63;
+  { const int lane = tid & 31, w = (tid >> 5) & 1; G.ty = lane & 7; G.tx = (lane >> 3) + 4 * w; }
+  G.stg = s.stg + (size_t)G.g * GSTG_F;
+  G.bar = s.bars + 2 * G.g;
+  G.use0 = G.use1 = 0;
+  if (tid == 0) {
+    for (int i = 0; i < 2 * NGRP; ++i) mbar_init(&s.bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int S = d.S, TP = L.TP;
+  const float noise = d.noise, sig = (float)(1.0 - (double)noise);
+  const int ldr = TP + 4;  // row pitch of the block tier's prior records
+  float* Lg = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
+  float* dgp = s.v0;
+  float* aa = s.v1;
+  for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
+    const int b = p / d.D, dd = p - b * d.D;
+    const int T = P.lengths[b];
+    const long long r0 = P.offsets[b];
+    __syncthreads();
+    if (T <= 0) {
+      if (tid == 0) {
+        P.kl_pairs[p] = 0.0f;
+        if (P.logdets) { P.logdets[2 * p] = 0.0f; P.logdets[2 * p + 1] = 0.0f; }
+      }
+      continue;
+    }
+    if (tid == 0) bad = 0;
+    load_vectors(P, p, b, dd, T, r0, L, s, false);
+    const float* __restrict__ rec = P.prior + (size_t)b * P.prior_stride;
+    for (int i = tid; i < TP; i += NTHR) dgp[i] = __ldg(rec + (size_t)TP * ldr + i);
+    __syncthreads();
+    const Pair<KERNEL> pr(T, P.ell_q[dd], sig, noise);
+    const int nTb = pr.nTb;
+    // a = L_p^-1 m from the record (X_p column-major, X(i,k) at rec[k*ldr + i]; coalesced over i)
+    for (int i = tid; i < T; i += NTHR) {
+      float a0 = 0.0f, a1 = 0.0f;
+      int k = 0;
+      for (; k + 8 <= i + 1; k += 8) {
+        float xv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xv[e] = __ldg(rec + (size_t)(k + e) * ldr + i);
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) { a0 = fmaf(xv[e], s.mm[k + e], a0); a1 = fmaf(xv[e + 1], s.mm[k + e + 1], a1); }
+      }
+      for (; k <= i; ++k) a0 = fmaf(__ldg(rec + (size_t)k * ldr + i), s.mm[k], a0);
+      aa[i] = a0 + a1;
+    }
+    float ssq = 0.0f;
+    chol_panels_tile<KERNEL>(pr, Lg, s, G, &bad, [&](int J) {
+      const int m = nTb - J;
+      // z_s += L_q(:, panel J) eps_s(panel J): one row per thread, 128-bit row reads started at a lane-dependent column
+      for (int idx = tid; idx < m * TS; idx += NTHR) {
+        const float* row = s.panel + (size_t)J * TF + (size_t)idx * TS;  // tiles are contiguous: row idx of the panel
+        for (int sx = 0; sx < S; ++sx) {
+          const float* ev = s.eps + (size_t)sx * TP + TS * J;
+          float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int cc = ((j + idx) & 15) * 4;
+            const float4 l4 = *reinterpret_cast<const float4*>(row + cc);
+            const float4 e4 = *reinterpret_cast<const float4*>(ev + cc);
+            a0 = fmaf(l4.x, e4.x, a0); a1 = fmaf(l4.y, e4.y, a1); a0 = fmaf(l4.z, e4.z, a0); a1 = fmaf(l4.w, e4.w, a1);
+          }
+          s.zacc[(size_t)sx * TP + TS * J + idx] += a0 + a1;
+        }
+      }
+      // A(I,J) = sum_{K=J..I} X_p(I,K) L_q(K,J): tiles by decreasing length, dealt boustrophedon to the groups
+      for (int blk = 0; blk * NGRP < m; ++blk) {
+        const int idx = blk * NGRP + ((blk & 1) ? NGRP - 1 - G.g : G.g);
+        if (idx >= m) continue;
+        const int I = nTb - 1 - idx;
+        float acc[8][8];
+        acc_zero(acc);
+        const float* Abase = rec + (size_t)TS * I;
+        run_chunks<true>(acc, G, 4 * (I - J + 1),
+                         [&](int c, float* st, uint64_t* bar) {
+                           const float* src = Abase + (size_t)(TS * J + KC * c) * ldr;  // rows k of X_p^T, 64 entries each
+                           mbar_expect_tx(bar, CH * 4);
+#pragma unroll
+                           for (int kk = 0; kk < KC; ++kk) bulk_g2s(st + kk * TS, src + (size_t)kk * ldr, TS * 4, bar);
+                         },
+                         [&](int c) { return (const float*)(s.panel + (size_t)J * TF + (size_t)c * CH); });
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int i = TS * I + mrow(G.ty, r), cc = TS * J + mcol(G.tx, c);
+            const float v = (cc < i && i < T) ? acc[r][c] : 0.0f;
+            ssq = fmaf(v, v, ssq);
+          }
+      }
+    });
+    // ---- z out, KL ----------------------------------------------------------------------------------------------------
+    for (int i = tid; i < T; i += NTHR)
+      for (int sx = 0; sx < S; ++sx) P.z[((size_t)S * r0 + (size_t)sx * T + i) * d.D + dd] = s.zacc[(size_t)sx * TP + i];
+    double part = (double)ssq, ldp = 0.0, ldq = 0.0;
+    for (int i = tid; i < T; i += NTHR) {
+      const double lpd = (double)dgp[i], lqd = (double)s.dgq[i];
+      const double av = (double)aa[i];
+      part += diag_term(lqd / lpd) + av * av;
+      if (P.logdets) {
+        ldp += 2.0 * log(lpd);
+        ldq += 2.0 * log(lqd);
+      }
+    }
+    part = block_sum(part, s.red);
+    if (P.logdets) {
+      ldp = block_sum(ldp, s.red);
+      ldq = block_sum(ldq, s.red);
+    }
+    if (tid == 0) {
+      P.kl_pairs[p] = (float)(0.5 * part);
+      if (P.logdets) { P.logdets[2 * p] = (float)ldp; P.logdets[2 * p + 1] = (float)ldq; }
+      if (bad && P.status) atomicAdd(P.status, 1);
+    }
+  }
+}
+
+// ---- backward (S == 1) --------------------------------------------------------------------------------------------------------
+template <int KERNEL>
+__global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ int bad;
+  if (*P.prior_flag == 0) return;
+  const GpklDesc& d = P.d;
+  const TLay L(d.T_max, d.S);
+  Sm s(smem_f, L);
+  const int tid = threadIdx.x;
+  GCtx G;
+  G.g = tid >> 6; G.t = tid & 63;
+  { const int lane = tid & 31, w = (tid >> 5) & 1; G.ty = lane & 7; G.tx = (lane >> 3) + 4 * w; }
+  G.stg = s.stg + (size_t)G.g * GSTG_F;
+  G.bar = s.bars + 2 * G.g;
+  G.use0 = G.use1 = 0;
+  if (tid == 0) {
+    for (int i = 0; i < 2 * NGRP; ++i) mbar_init(&s.bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int TP = L.TP;
+  const float noise = d.noise, sig = (float)(1.0 - (double)noise);
+  const int ldr = TP + 4;
+  const double g_sum = P.g_kl_sum ? *P.g_kl_sum : 1.0;
+  float* Lg = P.scratch + (size_t)blockIdx.x * P.scratch_stride;  // L tiles, overwritten in place by X tiles
+  float* Cg = Lg + (size_t)L.ntri() * TF;                         // C' tiles
+  float* u = s.v0;    // g_z
+  float* w = s.v1;    // L_q^T g_z
+  float* pd = s.v2;   // 1/2 w eps - g/2
+  float* cum = s.v3;  // running column sums  sum_{j < i} eps_j X(j, l)
+  float* rdq = s.v4;  // 1 / diag L_q (whole sequence)
+  for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
+    const int b = p / d.D, dd = p - b * d.D;
+    const int T = P.lengths[b];
+    const long long r0 = P.offsets[b];
+    __syncthreads();
+    if (T <= 0) {
+      if (tid == 0 && P.gq_pairs) P.gq_pairs[p] = 0.0f;
+      continue;
+    }
+    const float g = (float)(g_sum + (P.g_kl_pairs ? (double)P.g_kl_pairs[p] : 0.0));
+    const float hg = 0.5f * g;
+    if (tid == 0) bad = 0;
+    load_vectors(P, p, b, dd, T, r0, L, s, true);
+    __syncthreads();
+    const float lq = P.ell_q[dd];
+    const Pair<KERNEL> pr(T, lq, sig, noise);
+    const int nTb = pr.nTb;
+    chol_panels_tile<KERNEL>(pr, Lg, s, G, &bad, [&](int J) {
+      const int m = nTb - J;
+      // w(panel J) = L_q(:, panel J)^T g_z: four row-interleaved partial sums per column, summed in a fixed order
+      {
+        const int c = tid & 63, part = tid >> 6;
+        const float* col = s.panel + (size_t)J * TF + c;
+        float acc = 0.0f;
+        for (int idx = part; idx < m * TS; idx += 4) acc = fmaf(col[(size_t)idx * TS], u[TS * J + idx], acc);
+        s.linv[part * TS + c] = acc;  // (L_JJ^-T is dead once the rows below exist)
+      }
+      if (tid < TS) rdq[TS * J + tid] = s.rdl[tid];
+      __syncthreads();
+      if (tid < TS) {
+        const float wk = (s.linv[tid] + s.linv[TS + tid]) + (s.linv[2 * TS + tid] + s.linv[3 * TS + tid]);
+        w[TS * J + tid] = wk;
+        pd[TS * J + tid] = 0.5f * wk * s.eps[TS * J + tid] - hg;
+      }
+    });
+    // ---- X_q = L_q^-1 in place, 64-row blocks; C' alongside ----------------------------------------------------------------
+    for (int I = 0; I < nTb; ++I) {
+      // L_II (column-major tile) -> shared memory, L_II^-1 as operand (linv) and as the diagonal X tile (panel tile I)
+      float* Dt = s.stg;                // group 0's stage area as the tile, group 1's as invert64's scratch
+      {
+        const float* src = Lg + (size_t)tri(I, I) * TF;
+        for (int e = tid * 4; e < TF; e += NTHR * 4) *reinterpret_cast<float4*>(Dt + e) = __ldcg(reinterpret_cast<const float4*>(src + e));
+        if (tid < TS) s.rdl[tid] = rdq[TS * I + tid];
+      }
+      if (tid == 0) bulk_wait_read0();  // the bulk stores of the previous row block have finished reading the panel
+      __syncthreads();
+      invert64(Dt, s.rdl, s.linv, s.panel + (size_t)I * TF, s.stg + GSTG_F);
+      fence_async();                     // stage areas were used as scratch by threads
+      __syncthreads();
+      // off-diagonal tiles C < I:  Y = -sum_{K=C}^{I-1} L(I,K) X(K,C),  X(I,C) = L_II^-1 Y   (longest first: C ascending)
+      for (int blk = 0; blk * NGRP < I; ++blk) {
+        const int C = blk * NGRP + ((blk & 1) ? NGRP - 1 - G.g : G.g);
+        if (C >= I) continue;
+        float acc[8][8];
+        acc_zero(acc);
+        const float* Arow = Lg + (size_t)tri(I, C) * TF;  // L(I,C), L(I,C+1), ... are consecutive tiles
+        run_chunks<false>(acc, G, 4 * (I - C),
+                          [&](int c, float* st, uint64_t* bar) {
+                            const int K = C + (c >> 2), q = c & 3;
+                            mbar_expect_tx(bar, 2 * CH * 4);
+                            bulk_g2s(st, Arow + (size_t)c * CH, CH * 4, bar);
+                            bulk_g2s(st + CH, Lg + (size_t)tri(K, C) * TF + (size_t)q * CH, CH * 4, bar);
+                          },
+                          [](int) { return (const float*)nullptr; });
+        float* Y = s.panel + (size_t)C * TF;
+        store_rowmajor<-1>(Y, acc, G.ty, G.tx);
+        group_sync(G.g);
+        acc_zero(acc);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) mk_chunk(acc, s.linv + q * CH, Y + q * CH, G.ty, G.tx);
+        group_sync(G.g);  // both warps have read Y
+        store_rowmajor<1>(Y, acc, G.ty, G.tx);
+      }
+      fence_async();  // panel tiles (X row block I) are read by the bulk stores below
+      __syncthreads();
+      if (tid == 0) {  // X(I, 0..I) -> global, in place of L(I, 0..I) (every read of that row of L tiles is complete)
+        bulk_s2g(Lg + (size_t)tri(I, 0) * TF, s.panel, (unsigned)((I + 1) * TF * 4));
+        bulk_commit();
+      }
+      // C'(i,l) = w_i sum_{j<i} eps_j X(j,l) + pd_i X(i,l) down every column l <= 64 I + 63, straight to global (coalesced over l)
+      for (int l = tid; l < TS * (I + 1); l += NTHR) {
+        const int Cb = l >> 6, lc = l & 63;
+        const float* xs = s.panel + (size_t)Cb * TF + lc;
+        float* cg = Cg + (size_t)tri(I, Cb) * TF + lc;
+        float cm = cum[l];
+#pragma unroll 8
+        for (int r = 0; r < TS; ++r) {
+          const int i = TS * I + r;
+          const float x = xs[r * TS];
+          cg[r * TS] = fmaf(w[i], cm, pd[i] * x);
+          cm = fmaf(s.eps[i], x, cm);
+        }
+        cum[l] = cm;
+      }
+      fence_async();  // C' tiles (thread stores) are read by bulk copies in the contraction
+      __syncthreads();
+    }
+    if (tid == 0) bulk_wait0();  // X tiles are in global memory
+    __syncthreads();
+    // ---- d/d mean: alpha = K_p^-1 m from the record (symmetric: coalesced over k) -------------------------------------------
+    const float* __restrict__ kinv = P.prior + (size_t)b * P.prior_stride;
+    for (int k = tid; k < T; k += NTHR) {
+      float a0 = 0.0f, a1 = 0.0f;
+      int l = 0;
+      for (; l + 8 <= T; l += 8) {
+        float xv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xv[e] = __ldg(kinv + (size_t)(l + e) * ldr + k);
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) { a0 = fmaf(xv[e], s.mm[l + e], a0); a1 = fmaf(xv[e + 1], s.mm[l + e + 1], a1); }
+      }
+      for (; l < T; ++l) a0 = fmaf(__ldg(kinv + (size_t)l * ldr + k), s.mm[l], a0);
+      P.g_mean[(size_t)(r0 + k) * d.D + dd] = g * (a0 + a1) + u[k];
+    }
+    // ---- contraction: sum_{k != l} dK_kl (hg K_p^-1 + X_q^T C')_kl, tiles by shell max(kt,lt) (longest first), boustrophedon --
+    double total = 0.0;
+    for (int blk = 0; blk * NGRP < nTb * nTb; ++blk) {
+      const int n = blk * NGRP + ((blk & 1) ? NGRP - 1 - G.g : G.g);
+      if (n >= nTb * nTb) continue;
+      int mx = (int)sqrtf((float)n);
+      while ((mx + 1) * (mx + 1) <= n) ++mx;
+      while (mx * mx > n) --mx;
+      const int pos = n - mx * mx;
+      const int kt = pos <= mx ? mx : pos - mx - 1, lt = pos <= mx ? pos : mx;
+      float acc[8][8];
+      acc_zero(acc);
+      run_chunks<false>(acc, G, 4 * (nTb - mx),
+                        [&](int c, float* st, uint64_t* bar) {
+                          const int Ib = mx + (c >> 2), q = c & 3;
+                          mbar_expect_tx(bar, 2 * CH * 4);
+                          bulk_g2s(st, Lg + (size_t)tri(Ib, kt) * TF + (size_t)q * CH, CH * 4, bar);
+                          bulk_g2s(st + CH, Cg + (size_t)tri(Ib, lt) * TF + (size_t)q * CH, CH * 4, bar);
+                        },
+                        [](int) { return (const float*)nullptr; });
+      float4 kq[8][2];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int k = TS * kt + mrow(G.ty, r), l0 = TS * lt + 4 * G.tx;
+        kq[r][0] = __ldg(reinterpret_cast<const float4*>(kinv + (size_t)k * ldr + l0));
+        kq[r][1] = __ldg(reinterpret_cast<const float4*>(kinv + (size_t)k * ldr + l0 + 32));
+      }
+      float tl[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) tl[c] = s.ts[TS * lt + mcol(G.tx, c)];
+      float part = 0.0f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int k = TS * kt + mrow(G.ty, r);
+        const float tk = s.ts[k];
+        const float kv[8] = {kq[r][0].x, kq[r][0].y, kq[r][0].z, kq[r][0].w, kq[r][1].x, kq[r][1].y, kq[r][1].z, kq[r][1].w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int l = TS * lt + mcol(G.tx, c);
+          const float dt = tk - tl[c];
+          const float dk = pr.kc.dell(dt, pr.kc.val_fast(dt));
+          const float wv = fmaf(hg, kv[c], acc[r][c]);
+          part = fmaf((k < T && l < T && k != l) ? wv : 0.0f, dk, part);
+        }
+      }
+      total += (double)part;
+    }
+    const double gq = block_sum(total, s.red);
+    if (tid == 0) {
+      P.gq_pairs[p] = (float)gq;
+      if (bad && P.status) atomicAdd(P.status, 1);
+    }
+  }
+}
+
+size_t tile_smem_bytes(const GpklDesc& d) { return TLay(d.T_max, d.S).floats() * sizeof(float); }
+
+}  // namespace
+
+bool tile_tier_supports(const GpklDesc& d, bool backward) {
+  static const bool off = [] { const char* e = getenv("GPKL_TILE"); return e && e[0] == '0'; }();
+  if (off) return false;
+  if (d.posterior != GPKL_POST_GP || d.T_max <= 208 || d.T_max > 512) return false;
+  if (backward && d.S != 1) return false;
+  return tile_smem_bytes(d) <= kMaxDynSmem;
+}
+
+size_t tile_slot_floats(const GpklDesc& d) {
+  const TLay L(d.T_max, d.S);
+  return 2 * (size_t)L.ntri() * TF;
+}
+
+// The shared-prior kernel of the tile tier; the caller has launched the block tier's pre-pass (records in P.prior) before
+// it and launches the per-pair kernel (skip_if_shared) behind it.
+cudaError_t launch_tile(const Params& P, bool backward, cudaStream_t st) {
+  const size_t smem = tile_smem_bytes(P.d);
+  const int npairs = P.d.B * P.d.D;
+  const int grid = npairs < kNumSMs ? npairs : kNumSMs;
+  void (*kern)(Params);
+  if (P.d.kernel == GPKL_KERNEL_RBF) kern = backward ? bwd_tile<GPKL_KERNEL_RBF> : fwd_tile<GPKL_KERNEL_RBF>;
+  else kern = backward ? bwd_tile<GPKL_KERNEL_CAUCHY> : fwd_tile<GPKL_KERNEL_CAUCHY>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, NTHR, smem, st>>>(P);
+  note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace gpkl
