@@ -187,13 +187,245 @@ def run_reference(args, w, rank, world):
     }))
 
 
+def verbatim_reference_timing():
+    """the UNMODIFIED reference timed under the TF1 stub at its own configuration (B=5, D=100, T=20).
+    The reference cannot travel to the GPU box, so the record was measured in the dev container by the committed
+    oracle/time_verbatim.py; the float64 port is timed here on the same configuration for scale."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_verbatim_reference_cpu.json")))
+    except Exception:
+        return None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import gp_kl_oracle as orc
+        case = orc.synthetic_batch(5, 100, 20, 1, ragged=False, seed=1234, grid=True)
+        a = (case["mean"], case["times"], case["lengths"], case["ell_q"], case["ell_p"], case["eps"], case["g_z"])
+        orc.gp_prior_kl_grads(*a)
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            orc.gp_prior_kl_grads(*a)
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        rec["oracle_port_same_config_this_box"] = {"value": 5 / ts[2], "unit": "sequences/s", "cores": os.cpu_count() or 1}
+    except Exception:
+        pass
+    return rec
+
+
+def measure_device(gpkl, L, w, dev, steps, warmup, cfg, *, world=1, flush=None, grad_ell_p=False, use_graph=False):
+    """Device-resident fwd+bwd steps of one workload: CUDA events per step on the launch stream, L2 flushed between timed
+    steps (outside the events), async all-reduce of the lengthscale-gradient bucket at N>1 (waited two steps later and
+    drained inside the timed region).  use_graph: the step's launches are captured once and replayed (launch-bound sizes).
+    Returns per-rank totals; the caller takes the max over ranks."""
+    import ctypes
+    import torch.distributed as dist
+    from gpkl.parallel import GradBucket
+    T, D, B = w["T"], w["D"], w["B"]
+    rank = int(os.environ.get("RANK", "0"))
+    case = make_case(w, 1234 + rank)
+    c = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
+    buckets = [GradBucket(D, dev), GradBucket(D, dev)]
+    pending = [None, None]
+    one = torch.ones((), dtype=torch.float64, device=dev)
+    g_mean = torch.empty_like(c["mean"])
+    step_no = [0]
+
+    def compute(bk):
+        f = gpkl.gp_prior_kl_forward(c["mean"], c["times"], c["lengths"], c["ell_q"], c["ell_p"], c["eps"], **cfg)
+        out = bk.out_views()
+        out["g_mean"] = g_mean
+        gpkl.gp_prior_kl_backward(c["mean"], c["times"], c["lengths"], c["ell_q"], c["ell_p"], c["eps"], c["g_z"],
+                                  one, None, grad_ell_p=grad_ell_p, out=out, **cfg)
+        bk.kl.copy_(f["kl_sum"].to(torch.float32).reshape(1))
+
+    graphs = [None, None]
+    if use_graph:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for k in (0, 1):
+                compute(buckets[k])  # warms the workspace cache of the capture stream
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        for k in (0, 1):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                compute(buckets[k])
+            graphs[k] = g
+
+    def step():
+        k = step_no[0] & 1
+        step_no[0] += 1
+        if pending[k] is not None:
+            pending[k].wait()  # the reduction that last used this bucket is done (stream-level wait)
+            pending[k] = None
+        if use_graph:
+            graphs[k].replay()
+        else:
+            compute(buckets[k])
+        pending[k] = buckets[k].all_reduce(async_op=True)
+
+    def drain():
+        for k in (0, 1):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+        if flush is not None:
+            flush.zero_()
+    drain()
+    L.gpkl_profile_enable(0 if use_graph else 1)
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = L.gpkl_launch_count()
+    sampler.sample()
+    sampler.start()
+    evs = []
+    for _ in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+        if flush is not None:
+            flush.zero_()  # evict the step's data from L2 between timed iterations (outside the events)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    drain()  # the last all-reduces finish inside the timed region
+    e1.record()
+    evs.append((e0, e1))
+    barrier()
+    sampler.stop_flag = True
+    sampler.sample()
+    per_step_launches = None
+    lib_launches = L.gpkl_launch_count() - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    fwd_ms, bwd_ms = ctypes.c_double(0), ctypes.c_double(0)
+    nf, nb = ctypes.c_int32(0), ctypes.c_int32(0)
+    L.gpkl_profile_read(ctypes.byref(fwd_ms), ctypes.byref(nf), ctypes.byref(bwd_ms), ctypes.byref(nb))
+    L.gpkl_profile_enable(0)
+    return {"total_ms": total_ms, "fwd_ms": fwd_ms.value / max(nf.value, 1), "bwd_ms": bwd_ms.value / max(nb.value, 1),
+            "lib_launches": int(lib_launches), "clocks": sampler.result(), "case": case, "dev_case": c}
+
+
+def roofline_block(w, B, fwd_ms, bwd_ms, peak, shared_prior, step_ms, hbm_peak, hbm_src, traffic):
+    T, D = w["T"], w["D"]
+    npairs = B * D
+    f_fwd, f_bwd = model_flops_pair(T)
+    x_fwd, x_bwd = executed_flops(T, B, D, shared_prior)
+    ach_bwd = x_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0
+    ach_fwd = x_fwd / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0
+    mod_bwd = npairs * f_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0
+    mod_fwd = npairs * f_fwd / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0
+    return {
+        "bound": "fp32", "kernel": "backward (Cholesky / inverse / contraction adjoints)", "achieved": ach_bwd, "peak": peak,
+        "unit": "TFLOP/s", "frac": ach_bwd / peak if peak > 0 else None, "traffic": traffic,
+        "peak_source": "FFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry; "
+                       "nominal 148x128x2x1.965GHz = 74.4)",
+        "algorithmic": ("shared prior: %d pairs x 4/3 T^3 + %d sequences x T^3 flops" % (npairs, B)) if shared_prior
+                       else "%d pairs x 2*T^3 flops" % npairs,
+        "model_frac": mod_bwd / peak if peak > 0 else None, "shared_prior": bool(shared_prior),
+        "launch_ms": bwd_ms,
+        "fwd_bwd_frac": (x_fwd + x_bwd) / ((fwd_ms + bwd_ms) * 1e-3) / 1e12 / peak if peak > 0 and fwd_ms + bwd_ms > 0 else None,
+        "hbm_frac": npairs * algo_bytes_pair(T) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / hbm_peak if fwd_ms + bwd_ms > 0 else None,
+        "hbm_peak_source": hbm_src,
+        "forward": {"achieved": ach_fwd, "frac": ach_fwd / peak if peak > 0 else None,
+                    "model_frac": mod_fwd / peak if peak > 0 else None, "launch_ms": fwd_ms,
+                    "algorithmic": ("shared prior: %d pairs x 2/3 T^3 + %d sequences x 2/3 T^3 flops" % (npairs, B))
+                                   if shared_prior else "%d pairs x T^3 flops" % npairs},
+        "kernel_share_of_step": (fwd_ms + bwd_ms) / step_ms if step_ms > 0 else None,
+    }
+
+
+def elbo_step_bench(gpkl, w, dev, world, steps=3, warmup=2):
+    """The metric BASELINE.json names: one full ELBO forward+backward+Adam step.  Stock torch.nn encoder / decoder (out of
+    scope for kernels, SURVEY.md S2: per-time-step MLPs 35 -> 128 -> D and D -> 128 -> 35, the shape of the reference's
+    dense nets, Full_GP_VAE_dynamic_time.py:27-58, :262-292) around the fused GP-prior op and the reconstruction / loss op
+    (:349-360), Adam(2e-4) (:361); at N>1 every parameter gradient plus the lengthscale gradients are summed with one
+    NCCL all-reduce per step.  Returns seq/s (whole job) and the share of the step spent in the GP-prior kernels."""
+    import ctypes
+    import torch.distributed as dist
+    L = gpkl._lib.lib()
+    T, D, B = w["T"], w["D"], w["B"]
+    F = 35
+    rank = int(os.environ.get("RANK", "0"))
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    case = make_case(w, 1234 + rank)
+    times, lengths = case["times"].to(dev), case["lengths"].to(dev)
+    total_T = int(case["lengths"].sum())
+    x = (torch.rand(total_T, F, generator=g) < 0.2).to(torch.float32).to(dev)
+    torch.manual_seed(7)
+    enc = torch.nn.Sequential(torch.nn.Linear(F, 128), torch.nn.ReLU(), torch.nn.Linear(128, D)).to(dev)
+    dec = torch.nn.Sequential(torch.nn.Linear(D, 128), torch.nn.ReLU(), torch.nn.Linear(128, F), torch.nn.Sigmoid()).to(dev)
+    ell_q = torch.nn.Parameter(case["ell_q"].to(dev))
+    ell_p = case["ell_p"].to(dev)
+    params = list(enc.parameters()) + list(dec.parameters()) + [ell_q]
+    opt = torch.optim.Adam(params, lr=2e-4)
+    eps = case["eps"].to(dev)
+
+    def one():
+        opt.zero_grad(set_to_none=True)
+        mean = enc(x)
+        z, kl_sum, _ = gpkl.gp_prior_kl(mean, times, lengths, ell_q, ell_p, eps, kernel=w["kernel"])
+        xd = dec(z)
+        loss = gpkl.elbo_loss(x, xd, lengths, kl_sum, beta=1.0)
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            off = 0
+            for p in params:
+                n = p.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p))
+                off += n
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    L.gpkl_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    torch.cuda.synchronize()
+    fwd_ms, bwd_ms = ctypes.c_double(0), ctypes.c_double(0)
+    nf, nb = ctypes.c_int32(0), ctypes.c_int32(0)
+    L.gpkl_profile_read(ctypes.byref(fwd_ms), ctypes.byref(nf), ctypes.byref(bwd_ms), ctypes.byref(nb))
+    L.gpkl_profile_enable(0)
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    kl_ms = (fwd_ms.value + bwd_ms.value) / steps
+    return {"value": B * world / (ms * 1e-3), "unit": "sequences/s", "ms_per_step": ms, "steps": steps,
+            "gp_prior_kernels_ms": kl_ms, "gp_prior_share_of_step": kl_ms / ms if ms > 0 else None,
+            "loss": float(loss), "model": "per-time-step MLP %d-128-%d encoder, %d-128-%d decoder (stock torch.nn), "
+                                          "Bernoulli recon + KL, Adam(2e-4)" % (F, D, D, F)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS),
+                    help="headline workload; c4 (T=512, D=64, B=1024, Cauchy) is the config BASELINE.json quotes the "
+                         "'1/2/4/8 B200; Cholesky %% of FP32 peak' metric on and it fits one GPU")
     ap.add_argument("--tier", default="auto")
     ap.add_argument("--grad-ell-p", action="store_true", help="also produce d/d ell_p (fixed-T model)")
     ap.add_argument("--per-pair-prior", action="store_true",
@@ -201,6 +433,8 @@ def main():
                          "shared-prior fast path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the short T-sweep of kernel FP32 fractions")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short c2 / c1 / c3 lines (N=1 only)")
+    ap.add_argument("--no-elbo", action="store_true", help="skip the full ELBO step (stock torch encoder/decoder + Adam)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -214,7 +448,6 @@ def main():
 
     import torch.distributed as dist
     import gpkl
-    from gpkl.parallel import GradBucket
     import ctypes
     L = gpkl._lib.lib()
     torch.cuda.set_device(local_rank)
@@ -225,49 +458,11 @@ def main():
     warmup = max(args.warmup, 3)
 
     T, D, B = w["T"], w["D"], w["B"]
-    case = make_case(w, 1234 + rank)
-    host = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
-    c = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
     cfg = dict(kernel=w["kernel"], posterior="gp", noise=1e-3, S=1, tier=args.tier, shared_prior=not args.per_pair_prior)
     # the synthetic inputs carry the reference's prior (ell_p = 1 for every latent dim), so the library takes its
     # shared-prior path unless told otherwise; T > 512 (slot tier), d/d ell_p and the generic tier factor per pair
     shared_prior = (not args.per_pair_prior) and (not args.grad_ell_p) and T <= 512 and args.tier != "generic"
-    # two gradient buckets: step k's all-reduce (async, NCCL's own stream) overlaps step k+1's compute, the
-    # way DDP overlaps bucket reduction with the rest of backward; a bucket is waited for before it is rewritten
-    buckets = [GradBucket(D, dev), GradBucket(D, dev)]
-    pending = [None, None]
-    bucket = buckets[0]
-    one = torch.ones((), dtype=torch.float64, device=dev)
-    g_mean = torch.empty_like(c["mean"])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 256 MiB > 126 MB L2
-    step_no = [0]
-
-    def step():
-        k = step_no[0] & 1
-        step_no[0] += 1
-        bk = buckets[k]
-        if pending[k] is not None:
-            pending[k].wait()          # stream-level wait: the reduction that last used this bucket is done
-            pending[k] = None
-        f = gpkl.gp_prior_kl_forward(c["mean"], c["times"], c["lengths"], c["ell_q"], c["ell_p"], c["eps"], **cfg)
-        out = bk.out_views()
-        out["g_mean"] = g_mean
-        gpkl.gp_prior_kl_backward(c["mean"], c["times"], c["lengths"], c["ell_q"], c["ell_p"], c["eps"], c["g_z"],
-                                  one, None, grad_ell_p=args.grad_ell_p, out=out, **cfg)
-        bk.kl.copy_(f["kl_sum"].to(torch.float32).reshape(1))
-        pending[k] = bk.all_reduce(async_op=True)
-        return f
-
-    def drain():
-        for k in (0, 1):
-            if pending[k] is not None:
-                pending[k].wait()
-                pending[k] = None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---- FP32 CUDA-core peak (FFMA microbenchmark, timed alone) --------------------------------------
     sink = torch.empty(148 * 8 * 256, dtype=torch.float32, device=dev)
@@ -284,88 +479,61 @@ def main():
             best_peak = max(best_peak, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
 
     # ---- device-resident timed region ----------------------------------------------------------------
-    for _ in range(warmup):
-        step()
-        flush.zero_()
-    drain()
-    L.gpkl_profile_enable(1)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    launches0 = L.gpkl_launch_count()
-    sampler.sample()
-    sampler.start()
-    evs = []
-    for _ in range(args.steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step()
-        e1.record()
-        evs.append((e0, e1))
-        flush.zero_()   # evict the step's inputs from L2 between timed iterations (outside the events)
-    # the last all-reduces must finish inside the timed region: their tail is timed as well
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    drain()
-    e1.record()
-    evs.append((e0, e1))
-    barrier()
-    sampler.stop_flag = True
-    sampler.sample()
-    launches = (L.gpkl_launch_count() - launches0) + (args.steps if world > 1 else 0) + args.steps
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    fwd_ms, bwd_ms = ctypes.c_double(0), ctypes.c_double(0)
-    nf, nb = ctypes.c_int32(0), ctypes.c_int32(0)
-    L.gpkl_profile_read(ctypes.byref(fwd_ms), ctypes.byref(nf), ctypes.byref(bwd_ms), ctypes.byref(nb))
-    L.gpkl_profile_enable(0)
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    m = measure_device(gpkl, L, w, dev, args.steps, warmup, cfg, world=world, flush=flush, grad_ell_p=args.grad_ell_p)
+    case = m["case"]
+    host = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
+    # our launches: the library's own count + per step the KL copy into the bucket (+ the NCCL all-reduce at N>1)
+    launches = m["lib_launches"] + args.steps + (args.steps if world > 1 else 0)
+    tmax = torch.tensor([m["total_ms"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_per_step = float(tmax) / args.steps
     value = B * world / (ms_per_step * 1e-3)
 
-    # ---- end-to-end: host (pinned) buffers in, results out, copies inside the timed region ------------
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- end-to-end: host (pinned) buffers in, EVERY result out (z, KL per pair, d/d mean, d/d ell), copies timed -----
     total_T = case["mean"].shape[0]
-    if world == 1:
-        hs = gpkl.HostStep(B, D, T, 1, total_T, kernel=w["kernel"], grad_ell_p=args.grad_ell_p, tier=args.tier,
-                           device=dev, shared_prior=not args.per_pair_prior)
+    hs = gpkl.HostStep(B, D, T, 1, total_T, kernel=w["kernel"], grad_ell_p=args.grad_ell_p, tier=args.tier,
+                       device=dev, shared_prior=not args.per_pair_prior)
+    from gpkl.parallel import GradBucket
+    bucket = GradBucket(D, dev)
+    res_host = torch.empty(2 * D + 1, dtype=torch.float32).pin_memory()
 
-        def e2e_step():
-            hs(host["mean"], host["times"], host["lengths"], host["ell_q"], host["ell_p"], host["eps"], host["g_z"],
-               full_outputs=False)
-            return hs.h2d_bytes, hs.d2h_bytes
-    else:
-        res_host = torch.empty(2 * D + 1, dtype=torch.float32).pin_memory()
-
-        def e2e_step():
-            cc = {k: host[k].to(dev, non_blocking=True) for k in ("mean", "times", "lengths", "ell_q", "ell_p", "eps", "g_z")}
-            f = gpkl.gp_prior_kl_forward(cc["mean"], cc["times"], cc["lengths"], cc["ell_q"], cc["ell_p"], cc["eps"], **cfg)
-            out = bucket.out_views()
-            out["g_mean"] = g_mean
-            gpkl.gp_prior_kl_backward(cc["mean"], cc["times"], cc["lengths"], cc["ell_q"], cc["ell_p"], cc["eps"],
-                                      cc["g_z"], one, None, grad_ell_p=args.grad_ell_p, out=out, **cfg)
-            bucket.kl.copy_(f["kl_sum"].to(torch.float32).reshape(1))
-            bucket.all_reduce()      # synchronous here: the caller reads the reduced result every step
+    def e2e_step():
+        hs(host["mean"], host["times"], host["lengths"], host["ell_q"], host["ell_p"], host["eps"], host["g_z"],
+           full_outputs=True)
+        extra = 0
+        if world > 1:  # the ranks' lengthscale gradients and KL are summed before the caller reads them
+            torch.cuda.current_stream(dev).synchronize()
+            bucket.g_ell_q.copy_(hs.g_ell_q, non_blocking=True)
+            bucket.kl.copy_(hs.kl_sum.to(torch.float32).reshape(1), non_blocking=True)
+            bucket.all_reduce()
             res_host.copy_(bucket.flat, non_blocking=True)
-            h2d = sum(host[k].numel() * host[k].element_size() for k in ("mean", "times", "lengths", "ell_q", "ell_p", "eps", "g_z"))
-            return h2d, res_host.numel() * 4
-    for _ in range(3):
+            extra = res_host.numel() * 4
+        return hs.h2d_bytes, hs.d2h_bytes + extra
+    for _ in range(2):
         h2d_b, d2h_b = e2e_step()
         torch.cuda.synchronize()
     barrier()
     e2e_ms = 0.0
-    n_e2e = max(10, min(args.steps, 200))
+    n_e2e = max(3, min(args.steps, 10 if ms_per_step > 50.0 else 200))
     for _ in range(n_e2e):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         h2d_b, d2h_b = e2e_step()
         e1.record()
-        e1.synchronize()   # the caller reads the step's result (KL, lengthscale grads) every step
+        e1.synchronize()   # the caller reads the step's results every step
         e2e_ms += e0.elapsed_time(e1)
     barrier()
     t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_val = B * world / (float(t2) / n_e2e * 1e-3)
+    del hs
 
     # ---- roofline of the dominant kernel (backward) -------------------------------------------------
     peaks = {}
@@ -375,42 +543,14 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"
-    f_fwd, f_bwd = model_flops_pair(T)
-    npairs = B * D
-    bwd_avg_ms = bwd_ms.value / max(nb.value, 1)
-    fwd_avg_ms = fwd_ms.value / max(nf.value, 1)
-    # achieved = flops the implementation must EXECUTE (fewer than the model's with the shared prior) / kernel time
-    # (pre-pass + per-pair kernel, bracketed together); model_frac = the reference model's flops (T^3 / 2T^3 per pair,
-    # SURVEY S8d) / the same time -- what an implementation factoring K_p per pair would need to sustain to be as fast
-    x_fwd, x_bwd = executed_flops(T, B, D, shared_prior)
-    ach_bwd = x_bwd / (bwd_avg_ms * 1e-3) / 1e12
-    ach_fwd = x_fwd / (fwd_avg_ms * 1e-3) / 1e12
-    mod_bwd = npairs * f_bwd / (bwd_avg_ms * 1e-3) / 1e12
-    mod_fwd = npairs * f_fwd / (fwd_avg_ms * 1e-3) / 1e12
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         traffic = tr.get(args.workload, {}).get("bwd_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {
-        "bound": "fp32", "kernel": "backward (Cholesky/trisolve adjoints)", "achieved": ach_bwd, "peak": best_peak,
-        "unit": "TFLOP/s", "frac": ach_bwd / best_peak if best_peak > 0 else None, "traffic": traffic,
-        "peak_source": "FFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry; "
-                       "nominal 148x128x2x1.965GHz = 74.4)",
-        "algorithmic": ("shared prior: %d pairs x 4/3 T^3 + %d sequences x T^3 flops" % (npairs, B)) if shared_prior
-                       else "%d pairs x 2*T^3 flops" % npairs,
-        "model_frac": mod_bwd / best_peak if best_peak > 0 else None, "shared_prior": bool(shared_prior),
-        "launch_ms": bwd_avg_ms,
-        "hbm_frac": npairs * algo_bytes_pair(T) / ((fwd_avg_ms + bwd_avg_ms) * 1e-3) / 1e9 / hbm_peak,
-        "hbm_peak_source": hbm_src,
-        "forward": {"achieved": ach_fwd, "frac": ach_fwd / best_peak if best_peak > 0 else None,
-                    "model_frac": mod_fwd / best_peak if best_peak > 0 else None,
-                    "launch_ms": fwd_avg_ms,
-                    "algorithmic": ("shared prior: %d pairs x 2/3 T^3 + %d sequences x 2/3 T^3 flops" % (npairs, B))
-                                   if shared_prior else "%d pairs x T^3 flops" % npairs},
-        "kernel_share_of_step": (fwd_avg_ms + bwd_avg_ms) / (total_ms / args.steps),
-    }
+    roofline = roofline_block(w, B, m["fwd_ms"], m["bwd_ms"], best_peak, shared_prior, m["total_ms"] / args.steps,
+                              hbm_peak, hbm_src, traffic)
 
     out = {
         "metric": "GP-prior KL fwd+bwd sequences/s", "value": value, "unit": "sequences/s", "n_gpus": world,
@@ -420,17 +560,46 @@ def main():
                    "parallelism": "dp%d (sequences sharded; async all-reduce of lengthscale grads overlapped with the next step)" % world,
                    "l2": "256 MiB flush between timed iterations", "tier": args.tier,
                    "grad_ell_p": bool(args.grad_ell_p)},
-        "clocks": sampler.result(),
+        "clocks": m["clocks"],
         "e2e": {"value": e2e_val, "unit": "sequences/s", "h2d_bytes_per_step": int(h2d_b),
-                "d2h_bytes_per_step": int(d2h_b), "ms_per_step": float(t2) / n_e2e},
+                "d2h_bytes_per_step": int(d2h_b), "ms_per_step": float(t2) / n_e2e, "steps": n_e2e,
+                "outputs_copied_back": "z, kl_pairs, kl_sum, g_mean, g_ell_q"},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
-    # ---- short T-sweep (N=1): FP32 fraction of the forward / backward kernels at larger T (north_star's
-    #      ">= 50 % of FP32 peak for T >= 128" is judged on these; the headline workload is T=48) -------------
+    # ---- the BASELINE metric itself: full ELBO step (encoder + GP-prior op + decoder + recon + Adam) ----------------------
+    if not args.no_elbo:
+        try:
+            out["elbo_step"] = elbo_step_bench(gpkl, w, dev, world)
+        except Exception as ex:  # never lose the headline line to the auxiliary measurement
+            out["elbo_step"] = {"error": repr(ex)[:200]}
+    # ---- secondary workloads (N=1): the other single-GPU BASELINE configs, eager and CUDA-graph replay ---------------
+    if world == 1 and not args.no_secondary:
+        sec = []
+        for name in ("c2", "c1", "c3"):
+            if name == args.workload:
+                continue
+            ws = WORKLOADS[name]
+            scfg = dict(kernel=ws["kernel"], posterior="gp", noise=1e-3, S=1, tier=args.tier, shared_prior=not args.per_pair_prior)
+            row = {"workload": name + ": " + ws["desc"]}
+            for mode in ("eager", "graph"):
+                r = measure_device(gpkl, L, ws, dev, 50, 5, scfg, world=1, flush=flush, use_graph=(mode == "graph"))
+                msps = r["total_ms"] / 50
+                row[mode] = {"value": ws["B"] / (msps * 1e-3), "ms_per_step": msps}
+                if mode == "eager":
+                    rf = roofline_block(ws, ws["B"], r["fwd_ms"], r["bwd_ms"], best_peak, True, msps, hbm_peak, hbm_src, None)
+                    row["roofline"] = {k: rf[k] for k in ("frac", "model_frac", "hbm_frac", "kernel_share_of_step", "launch_ms")}
+                    row["roofline"]["forward_frac"] = rf["forward"]["frac"]
+                    row["roofline"]["forward_launch_ms"] = rf["forward"]["launch_ms"]
+            sec.append(row)
+        out["secondary"] = sec
+    # ---- short T-sweep (N=1): FP32 fraction of the forward / backward kernels at T >= 128 --------------------------------
     if world == 1 and not args.no_sweep:
         sweep = []
-        for Ts, Bs in ((128, 128), (256, 64), (512, 16)):
+        one = torch.ones((), dtype=torch.float64, device=dev)
+        fwd_ms, bwd_ms = ctypes.c_double(0), ctypes.c_double(0)
+        nf, nb = ctypes.c_int32(0), ctypes.c_int32(0)
+        for Ts, Bs in ((128, 128), (256, 64), (384, 32), (512, 16)):
             ws = dict(T=Ts, D=64, B=Bs, kernel="rbf")
             cs = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in make_case(ws, 4321).items()}
             scfg = dict(kernel="rbf", posterior="gp", noise=1e-3, S=1, tier=args.tier, shared_prior=not args.per_pair_prior)
@@ -463,6 +632,9 @@ def main():
         val, sample, _, _ = cpu_port_throughput(w, args.cpu_budget, os.cpu_count() or 1)
         out["cpu_baseline"] = {"value": val, "unit": "sequences/s", "cores": os.cpu_count() or 1, "kind": "port",
                                "sample": sample}
+        vb = verbatim_reference_timing()
+        if vb is not None:
+            out["cpu_baseline"]["verbatim"] = vb
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

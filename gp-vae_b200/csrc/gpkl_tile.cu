@@ -201,6 +201,17 @@ __device__ __forceinline__ void run_chunks(float (&acc)[8][8], GCtx& G, int n, I
   }
 }
 
+// Phase clock (developer aid, tools/tile_trace.py): thread 0 of CTA 0 accumulates the cycles between ticks into
+// dbg[48 + k]; a no-op (NULL) for every other thread and whenever no trace buffer is set.
+struct PhClock {
+  long long t0;
+  long long* dbg;
+  __device__ __forceinline__ void start() { if (dbg) t0 = clock64(); }
+  __device__ __forceinline__ void tick(int k) {
+    if (dbg) { const long long t = clock64(); dbg[48 + k] += t - t0; t0 = t; }
+  }
+};
+
 // Everything a pair's phases share.
 struct Sm {
   double* red;
@@ -345,7 +356,7 @@ __device__ __forceinline__ void invert64(const float* __restrict__ D, const floa
 // -- the loop issues the CTA barrier).
 template <int KERNEL, class HookF>
 __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* __restrict__ Lg, Sm& s, GCtx& G, int* bad,
-                                                 HookF hook) {
+                                                 PhClock& pc, HookF hook) {
   const int tid = threadIdx.x;
   const int nTb = pr.nTb;
   for (int J = 0; J < nTb; ++J) {
@@ -407,6 +418,7 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
         __syncthreads();
       }
     }
+    pc.tick(1);
     // ---- (2) diagonal block: factor in place (column-major), invert, publish -------------------------------------------
     float* D = s.panel + (size_t)J * TF;
     factor64(D, s.dgq + TS * J, s.rdl, pr.T - TS * J, bad);
@@ -431,6 +443,7 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
       }
       __syncthreads();
     }
+    pc.tick(2);
     // ---- (3) rows below: L(I,J) = raw(I,J) L_JJ^-T, one tile per group job, operands resident --------------------------
     for (int rd = 0; rd * NGRP < m - 1; ++rd) {
       const int ti = 1 + rd * NGRP + G.g;
@@ -447,9 +460,11 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
     }
     fence_async();  // the L tiles written above are read by bulk copies from the next panel on
     __syncthreads();
+    pc.tick(3);
     // ---- (4) per-panel consumers of the finished panel -----------------------------------------------------------------
     hook(J);
     __syncthreads();
+    pc.tick(4);
   }
 }
 
@@ -498,6 +513,9 @@ __global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
   float* Lg = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
   float* dgp = s.v0;
   float* aa = s.v1;
+  PhClock pc;
+  pc.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
+  pc.start();
   for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
     const int T = P.lengths[b];
@@ -532,7 +550,9 @@ __global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
       aa[i] = a0 + a1;
     }
     float ssq = 0.0f;
-    chol_panels_tile<KERNEL>(pr, Lg, s, G, &bad, [&](int J) {
+    __syncthreads();
+    pc.tick(0);
+    chol_panels_tile<KERNEL>(pr, Lg, s, G, &bad, pc, [&](int J) {
       const int m = nTb - J;
       // z_s += L_q(:, panel J) eps_s(panel J): one row per thread, 128-bit row reads started at a lane-dependent column
       for (int idx = tid; idx < m * TS; idx += NTHR) {
@@ -599,6 +619,8 @@ __global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
       if (P.logdets) { P.logdets[2 * p] = (float)ldp; P.logdets[2 * p + 1] = (float)ldq; }
       if (bad && P.status) atomicAdd(P.status, 1);
     }
+    pc.tick(5);
+    if (pc.dbg) pc.dbg[63] += 1;
   }
 }
 
@@ -634,6 +656,9 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
   float* pd = s.v2;   // 1/2 w eps - g/2
   float* cum = s.v3;  // running column sums  sum_{j < i} eps_j X(j, l)
   float* rdq = s.v4;  // 1 / diag L_q (whole sequence)
+  PhClock pc;
+  pc.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
+  pc.start();
   for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
     const int T = P.lengths[b];
@@ -651,7 +676,8 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
     const float lq = P.ell_q[dd];
     const Pair<KERNEL> pr(T, lq, sig, noise);
     const int nTb = pr.nTb;
-    chol_panels_tile<KERNEL>(pr, Lg, s, G, &bad, [&](int J) {
+    pc.tick(0);
+    chol_panels_tile<KERNEL>(pr, Lg, s, G, &bad, pc, [&](int J) {
       const int m = nTb - J;
       // w(panel J) = L_q(:, panel J)^T g_z: four row-interleaved partial sums per column, summed in a fixed order
       {
@@ -683,6 +709,7 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
       invert64(Dt, s.rdl, s.linv, s.panel + (size_t)I * TF, s.stg + GSTG_F);
       fence_async();                     // stage areas were used as scratch by threads
       __syncthreads();
+      pc.tick(6);
       // off-diagonal tiles C < I:  Y = -sum_{K=C}^{I-1} L(I,K) X(K,C),  X(I,C) = L_II^-1 Y   (longest first: C ascending)
       for (int blk = 0; blk * NGRP < I; ++blk) {
         const int C = blk * NGRP + ((blk & 1) ? NGRP - 1 - G.g : G.g);
@@ -709,6 +736,7 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
       }
       fence_async();  // panel tiles (X row block I) are read by the bulk stores below
       __syncthreads();
+      pc.tick(7);
       if (tid == 0) {  // X(I, 0..I) -> global, in place of L(I, 0..I) (every read of that row of L tiles is complete)
         bulk_s2g(Lg + (size_t)tri(I, 0) * TF, s.panel, (unsigned)((I + 1) * TF * 4));
         bulk_commit();
@@ -730,6 +758,7 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
       }
       fence_async();  // C' tiles (thread stores) are read by bulk copies in the contraction
       __syncthreads();
+      pc.tick(8);
     }
     if (tid == 0) bulk_wait0();  // X tiles are in global memory
     __syncthreads();
@@ -748,6 +777,8 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
       for (; l < T; ++l) a0 = fmaf(__ldg(kinv + (size_t)l * ldr + k), s.mm[l], a0);
       P.g_mean[(size_t)(r0 + k) * d.D + dd] = g * (a0 + a1) + u[k];
     }
+    __syncthreads();
+    pc.tick(9);
     // ---- contraction: sum_{k != l} dK_kl (hg K_p^-1 + X_q^T C')_kl, tiles by shell max(kt,lt) (longest first), boustrophedon --
     double total = 0.0;
     for (int blk = 0; blk * NGRP < nTb * nTb; ++blk) {
@@ -800,6 +831,8 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
       P.gq_pairs[p] = (float)gq;
       if (bad && P.status) atomicAdd(P.status, 1);
     }
+    pc.tick(10);
+    if (pc.dbg) pc.dbg[63] += 1;
   }
 }
 
