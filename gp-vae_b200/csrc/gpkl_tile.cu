@@ -49,11 +49,12 @@ namespace {
 
 constexpr int TS = 64;             // tile edge
 constexpr int TF = TS * TS;        // floats per tile (16 KB)
-constexpr int KC = 16;             // contraction steps per staged chunk
-constexpr int CH = KC * TS;        // floats per operand chunk (4 KB)
+constexpr int KC = 8;              // contraction steps per staged chunk
+constexpr int CH = KC * TS;        // floats per operand chunk (2 KB)
+constexpr int UC = TS / KC;        // chunks per 64-step tile of the contraction index
 constexpr int STAGE_F = 2 * CH;    // one stage: A chunk | B chunk
-constexpr int GSTG_F = 2 * STAGE_F;  // two stages per group == one tile (doubles as the group's partial-tile buffer)
-constexpr int NGRP = 4;            // thread groups per CTA
+constexpr int WSTG_F = 2 * STAGE_F;  // two stages per warp (8 KB); the two warps of a pair together hold one tile
+constexpr int NW = 8;              // workers (warps) per CTA
 constexpr int NTHR = 256;
 constexpr int NVEC = 8;            // per-pair vectors of TP floats besides the per-sample ones
 
@@ -68,7 +69,8 @@ struct TLay {
   __host__ __device__ int ntri() const { return nT * (nT + 1) / 2; }
   __host__ __device__ size_t nvec() const { return (size_t)NVEC + 2 * (size_t)(S > 1 ? S - 1 : 0); }
   __host__ __device__ size_t floats() const {
-    return 64 /*red*/ + 16 /*mbarriers*/ + 64 /*rdl*/ + (size_t)nT * TF + (size_t)NGRP * GSTG_F + TF + nvec() * TP;
+    return 64 /*red*/ + 32 /*mbarriers*/ + 16 /*flush counters*/ + 64 /*rdl*/ + (size_t)nT * TF + (size_t)NW * WSTG_F + TF +
+           nvec() * TP;
   }
 };
 
@@ -112,17 +114,18 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // generic-proxy writes (st.shared / st.global by threads) ordered before later async-proxy (bulk copy) accesses
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// ---- thread group -----------------------------------------------------------------------------------------------------
-struct GCtx {
-  int g, t, ty, tx;     // group, thread within the group, micro-tile coordinates (rows 4ty.., 32+4ty..; cols 4tx.., 32+4tx..)
-  float* stg;           // this group's two stages (GSTG_F floats)
+// ---- worker (one warp) ------------------------------------------------------------------------------------------------
+struct WCtx {
+  int w, lane, ty, tx;  // warp, lane, micro-tile coordinates: rows 4ty+{0..3} (+32), cols 4tx+{0..3} (+16, +32, +48)
+  float* stg;           // this warp's two stages (WSTG_F floats)
   uint64_t* bar;        // the two "stage full" barriers
   unsigned use0, use1;  // fills consumed per stage (phase parity)
+  long long* dbg;       // developer aid: lane 0 of warp 0 of CTA 0 splits the staged loops into wait / compute / issue cycles
 };
 
-// named barrier of one group (ids must be literals: a register id makes ptxas reserve all 16 hardware barriers)
-__device__ __forceinline__ void group_sync(int g) {
-  switch (g) {
+// named barrier of one warp PAIR (ids must be literals: a register id makes ptxas reserve all 16 hardware barriers)
+__device__ __forceinline__ void pair_sync(int q) {
+  switch (q) {
     case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
     case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
     case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
@@ -130,15 +133,17 @@ __device__ __forceinline__ void group_sync(int g) {
   }
 }
 
-__device__ __forceinline__ void acc_zero(float (&acc)[8][8]) {
+__device__ __forceinline__ void acc_zero(float (&acc)[8][16]) {
 #pragma unroll
   for (int r = 0; r < 8; ++r)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[r][c] = 0.0f;
+    for (int c = 0; c < 16; ++c) acc[r][c] = 0.0f;
 }
 
-// acc[r][c] += sum_{kk < KC} A[kk][row(r)] * B[kk][col(c)]  (operand rows are 64 floats apart)
-__device__ __forceinline__ void mk_chunk(float (&acc)[8][8], const float* __restrict__ As, const float* __restrict__ Bs, int ty,
+// acc[r][c] += sum_{kk < KC} A[kk][row(r)] * B[kk][col(c)]  (operand rows are 64 floats apart).  8 x 16 outputs per thread:
+// six 128-bit loads (24 floats) feed 64 packed FFMA2 -- 0.75 bytes of shared-memory delivery per FMA; the 8 x 8 tile of the
+// first version needed 1.0, exactly the SM's 128 B/clk at FP32 peak, and ran at 45-60 % of it.
+__device__ __forceinline__ void mk_chunk(float (&acc)[8][16], const float* __restrict__ As, const float* __restrict__ Bs, int ty,
                                          int tx) {
   const float* ap = As + 4 * ty;
   const float* bp = Bs + 4 * tx;
@@ -147,58 +152,124 @@ __device__ __forceinline__ void mk_chunk(float (&acc)[8][8], const float* __rest
     const float4 a0 = *reinterpret_cast<const float4*>(ap + kk * TS);
     const float4 a1 = *reinterpret_cast<const float4*>(ap + kk * TS + 32);
     const float4 b0 = *reinterpret_cast<const float4*>(bp + kk * TS);
-    const float4 b1 = *reinterpret_cast<const float4*>(bp + kk * TS + 32);
+    const float4 b1 = *reinterpret_cast<const float4*>(bp + kk * TS + 16);
+    const float4 b2 = *reinterpret_cast<const float4*>(bp + kk * TS + 32);
+    const float4 b3 = *reinterpret_cast<const float4*>(bp + kk * TS + 48);
     const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float b[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int c = 0; c < 8; c += 2) fma2(acc[r][c], acc[r][c + 1], a[r], a[r], b[c], b[c + 1]);
+      for (int c = 0; c < 16; c += 2) fma2(acc[r][c], acc[r][c + 1], a[r], a[r], b[c], b[c + 1]);
   }
 }
 
 __device__ __forceinline__ int mrow(int ty, int r) { return 4 * ty + (r & 3) + 32 * (r >> 2); }
-__device__ __forceinline__ int mcol(int tx, int c) { return 4 * tx + (c & 3) + 32 * (c >> 2); }
+__device__ __forceinline__ int mcol(int tx, int c) { return 4 * tx + (c & 3) + 16 * (c >> 2); }
 
-// tile stores from the micro-kernel's registers.  SGN: +1 / -1.
+// tile stores / read-modify-writes from the micro-kernel's registers.
+// column-major [c][i]: the 8 row-threads of a quarter warp touch 128 contiguous bytes (conflict-free, coalesced)
 template <int SGN>
-__device__ __forceinline__ void store_colmajor(float* __restrict__ dst, const float (&acc)[8][8], int ty, int tx) {
+__device__ __forceinline__ void store_colmajor(float* __restrict__ dst, const float (&acc)[8][16], int ty, int tx) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    float* d = dst + (size_t)mcol(tx, c) * TS + 4 * ty;  // [c][i]: 8 row-threads of a quarter warp -> 128 contiguous bytes
+  for (int c = 0; c < 16; ++c) {
+    float* d = dst + (size_t)mcol(tx, c) * TS + 4 * ty;
     *reinterpret_cast<float4*>(d) = make_float4(SGN * acc[0][c], SGN * acc[1][c], SGN * acc[2][c], SGN * acc[3][c]);
     *reinterpret_cast<float4*>(d + 32) = make_float4(SGN * acc[4][c], SGN * acc[5][c], SGN * acc[6][c], SGN * acc[7][c]);
   }
 }
+__device__ __forceinline__ void sub_colmajor(float* __restrict__ dst, const float (&acc)[8][16], int ty, int tx) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    float* d = dst + (size_t)mcol(tx, c) * TS + 4 * ty;
+    float4 lo = *reinterpret_cast<float4*>(d), hi = *reinterpret_cast<float4*>(d + 32);
+    lo.x -= acc[0][c]; lo.y -= acc[1][c]; lo.z -= acc[2][c]; lo.w -= acc[3][c];
+    hi.x -= acc[4][c]; hi.y -= acc[5][c]; hi.z -= acc[6][c]; hi.w -= acc[7][c];
+    *reinterpret_cast<float4*>(d) = lo;
+    *reinterpret_cast<float4*>(d + 32) = hi;
+  }
+}
+__device__ __forceinline__ void add_colmajor(float (&acc)[8][16], const float* __restrict__ src, int ty, int tx) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const float* d = src + (size_t)mcol(tx, c) * TS + 4 * ty;
+    const float4 lo = *reinterpret_cast<const float4*>(d), hi = *reinterpret_cast<const float4*>(d + 32);
+    acc[0][c] += lo.x; acc[1][c] += lo.y; acc[2][c] += lo.z; acc[3][c] += lo.w;
+    acc[4][c] += hi.x; acc[5][c] += hi.y; acc[6][c] += hi.z; acc[7][c] += hi.w;
+  }
+}
+// row-major [i][c]
 template <int SGN>
-__device__ __forceinline__ void store_rowmajor(float* __restrict__ dst, const float (&acc)[8][8], int ty, int tx) {
+__device__ __forceinline__ void store_rowmajor(float* __restrict__ dst, const float (&acc)[8][16], int ty, int tx) {
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    float* d = dst + (size_t)mrow(ty, r) * TS + 4 * tx;  // [i][c]
-    *reinterpret_cast<float4*>(d) = make_float4(SGN * acc[r][0], SGN * acc[r][1], SGN * acc[r][2], SGN * acc[r][3]);
-    *reinterpret_cast<float4*>(d + 32) = make_float4(SGN * acc[r][4], SGN * acc[r][5], SGN * acc[r][6], SGN * acc[r][7]);
+    float* d = dst + (size_t)mrow(ty, r) * TS + 4 * tx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(d + 16 * j) =
+          make_float4(SGN * acc[r][4 * j], SGN * acc[r][4 * j + 1], SGN * acc[r][4 * j + 2], SGN * acc[r][4 * j + 3]);
+  }
+}
+__device__ __forceinline__ void sub_rowmajor(float* __restrict__ dst, const float (&acc)[8][16], int ty, int tx) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    float* d = dst + (size_t)mrow(ty, r) * TS + 4 * tx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 v = *reinterpret_cast<float4*>(d + 16 * j);
+      v.x -= acc[r][4 * j]; v.y -= acc[r][4 * j + 1]; v.z -= acc[r][4 * j + 2]; v.w -= acc[r][4 * j + 3];
+      *reinterpret_cast<float4*>(d + 16 * j) = v;
+    }
   }
 }
 
-// Staged contraction of one job: n chunks; issue(c, stage, bar) is executed by ONE thread of the group and starts the
-// bulk copies of chunk c into `stage` (A chunk at stage, B chunk at stage + CH) after arming `bar` with their byte count.
-// B_RES: the B operand is resident in shared memory, bres(c) returns its chunk.
+// Staged contraction of one job: n chunks; issue(c, stage, bar) is executed by lanes 0..7 of the warp (lane passed in) and
+// starts the bulk copies of chunk c into `stage` (A chunk at stage, B chunk at stage + CH), lane 0 arming `bar` with their
+// byte count.  B_RES: the B operand is resident in shared memory, bres(c) returns its chunk.
 template <bool B_RES, class IssueF, class BresF>
-__device__ __forceinline__ void run_chunks(float (&acc)[8][8], GCtx& G, int n, IssueF issue, BresF bres) {
-  if (G.t == 0) {
-    if (n > 0) issue(0, G.stg, &G.bar[0]);
-    if (n > 1) issue(1, G.stg + STAGE_F, &G.bar[1]);
+__device__ __forceinline__ void run_chunks(float (&acc)[8][16], WCtx& W, int n, IssueF issue, BresF bres) {
+  if (W.lane < 8) {
+    if (n > 0) issue(0, W.stg, &W.bar[0], W.lane);
+    if (n > 1) issue(1, W.stg + STAGE_F, &W.bar[1], W.lane);
   }
+  __syncwarp();
   for (int c = 0; c < n; ++c) {
     const int s = c & 1;
-    if (s) { mbar_wait(&G.bar[1], G.use1 & 1u); ++G.use1; }
-    else { mbar_wait(&G.bar[0], G.use0 & 1u); ++G.use0; }
-    const float* As = G.stg + s * STAGE_F;
+    long long t0 = 0, t1 = 0, t2 = 0;
+    if (W.dbg) t0 = clock64();
+    if (s) { mbar_wait(&W.bar[1], W.use1 & 1u); ++W.use1; }
+    else { mbar_wait(&W.bar[0], W.use0 & 1u); ++W.use0; }
+    if (W.dbg) t1 = clock64();
+    const float* As = W.stg + s * STAGE_F;
     const float* Bs = B_RES ? bres(c) : As + CH;
-    mk_chunk(acc, As, Bs, G.ty, G.tx);
-    group_sync(G.g);  // both warps are done with stage s
-    if (G.t == 0 && c + 2 < n) issue(c + 2, G.stg + s * STAGE_F, &G.bar[s]);
+    mk_chunk(acc, As, Bs, W.ty, W.tx);
+    __syncwarp();  // every lane is done with stage s
+    if (W.dbg) t2 = clock64();
+    if (W.lane < 8 && c + 2 < n) issue(c + 2, W.stg + s * STAGE_F, &W.bar[s], W.lane);
+    __syncwarp();
+    if (W.dbg) { const long long t3 = clock64(); W.dbg[32] += t1 - t0; W.dbg[33] += t2 - t1; W.dbg[34] += t3 - t2; W.dbg[35] += 1; }
   }
+}
+
+// Ordered flush of split contractions: the parts of one destination tile are applied in part order (bit-reproducible, and
+// exclusive access to the tile) through a shared-memory counter per tile.  Every lane calls both.
+__device__ __forceinline__ void flush_begin(volatile int* cnt, int part) {
+  if (part > 0) {
+    while (*cnt < part) {}
+  }
+  __threadfence_block();
+}
+__device__ __forceinline__ void flush_end(volatile int* cnt, int part, int lane) {
+  __threadfence_block();
+  __syncwarp();
+  if (lane == 0) *cnt = part + 1;
+}
+// first warp whose chunk range [w U / 8, (w+1) U / 8) reaches beyond chunk index `off` (the first contributor to the tile
+// whose chunks start at off)
+__device__ __forceinline__ int first_warp_after(int U, int off) {
+  int w = 0;
+  while (((w + 1) * U) / NW <= off) ++w;
+  return w;
 }
 
 // Phase clock (developer aid, tools/tile_trace.py): thread 0 of CTA 0 accumulates the cycles between ticks into
@@ -216,14 +287,16 @@ struct PhClock {
 struct Sm {
   double* red;
   uint64_t* bars;
+  int* cnt;
   float *rdl, *panel, *stg, *linv;
   float *ts, *mm, *dgq, *v0, *v1, *v2, *v3, *v4, *eps, *zacc;  // v0..v4: direction-specific vectors (see kernels)
   __device__ Sm(float* base, const TLay& L) {
     red = reinterpret_cast<double*>(base); base += 64;
-    bars = reinterpret_cast<uint64_t*>(base); base += 16;
+    bars = reinterpret_cast<uint64_t*>(base); base += 32;
+    cnt = reinterpret_cast<int*>(base); base += 16;
     rdl = base; base += 64;
     panel = base; base += (size_t)L.nT * TF;
-    stg = base; base += (size_t)NGRP * GSTG_F;
+    stg = base; base += (size_t)NW * WSTG_F;
     linv = base; base += TF;
     ts = base; base += L.TP;
     mm = base; base += L.TP;
@@ -263,12 +336,51 @@ struct Pair {
 
 // ---- the 64 x 64 diagonal block: Cholesky + inverse in shared memory, all 256 threads ------------------------------------
 // D: the block, column-major (D[c*64 + i], i >= c valid), factored in place.  dgl: diag(L) out (64), rdl: 1/diag(L) out (64).
-// Tl: number of real rows of the block (may exceed 64).  16-column sub-panels: one warp factors the 16 x 16 diagonal block in
-// registers (diag_factor), the rows below are solved one per thread, the trailing columns updated in 4 x 4 tiles.
-__device__ __forceinline__ void factor64(float* __restrict__ D, float* __restrict__ dgl, float* __restrict__ rdl, int Tl, int* bad) {
+// Tl: number of real rows of the block (may exceed 64).  Output LT[c'][c] = Linv[c][c'] (the contraction-major operand of
+// both uses: rows-below = raw Linv^T and X = Linv Y), zeros where c < c'.  Lrm (scratch, one tile): Linv row-major, the
+// contraction-major operand of the inverse's own products; tmpR: >= 768 floats of scratch.
+// By 16-column sub-panels P = 0..3, three barriers each:
+//   (1) warp 0 factors the 16 x 16 diagonal block in registers (diag_factor, the serial chain: ~2.4 K cycles) WHILE the other
+//       warps form the right-hand side of the inverse's block row P,  R = -L[P, 0:16P] Linv[0:16P, 0:16P]  (4 x 4 register tiles)
+//   (2) rows below the diagonal block are solved one per thread, and AT THE SAME TIME other threads solve the inverse's
+//       block row,  Linv[P, :] = L_PP^-1 [R | I]  (one column per thread)
+//   (3) the trailing columns are updated in 4 x 4 tiles.
+__device__ __forceinline__ void factor_invert64(float* __restrict__ D, float* __restrict__ dgl, float* __restrict__ rdl, int Tl,
+                                                int* bad, float* __restrict__ LT, float* __restrict__ Lrm,
+                                                float* __restrict__ tmpR) {
   const int tid = threadIdx.x;
-  for (int jl = 0; jl < TS; jl += 16) {
-    if (tid < 32) diag_factor<false>(D, TS, jl, Tl, D + (size_t)jl * TS, TS, dgl, rdl, bad);
+  for (int e = tid * 4; e < TF; e += NTHR * 4) {
+    *reinterpret_cast<float4*>(LT + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    *reinterpret_cast<float4*>(Lrm + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+  __syncthreads();
+  for (int P = 0; P < 4; ++P) {
+    const int jl = 16 * P;
+    if (tid < 32) {
+      diag_factor<false>(D, TS, jl, Tl, D + (size_t)jl * TS, TS, dgl, rdl, bad);
+    } else {
+      // R[r][col] = -sum_{k = col..jl-1} L[jl + r][k] Linv[k][col], col < jl: 4 row groups x (jl/4) column groups
+      for (int id = tid - 32; id < jl; id += NTHR - 32) {
+        const int r4 = id & 3, c4 = id >> 2;
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+        for (int k = 4 * c4; k < jl; ++k) {
+          const float4 u4 = *reinterpret_cast<const float4*>(D + (size_t)k * TS + jl + 4 * r4);
+          const float4 v4 = *reinterpret_cast<const float4*>(Lrm + (size_t)k * TS + 4 * c4);
+          const float u[4] = {u4.x, u4.y, u4.z, u4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(-u[r], v[c], acc[r][c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<float4*>(tmpR + (size_t)(4 * c4 + c) * 16 + 4 * r4) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+      }
+    }
     __syncthreads();
     const int nbelow = TS - jl - 16;
     if (tid < nbelow) {
@@ -279,6 +391,25 @@ __device__ __forceinline__ void factor64(float* __restrict__ D, float* __restric
       diag_solve16(b, D, TS, jl, rdl);
 #pragma unroll
       for (int c = 0; c < 16; ++c) D[(size_t)(jl + c) * TS + i] = b[c];
+    } else if (tid >= 64 && tid < 64 + jl + 16) {
+      const int col = tid - 64;
+      float b[16];
+      if (col < jl) {
+#pragma unroll
+        for (int r = 0; r < 16; r += 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(tmpR + (size_t)col * 16 + r);
+          b[r] = t4.x; b[r + 1] = t4.y; b[r + 2] = t4.z; b[r + 3] = t4.w;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) b[r] = (r == col - jl) ? 1.0f : 0.0f;
+      }
+      diag_solve16(b, D, TS, jl, rdl);
+#pragma unroll
+      for (int r = 0; r < 16; r += 4)
+        *reinterpret_cast<float4*>(LT + (size_t)col * TS + jl + r) = make_float4(b[r], b[r + 1], b[r + 2], b[r + 3]);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) Lrm[(size_t)(jl + r) * TS + col] = b[r];
     }
     __syncthreads();
     const int nt4 = nbelow >> 2;
@@ -306,123 +437,68 @@ __device__ __forceinline__ void factor64(float* __restrict__ D, float* __restric
       for (int c = 0; c < 4; ++c)
         *reinterpret_cast<float4*>(D + (size_t)(cb + c) * TS + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
     }
-    __syncthreads();
-  }
-}
-
-// Inverse of the factored block.  D as above (L column-major), rdl = 1/diag(L).  Output LT[c'][c] = Linv[c][c'] (the
-// contraction-major operand of both uses: rows-below = raw Linv^T and X = Linv Y), zeros where c < c'; optionally also
-// Lrm[r][c] = Linv[r][c] row-major with zeros above the diagonal (the diagonal X tile).  tmp: >= 1024 floats of scratch.
-__device__ __forceinline__ void invert64(const float* __restrict__ D, const float* __restrict__ rdl, float* __restrict__ LT,
-                                         float* __restrict__ Lrm, float* __restrict__ tmp) {
-  const int tid = threadIdx.x;
-  for (int e = tid * 4; e < TF; e += NTHR * 4) {
-    *reinterpret_cast<float4*>(LT + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    if (Lrm) *reinterpret_cast<float4*>(Lrm + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  }
-  __syncthreads();
-  for (int P = 0; P < 4; ++P) {
-    const int p0 = 16 * P, ncol = p0 + 16;
-    // right-hand side of block row P: R[r][col] = [p0 + r == col] - sum_{k = col}^{p0-1} L[p0+r][k] Linv[k][col]
-    for (int id = tid; id < 16 * ncol; id += NTHR) {
-      const int r = id & 15, col = id >> 4;
-      float acc = (p0 + r == col) ? 1.0f : 0.0f;
-      for (int k = col; k < p0; ++k) acc = fmaf(-D[(size_t)k * TS + p0 + r], LT[(size_t)col * TS + k], acc);
-      tmp[col * 16 + r] = acc;
-    }
-    __syncthreads();
-    if (tid < ncol) {
-      const int col = tid;
-      float b[16];
-#pragma unroll
-      for (int r = 0; r < 16; ++r) b[r] = tmp[col * 16 + r];
-      diag_solve16(b, D, TS, p0, rdl);
-#pragma unroll
-      for (int r = 0; r < 16; r += 4)
-        *reinterpret_cast<float4*>(LT + (size_t)col * TS + p0 + r) = make_float4(b[r], b[r + 1], b[r + 2], b[r + 3]);
-      if (Lrm) {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) Lrm[(size_t)(p0 + r) * TS + col] = b[r];
-      }
-    }
-    __syncthreads();
+    if (nt4 > 0) __syncthreads();
   }
 }
 
 // ---- the factorisation of K_q by 64-column panels -------------------------------------------------------------------------
 // Lg: this CTA's tile-packed triangle in global memory (L tiles column-major).  After panel J: panel tiles I >= J hold the
 // finished columns of the panel ROW-major (zeros above the diagonal), LinvT = L_JJ^-T operand, dgq[64J..] = diag.  hook(J)
-// runs with the panel in place (all threads; it must end with every thread past its last panel read before returning
-// -- the loop issues the CTA barrier).
+// runs with the panel in place (all threads; the loop issues the CTA barrier behind it).
+// Panel update: the m (nTb - J) tiles x 8J chunks of the panel form ONE chunk sequence that is cut into 8 equal ranges, one
+// per warp; a warp walks its range from the last tile to the first (so the tile it shares with its predecessor is flushed
+// late and the one it shares with its successor early) and subtracts each finished segment from the tile, which all threads
+// pre-filled with the generated kernel matrix, in part order (flush_begin / flush_end).
 template <int KERNEL, class HookF>
-__device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* __restrict__ Lg, Sm& s, GCtx& G, int* bad,
+__device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* __restrict__ Lg, Sm& s, WCtx& W, int* bad,
                                                  PhClock& pc, HookF hook) {
   const int tid = threadIdx.x;
   const int nTb = pr.nTb;
   for (int J = 0; J < nTb; ++J) {
     const int m = nTb - J;  // tiles I = J .. nTb-1 of this panel
     // ---- (1) raw panel, column-major per tile: K(I,J) - sum_{K<J} L(I,K) L(J,K)^T ------------------------------------
-    if (J == 0) {
-      for (int ti = 0; ti < m; ++ti) {
-        float* dst = s.panel + (size_t)ti * TF;
-        for (int e = tid * 4; e < TF; e += NTHR * 4) {
-          const int c = e >> 6, i = e & 63;
-          *reinterpret_cast<float4*>(dst + e) = pr.kgen4(c, TS * ti + i, s.ts);
+    if (tid < NW) s.cnt[tid] = 0;
+    for (int ti = 0; ti < m; ++ti) {
+      float* dst = s.panel + (size_t)(J + ti) * TF;
+      for (int e = tid * 4; e < TF; e += NTHR * 4) {
+        const int c = e >> 6, i = e & 63;
+        *reinterpret_cast<float4*>(dst + e) = pr.kgen4(TS * J + c, TS * (J + ti) + i, s.ts);
+      }
+    }
+    __syncthreads();
+    if (J > 0) {
+      const int n = UC * J, U = m * n;  // chunks per tile, chunks of the panel
+      const int lo = (W.w * U) / NW, hi = ((W.w + 1) * U) / NW;
+      if (hi > lo) {
+        for (int ti = (hi - 1) / n; ti >= lo / n; --ti) {
+          const int c0 = (lo > ti * n ? lo : ti * n) - ti * n, c1 = (hi < (ti + 1) * n ? hi : (ti + 1) * n) - ti * n;
+          float acc[8][16];
+          acc_zero(acc);
+          const float* Arow = Lg + (size_t)tri(J + ti, 0) * TF + (size_t)c0 * CH;  // chunk (K, q) of a row of tiles: contiguous
+          const float* Brow = Lg + (size_t)tri(J, 0) * TF + (size_t)c0 * CH;
+          run_chunks<false>(acc, W, c1 - c0,
+                            [&](int c, float* st, uint64_t* bar, int lane) {
+                              if (lane == 0) {
+                                mbar_expect_tx(bar, 2 * CH * 4);
+                                bulk_g2s(st, Arow + (size_t)c * CH, CH * 4, bar);
+                                bulk_g2s(st + CH, Brow + (size_t)c * CH, CH * 4, bar);
+                              }
+                            },
+                            [](int) { return (const float*)nullptr; });
+          const int part = W.w - first_warp_after(U, ti * n);
+          volatile int* cnt = s.cnt + ti;
+          flush_begin(cnt, part);
+          sub_colmajor(s.panel + (size_t)(J + ti) * TF, acc, W.ty, W.tx);
+          flush_end(cnt, part, W.lane);
         }
       }
       __syncthreads();
-    } else {
-      const int nch = 4 * J;  // chunks per tile
-      // split every tile's contraction over sp groups (1, 2 or 4): the split that needs the fewest chunk-times
-      int sp = 1, best = ((m + 3) / 4) * nch;
-      { const int c2 = ((2 * m + 3) / 4) * (nch / 2); if (c2 < best) { best = c2; sp = 2; } }
-      { const int c4 = m * (nch / 4); if (c4 < best) { best = c4; sp = 4; } }
-      const int per = nch / sp, tpr = NGRP / sp;  // chunks per job, tiles per round
-      const int rounds = (m + tpr - 1) / tpr;
-      for (int rd = 0; rd < rounds; ++rd) {
-        const int ti = rd * tpr + G.g / sp, part = G.g % sp;
-        float acc[8][8];
-        acc_zero(acc);
-        if (ti < m) {
-          const int I = J + ti, c0 = part * per;
-          const float* Arow = Lg + (size_t)tri(I, 0) * TF;
-          const float* Brow = Lg + (size_t)tri(J, 0) * TF;
-          run_chunks<false>(acc, G, per,
-                            [&](int c, float* st, uint64_t* bar) {
-                              const size_t off = (size_t)(c0 + c) * CH;  // chunk (K, q) of a row of tiles is contiguous
-                              mbar_expect_tx(bar, 2 * CH * 4);
-                              bulk_g2s(st, Arow + off, CH * 4, bar);
-                              bulk_g2s(st + CH, Brow + off, CH * 4, bar);
-                            },
-                            [](int) { return (const float*)nullptr; });
-        }
-        // the job's partial tile into the group's own stage area (all its copies have landed and been consumed)
-        store_colmajor<1>(G.stg, acc, G.ty, G.tx);
-        __syncthreads();
-        for (int q = 0; q < tpr; ++q) {
-          const int tq = rd * tpr + q;
-          if (tq >= m) break;
-          float* dst = s.panel + (size_t)(J + tq) * TF;
-          const float* src = s.stg + (size_t)(q * sp) * GSTG_F;
-          for (int e = tid * 4; e < TF; e += NTHR * 4) {
-            const int c = e >> 6, i = e & 63;
-            float4 kv = pr.kgen4(TS * J + c, TS * (J + tq) + i, s.ts);
-            for (int p = 0; p < sp; ++p) {
-              const float4 pv = *reinterpret_cast<const float4*>(src + (size_t)p * GSTG_F + e);
-              kv.x -= pv.x; kv.y -= pv.y; kv.z -= pv.z; kv.w -= pv.w;
-            }
-            *reinterpret_cast<float4*>(dst + e) = kv;
-          }
-        }
-        fence_async();  // the stage areas were written by threads; the next job's bulk copies overwrite them
-        __syncthreads();
-      }
     }
     pc.tick(1);
     // ---- (2) diagonal block: factor in place (column-major), invert, publish -------------------------------------------
     float* D = s.panel + (size_t)J * TF;
-    factor64(D, s.dgq + TS * J, s.rdl, pr.T - TS * J, bad);
-    invert64(D, s.rdl, s.linv, nullptr, s.stg);
+    factor_invert64(D, s.dgq + TS * J, s.rdl, pr.T - TS * J, bad, s.linv, s.stg, s.stg + TF);
+    __syncthreads();
     {
       float* gt = Lg + (size_t)tri(J, J) * TF;
       float* tmp = s.stg;  // one tile of scratch: the transposed copy, XOR-swizzled so that both passes are conflict-free
@@ -441,22 +517,20 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
         const int i = e >> 6, c = e & 63;
         D[e] = tmp[i * TS + (c ^ (i & 31))];
       }
+      fence_async();  // the stage areas served as scratch (thread writes); bulk copies overwrite them next
       __syncthreads();
     }
     pc.tick(2);
-    // ---- (3) rows below: L(I,J) = raw(I,J) L_JJ^-T, one tile per group job, operands resident --------------------------
-    for (int rd = 0; rd * NGRP < m - 1; ++rd) {
-      const int ti = 1 + rd * NGRP + G.g;
-      if (ti < m) {
-        float* tile = s.panel + (size_t)(J + ti) * TF;
-        float acc[8][8];
-        acc_zero(acc);
+    // ---- (3) rows below: L(I,J) = raw(I,J) L_JJ^-T, one tile per warp, operands resident ---------------------------------
+    for (int ti = 1 + W.w; ti < m; ti += NW) {
+      float* tile = s.panel + (size_t)(J + ti) * TF;
+      float acc[8][16];
+      acc_zero(acc);
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) mk_chunk(acc, tile + q * CH, s.linv + q * CH, G.ty, G.tx);
-        store_colmajor<1>(Lg + (size_t)tri(J + ti, J) * TF, acc, G.ty, G.tx);
-        group_sync(G.g);  // both warps have read the raw tile
-        store_rowmajor<1>(tile, acc, G.ty, G.tx);
-      }
+      for (int q = 0; q < UC; ++q) mk_chunk(acc, tile + q * CH, s.linv + q * CH, W.ty, W.tx);
+      store_colmajor<1>(Lg + (size_t)tri(J + ti, J) * TF, acc, W.ty, W.tx);
+      __syncwarp();  // the warp has read the whole raw tile
+      store_rowmajor<1>(tile, acc, W.ty, W.tx);
     }
     fence_async();  // the L tiles written above are read by bulk copies from the next panel on
     __syncthreads();
@@ -486,6 +560,47 @@ __device__ __forceinline__ void load_vectors(const Params& P, int p, int b, int 
   }
 }
 
+// out[j] = sum_{l < lim(j)} R[l*ldr + j] * m[l] for j < T (lim = T, or j+1 for a lower-triangular record whose upper part is
+// exact zeros): the two matrix-vector products against the per-sequence prior record (a = L_p^-1 m, alpha = K_p^-1 m).
+// 128 groups of four columns (one 128-bit load per row, a warp reads 512 contiguous bytes) x 2 halves of the row range,
+// sixteen loads in flight per thread; the halves meet in `scratch` (>= 1024 floats).  All 256 threads; TP <= 512.
+__device__ __forceinline__ void matvec_record(const float* __restrict__ R, int ldr, const float* __restrict__ m, int T, bool lower,
+                                              float* __restrict__ out, float* __restrict__ scratch) {
+  const int tid = threadIdx.x, j = 4 * (tid & 127), h = tid >> 7;
+  float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (j < T) {
+    const int lend = lower ? (T < j + 4 ? T : j + 4) : T;
+    const int l0 = h ? lend / 2 : 0, l1 = h ? lend : lend / 2;
+    const float* rp = R + (size_t)l0 * ldr + j;
+    int l = l0;
+    for (; l + 16 <= l1; l += 16) {
+      float4 x[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) x[e] = __ldg(reinterpret_cast<const float4*>(rp + (size_t)e * ldr));
+      rp += (size_t)16 * ldr;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float mv = m[l + e];
+        acc.x = fmaf(x[e].x, mv, acc.x); acc.y = fmaf(x[e].y, mv, acc.y); acc.z = fmaf(x[e].z, mv, acc.z); acc.w = fmaf(x[e].w, mv, acc.w);
+      }
+    }
+    for (; l < l1; ++l) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(rp));
+      rp += ldr;
+      const float mv = m[l];
+      acc.x = fmaf(x.x, mv, acc.x); acc.y = fmaf(x.y, mv, acc.y); acc.z = fmaf(x.z, mv, acc.z); acc.w = fmaf(x.w, mv, acc.w);
+    }
+  }
+  *reinterpret_cast<float4*>(scratch + h * 512 + j) = acc;
+  __syncthreads();
+  if (h == 0 && j < T) {
+    const float4 a = *reinterpret_cast<const float4*>(scratch + j), b = *reinterpret_cast<const float4*>(scratch + 512 + j);
+    *reinterpret_cast<float4*>(out + j) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+  fence_async();  // `scratch` is a stage area: bulk copies overwrite it next
+  __syncthreads();
+}
+
 // ---- forward ---------------------------------------------------------------------------------------------------------------
 template <int KERNEL>
 __global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
@@ -496,14 +611,15 @@ __global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
   const TLay L(d.T_max, d.S);
   Sm s(smem_f, L);
   const int tid = threadIdx.x;
-  GCtx G;
-  G.g = tid >> 6; G.t = tid & 63;
-  { const int lane = tid & 31, w = (tid >> 5) & 1; G.ty = lane & 7; G.tx = (lane >> 3) + 4 * w; }
-  G.stg = s.stg + (size_t)G.g * GSTG_F;
-  G.bar = s.bars + 2 * G.g;
-  G.use0 = G.use1 = 0;
+  WCtx W;
+  W.w = tid >> 5; W.lane = tid & 31;
+  W.ty = W.lane & 7; W.tx = W.lane >> 3;
+  W.stg = s.stg + (size_t)W.w * WSTG_F;
+  W.bar = s.bars + 2 * W.w;
+  W.use0 = W.use1 = 0;
+  W.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
   if (tid == 0) {
-    for (int i = 0; i < 2 * NGRP; ++i) mbar_init(&s.bars[i], 1);
+    for (int i = 0; i < 2 * NW; ++i) mbar_init(&s.bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -535,24 +651,12 @@ __global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
     __syncthreads();
     const Pair<KERNEL> pr(T, P.ell_q[dd], sig, noise);
     const int nTb = pr.nTb;
-    // a = L_p^-1 m from the record (X_p column-major, X(i,k) at rec[k*ldr + i]; coalesced over i)
-    for (int i = tid; i < T; i += NTHR) {
-      float a0 = 0.0f, a1 = 0.0f;
-      int k = 0;
-      for (; k + 8 <= i + 1; k += 8) {
-        float xv[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) xv[e] = __ldg(rec + (size_t)(k + e) * ldr + i);
-#pragma unroll
-        for (int e = 0; e < 8; e += 2) { a0 = fmaf(xv[e], s.mm[k + e], a0); a1 = fmaf(xv[e + 1], s.mm[k + e + 1], a1); }
-      }
-      for (; k <= i; ++k) a0 = fmaf(__ldg(rec + (size_t)k * ldr + i), s.mm[k], a0);
-      aa[i] = a0 + a1;
-    }
+    // a = L_p^-1 m from the record (X_p column-major, X(i,k) at rec[k*ldr + i], exact zeros above the diagonal)
+    matvec_record(rec, ldr, s.mm, T, true, aa, s.stg);
     float ssq = 0.0f;
     __syncthreads();
     pc.tick(0);
-    chol_panels_tile<KERNEL>(pr, Lg, s, G, &bad, pc, [&](int J) {
+    chol_panels_tile<KERNEL>(pr, Lg, s, W, &bad, pc, [&](int J) {
       const int m = nTb - J;
       // z_s += L_q(:, panel J) eps_s(panel J): one row per thread, 128-bit row reads started at a lane-dependent column
       for (int idx = tid; idx < m * TS; idx += NTHR) {
@@ -570,30 +674,46 @@ __global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
           s.zacc[(size_t)sx * TP + TS * J + idx] += a0 + a1;
         }
       }
-      // A(I,J) = sum_{K=J..I} X_p(I,K) L_q(K,J): tiles by decreasing length, dealt boustrophedon to the groups
-      for (int blk = 0; blk * NGRP < m; ++blk) {
-        const int idx = blk * NGRP + ((blk & 1) ? NGRP - 1 - G.g : G.g);
+      // A(I,J) = sum_{K=J..I} X_p(I,K) L_q(K,J): tiles by decreasing length, dealt boustrophedon to the four warp PAIRS; the two
+      // warps of a pair split a tile's contraction in halves and the odd warp hands its partial tile over through the
+      // pair's stage areas (the sums must be complete before they are squared, and there is no destination tile to
+      // accumulate into)
+      const int q = W.w >> 1, odd = W.w & 1;
+      float* parea = s.stg + (size_t)q * TF;
+      for (int blk = 0; blk * 4 < m; ++blk) {
+        const int idx = blk * 4 + ((blk & 1) ? 3 - q : q);
         if (idx >= m) continue;
         const int I = nTb - 1 - idx;
-        float acc[8][8];
+        const int n = UC * (I - J + 1), h = n >> 1;
+        const int c0 = odd ? h : 0, nc = odd ? n - h : h;
+        float acc[8][16];
         acc_zero(acc);
-        const float* Abase = rec + (size_t)TS * I;
-        run_chunks<true>(acc, G, 4 * (I - J + 1),
-                         [&](int c, float* st, uint64_t* bar) {
-                           const float* src = Abase + (size_t)(TS * J + KC * c) * ldr;  // rows k of X_p^T, 64 entries each
-                           mbar_expect_tx(bar, CH * 4);
-#pragma unroll
-                           for (int kk = 0; kk < KC; ++kk) bulk_g2s(st + kk * TS, src + (size_t)kk * ldr, TS * 4, bar);
+        const float* Abase = rec + (size_t)TS * I + (size_t)(TS * J + KC * c0) * ldr;  // rows k of X_p^T, 64 entries each
+        const float* Bbase = s.panel + (size_t)J * TF + (size_t)c0 * CH;
+        run_chunks<true>(acc, W, nc,
+                         [&](int c, float* st, uint64_t* bar, int lane) {
+                           if (lane == 0) mbar_expect_tx(bar, CH * 4);
+                           bulk_g2s(st + lane * TS, Abase + (size_t)(KC * c + lane) * ldr, TS * 4, bar);  // lanes 0..7: one row each
                          },
-                         [&](int c) { return (const float*)(s.panel + (size_t)J * TF + (size_t)c * CH); });
+                         [&](int c) { return Bbase + (size_t)c * CH; });
+        pair_sync(q);  // both warps are done with their stages
+        if (odd) {
+          store_colmajor<1>(parea, acc, W.ty, W.tx);
+          fence_async();  // (the area is overwritten by bulk copies of the next job)
+        }
+        pair_sync(q);
+        if (!odd) {
+          add_colmajor(acc, parea, W.ty, W.tx);
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+          for (int r = 0; r < 8; ++r)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int i = TS * I + mrow(G.ty, r), cc = TS * J + mcol(G.tx, c);
-            const float v = (cc < i && i < T) ? acc[r][c] : 0.0f;
-            ssq = fmaf(v, v, ssq);
-          }
+            for (int c = 0; c < 16; ++c) {
+              const int i = TS * I + mrow(W.ty, r), cc = TS * J + mcol(W.tx, c);
+              const float v = (cc < i && i < T) ? acc[r][c] : 0.0f;
+              ssq = fmaf(v, v, ssq);
+            }
+        }
+        pair_sync(q);  // the partial has been read
       }
     });
     // ---- z out, KL ----------------------------------------------------------------------------------------------------
@@ -634,14 +754,15 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
   const TLay L(d.T_max, d.S);
   Sm s(smem_f, L);
   const int tid = threadIdx.x;
-  GCtx G;
-  G.g = tid >> 6; G.t = tid & 63;
-  { const int lane = tid & 31, w = (tid >> 5) & 1; G.ty = lane & 7; G.tx = (lane >> 3) + 4 * w; }
-  G.stg = s.stg + (size_t)G.g * GSTG_F;
-  G.bar = s.bars + 2 * G.g;
-  G.use0 = G.use1 = 0;
+  WCtx W;
+  W.w = tid >> 5; W.lane = tid & 31;
+  W.ty = W.lane & 7; W.tx = W.lane >> 3;
+  W.stg = s.stg + (size_t)W.w * WSTG_F;
+  W.bar = s.bars + 2 * W.w;
+  W.use0 = W.use1 = 0;
+  W.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
   if (tid == 0) {
-    for (int i = 0; i < 2 * NGRP; ++i) mbar_init(&s.bars[i], 1);
+    for (int i = 0; i < 2 * NW; ++i) mbar_init(&s.bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -651,11 +772,11 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
   const double g_sum = P.g_kl_sum ? *P.g_kl_sum : 1.0;
   float* Lg = P.scratch + (size_t)blockIdx.x * P.scratch_stride;  // L tiles, overwritten in place by X tiles
   float* Cg = Lg + (size_t)L.ntri() * TF;                         // C' tiles
+  float* Vg = Cg + (size_t)L.ntri() * TF;                         // L_JJ^-T of the nT diagonal blocks
   float* u = s.v0;    // g_z
   float* w = s.v1;    // L_q^T g_z
   float* pd = s.v2;   // 1/2 w eps - g/2
   float* cum = s.v3;  // running column sums  sum_{j < i} eps_j X(j, l)
-  float* rdq = s.v4;  // 1 / diag L_q (whole sequence)
   PhClock pc;
   pc.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
   pc.start();
@@ -677,7 +798,7 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
     const Pair<KERNEL> pr(T, lq, sig, noise);
     const int nTb = pr.nTb;
     pc.tick(0);
-    chol_panels_tile<KERNEL>(pr, Lg, s, G, &bad, pc, [&](int J) {
+    chol_panels_tile<KERNEL>(pr, Lg, s, W, &bad, pc, [&](int J) {
       const int m = nTb - J;
       // w(panel J) = L_q(:, panel J)^T g_z: four row-interleaved partial sums per column, summed in a fixed order
       {
@@ -685,54 +806,92 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
         const float* col = s.panel + (size_t)J * TF + c;
         float acc = 0.0f;
         for (int idx = part; idx < m * TS; idx += 4) acc = fmaf(col[(size_t)idx * TS], u[TS * J + idx], acc);
-        s.linv[part * TS + c] = acc;  // (L_JJ^-T is dead once the rows below exist)
+        s.stg[part * TS + c] = acc;  // (the stage areas are idle between the phases)
       }
-      if (tid < TS) rdq[TS * J + tid] = s.rdl[tid];
+      // L_JJ^-T is needed again when X_q = L_q^-1 is formed: keep it in the slot instead of inverting the block twice
+      {
+        float* vg = Vg + (size_t)J * TF;
+        for (int e = tid * 4; e < TF; e += NTHR * 4) *reinterpret_cast<float4*>(vg + e) = *reinterpret_cast<const float4*>(s.linv + e);
+      }
       __syncthreads();
       if (tid < TS) {
-        const float wk = (s.linv[tid] + s.linv[TS + tid]) + (s.linv[2 * TS + tid] + s.linv[3 * TS + tid]);
+        const float wk = (s.stg[tid] + s.stg[TS + tid]) + (s.stg[2 * TS + tid] + s.stg[3 * TS + tid]);
         w[TS * J + tid] = wk;
         pd[TS * J + tid] = 0.5f * wk * s.eps[TS * J + tid] - hg;
       }
+      fence_async();  // the stage area served as scratch (thread writes); bulk copies overwrite it next
     });
     // ---- X_q = L_q^-1 in place, 64-row blocks; C' alongside ----------------------------------------------------------------
     for (int I = 0; I < nTb; ++I) {
-      // L_II (column-major tile) -> shared memory, L_II^-1 as operand (linv) and as the diagonal X tile (panel tile I)
-      float* Dt = s.stg;                // group 0's stage area as the tile, group 1's as invert64's scratch
+      // L_II^-T (kept by the factorisation) -> linv (the operand of X(I,C) = L_II^-1 Y), and transposed -- through an
+      // XOR-swizzled scratch tile, both passes conflict-free -- into panel tile I: the diagonal X tile, row-major
       {
-        const float* src = Lg + (size_t)tri(I, I) * TF;
-        for (int e = tid * 4; e < TF; e += NTHR * 4) *reinterpret_cast<float4*>(Dt + e) = __ldcg(reinterpret_cast<const float4*>(src + e));
-        if (tid < TS) s.rdl[tid] = rdq[TS * I + tid];
+        const float* src = Vg + (size_t)I * TF;
+        for (int e = tid * 4; e < TF; e += NTHR * 4) *reinterpret_cast<float4*>(s.linv + e) = __ldcg(reinterpret_cast<const float4*>(src + e));
+        if (tid < NW) s.cnt[tid] = 0;
       }
       if (tid == 0) bulk_wait_read0();  // the bulk stores of the previous row block have finished reading the panel
       __syncthreads();
-      invert64(Dt, s.rdl, s.linv, s.panel + (size_t)I * TF, s.stg + GSTG_F);
+      {
+        float* tmp = s.stg;
+        for (int e = tid; e < TF; e += NTHR) {
+          const int c = e >> 6, r = e & 63;  // LT[c][r] = Linv[r][c]
+          tmp[r * TS + (c ^ (r & 31))] = s.linv[e];
+        }
+        __syncthreads();
+        float* Xd = s.panel + (size_t)I * TF;
+        for (int e = tid; e < TF; e += NTHR) {
+          const int r = e >> 6, c = e & 63;
+          Xd[e] = tmp[r * TS + (c ^ (r & 31))];
+        }
+      }
       fence_async();                     // stage areas were used as scratch by threads
       __syncthreads();
       pc.tick(6);
-      // off-diagonal tiles C < I:  Y = -sum_{K=C}^{I-1} L(I,K) X(K,C),  X(I,C) = L_II^-1 Y   (longest first: C ascending)
-      for (int blk = 0; blk * NGRP < I; ++blk) {
-        const int C = blk * NGRP + ((blk & 1) ? NGRP - 1 - G.g : G.g);
-        if (C >= I) continue;
-        float acc[8][8];
-        acc_zero(acc);
-        const float* Arow = Lg + (size_t)tri(I, C) * TF;  // L(I,C), L(I,C+1), ... are consecutive tiles
-        run_chunks<false>(acc, G, 4 * (I - C),
-                          [&](int c, float* st, uint64_t* bar) {
-                            const int K = C + (c >> 2), q = c & 3;
-                            mbar_expect_tx(bar, 2 * CH * 4);
-                            bulk_g2s(st, Arow + (size_t)c * CH, CH * 4, bar);
-                            bulk_g2s(st + CH, Lg + (size_t)tri(K, C) * TF + (size_t)q * CH, CH * 4, bar);
-                          },
-                          [](int) { return (const float*)nullptr; });
+      // off-diagonal tiles C < I:  Y(C) = -sum_{K=C}^{I-1} L(I,K) X(K,C).  Tile C has 8 (I-C) chunks; the chunk sequence of the
+      // row block is cut into 8 equal ranges (one per warp, walked from its last tile to its first), segments flushed into
+      // the shared-memory tile in part order -- the scheme of the panel update above
+      if (I > 0) {
+        const int U = UC * I * (I + 1) / 2;
+        const int lo = (W.w * U) / NW, hi = ((W.w + 1) * U) / NW;
+        if (hi > lo) {
+          for (int C = I - 1; C >= 0; --C) {
+            const int off = UC * (C * I - C * (C - 1) / 2), n = UC * (I - C);  // chunks of tiles 0..C-1, of tile C
+            if (off >= hi || off + n <= lo) continue;
+            const int c0 = (lo > off ? lo : off) - off, c1 = (hi < off + n ? hi : off + n) - off;
+            float acc[8][16];
+            acc_zero(acc);
+            const float* Arow = Lg + (size_t)tri(I, C) * TF;  // L(I,C), L(I,C+1), ... are consecutive tiles
+            run_chunks<false>(acc, W, c1 - c0,
+                              [&](int c, float* st, uint64_t* bar, int lane) {
+                                if (lane == 0) {
+                                  const int cc = c0 + c, K = C + cc / UC, qq = cc % UC;
+                                  mbar_expect_tx(bar, 2 * CH * 4);
+                                  bulk_g2s(st, Arow + (size_t)cc * CH, CH * 4, bar);
+                                  bulk_g2s(st + CH, Lg + (size_t)tri(K, C) * TF + (size_t)qq * CH, CH * 4, bar);
+                                }
+                              },
+                              [](int) { return (const float*)nullptr; });
+            const int part = W.w - first_warp_after(U, off);
+            volatile int* cnt = s.cnt + C;
+            float* Y = s.panel + (size_t)C * TF;
+            flush_begin(cnt, part);
+            if (part == 0) store_rowmajor<-1>(Y, acc, W.ty, W.tx);
+            else sub_rowmajor(Y, acc, W.ty, W.tx);
+            flush_end(cnt, part, W.lane);
+          }
+        }
+      }
+      __syncthreads();
+      // X(I,C) = L_II^-1 Y(C), one tile per warp, operands resident
+      for (int C = W.w; C < I; C += NW) {
         float* Y = s.panel + (size_t)C * TF;
-        store_rowmajor<-1>(Y, acc, G.ty, G.tx);
-        group_sync(G.g);
+        float acc[8][16];
         acc_zero(acc);
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) mk_chunk(acc, s.linv + q * CH, Y + q * CH, G.ty, G.tx);
-        group_sync(G.g);  // both warps have read Y
-        store_rowmajor<1>(Y, acc, G.ty, G.tx);
+        for (int q = 0; q < UC; ++q) mk_chunk(acc, s.linv + q * CH, Y + q * CH, W.ty, W.tx);
+        __syncwarp();  // the warp has read all of Y
+        store_rowmajor<1>(Y, acc, W.ty, W.tx);
       }
       fence_async();  // panel tiles (X row block I) are read by the bulk stores below
       __syncthreads();
@@ -764,62 +923,51 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
     __syncthreads();
     // ---- d/d mean: alpha = K_p^-1 m from the record (symmetric: coalesced over k) -------------------------------------------
     const float* __restrict__ kinv = P.prior + (size_t)b * P.prior_stride;
-    for (int k = tid; k < T; k += NTHR) {
-      float a0 = 0.0f, a1 = 0.0f;
-      int l = 0;
-      for (; l + 8 <= T; l += 8) {
-        float xv[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) xv[e] = __ldg(kinv + (size_t)(l + e) * ldr + k);
-#pragma unroll
-        for (int e = 0; e < 8; e += 2) { a0 = fmaf(xv[e], s.mm[l + e], a0); a1 = fmaf(xv[e + 1], s.mm[l + e + 1], a1); }
-      }
-      for (; l < T; ++l) a0 = fmaf(__ldg(kinv + (size_t)l * ldr + k), s.mm[l], a0);
-      P.g_mean[(size_t)(r0 + k) * d.D + dd] = g * (a0 + a1) + u[k];
-    }
+    matvec_record(kinv, ldr, s.mm, T, false, s.v4, s.stg);
+    for (int k = tid; k < T; k += NTHR) P.g_mean[(size_t)(r0 + k) * d.D + dd] = g * s.v4[k] + u[k];
     __syncthreads();
     pc.tick(9);
     // ---- contraction: sum_{k != l} dK_kl (hg K_p^-1 + X_q^T C')_kl, tiles by shell max(kt,lt) (longest first), boustrophedon --
     double total = 0.0;
-    for (int blk = 0; blk * NGRP < nTb * nTb; ++blk) {
-      const int n = blk * NGRP + ((blk & 1) ? NGRP - 1 - G.g : G.g);
+    for (int blk = 0; blk * NW < nTb * nTb; ++blk) {
+      const int n = blk * NW + ((blk & 1) ? NW - 1 - W.w : W.w);
       if (n >= nTb * nTb) continue;
       int mx = (int)sqrtf((float)n);
       while ((mx + 1) * (mx + 1) <= n) ++mx;
       while (mx * mx > n) --mx;
       const int pos = n - mx * mx;
       const int kt = pos <= mx ? mx : pos - mx - 1, lt = pos <= mx ? pos : mx;
-      float acc[8][8];
+      float acc[8][16];
       acc_zero(acc);
-      run_chunks<false>(acc, G, 4 * (nTb - mx),
-                        [&](int c, float* st, uint64_t* bar) {
-                          const int Ib = mx + (c >> 2), q = c & 3;
-                          mbar_expect_tx(bar, 2 * CH * 4);
-                          bulk_g2s(st, Lg + (size_t)tri(Ib, kt) * TF + (size_t)q * CH, CH * 4, bar);
-                          bulk_g2s(st + CH, Cg + (size_t)tri(Ib, lt) * TF + (size_t)q * CH, CH * 4, bar);
+      run_chunks<false>(acc, W, UC * (nTb - mx),
+                        [&](int c, float* st, uint64_t* bar, int lane) {
+                          if (lane == 0) {
+                            const int Ib = mx + c / UC, qq = c % UC;
+                            mbar_expect_tx(bar, 2 * CH * 4);
+                            bulk_g2s(st, Lg + (size_t)tri(Ib, kt) * TF + (size_t)qq * CH, CH * 4, bar);
+                            bulk_g2s(st + CH, Cg + (size_t)tri(Ib, lt) * TF + (size_t)qq * CH, CH * 4, bar);
+                          }
                         },
                         [](int) { return (const float*)nullptr; });
-      float4 kq[8][2];
+      float tl[16];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int k = TS * kt + mrow(G.ty, r), l0 = TS * lt + 4 * G.tx;
-        kq[r][0] = __ldg(reinterpret_cast<const float4*>(kinv + (size_t)k * ldr + l0));
-        kq[r][1] = __ldg(reinterpret_cast<const float4*>(kinv + (size_t)k * ldr + l0 + 32));
-      }
-      float tl[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) tl[c] = s.ts[TS * lt + mcol(G.tx, c)];
+      for (int c = 0; c < 16; ++c) tl[c] = s.ts[TS * lt + mcol(W.tx, c)];
       float part = 0.0f;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const int k = TS * kt + mrow(G.ty, r);
+        const int k = TS * kt + mrow(W.ty, r);
         const float tk = s.ts[k];
-        const float kv[8] = {kq[r][0].x, kq[r][0].y, kq[r][0].z, kq[r][0].w, kq[r][1].x, kq[r][1].y, kq[r][1].z, kq[r][1].w};
+        const float* krow = kinv + (size_t)k * ldr + TS * lt + 4 * W.tx;
+        float4 kq[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int l = TS * lt + mcol(G.tx, c);
+        for (int j = 0; j < 4; ++j) kq[j] = __ldg(reinterpret_cast<const float4*>(krow + 16 * j));
+        const float kv[16] = {kq[0].x, kq[0].y, kq[0].z, kq[0].w, kq[1].x, kq[1].y, kq[1].z, kq[1].w,
+                              kq[2].x, kq[2].y, kq[2].z, kq[2].w, kq[3].x, kq[3].y, kq[3].z, kq[3].w};
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int l = TS * lt + mcol(W.tx, c);
           const float dt = tk - tl[c];
-          const float dk = pr.kc.dell(dt, pr.kc.val_fast(dt));
+          const float dk = pr.kc.dval_fast(dt);
           const float wv = fmaf(hg, kv[c], acc[r][c]);
           part = fmaf((k < T && l < T && k != l) ? wv : 0.0f, dk, part);
         }
@@ -850,13 +998,14 @@ bool tile_tier_supports(const GpklDesc& d, bool backward) {
 
 size_t tile_slot_floats(const GpklDesc& d) {
   const TLay L(d.T_max, d.S);
-  return 2 * (size_t)L.ntri() * TF;
+  return (2 * (size_t)L.ntri() + (size_t)L.nT) * TF;  // L / X tiles, C' tiles, L_JJ^-T of the diagonal blocks
 }
 
 // The shared-prior kernel of the tile tier; the caller has launched the block tier's pre-pass (records in P.prior) before
 // it and launches the per-pair kernel (skip_if_shared) behind it.
 cudaError_t launch_tile(const Params& P, bool backward, cudaStream_t st) {
   const size_t smem = tile_smem_bytes(P.d);
+  if (!P.scratch || P.scratch_stride < tile_slot_floats(P.d)) return cudaErrorInvalidValue;
   const int npairs = P.d.B * P.d.D;
   const int grid = npairs < kNumSMs ? npairs : kNumSMs;
   void (*kern)(Params);
