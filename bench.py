@@ -20,6 +20,12 @@ for _p in (ROOT, os.path.join(ROOT, "gp-vae_b200")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+# The CPU legs (--impl reference, cpu_baseline) use every host thread.  torchrun exports OMP_NUM_THREADS=1 to its ranks; the
+# thread count has to be fixed through the environment BEFORE torch is imported: torch.set_num_threads() after the
+# import makes this image's oneMKL fail inside the LU inverse at T = 512 ("Parameter 6 was incorrect on entry to DLASWP").
+if "--impl" in sys.argv and "reference" in sys.argv and os.environ.get("RANK", "0") == "0":
+    os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import torch  # noqa: E402
 
 # BASELINE.json configs (per-GPU batch).  c3 is the 8-GPU config: 512 sequences sharded 64 per GPU.
@@ -116,35 +122,62 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def _cpu_sample(orc, w, Bs, Ds, seed=1234):
+    """A bounded sample of the workload for the CPU legs: Bs sequences x the first Ds latent dims (every (sequence, dim)
+    pair is independent, so seq/s of the full width is the sample's pairs/s / D)."""
+    case = orc.synthetic_batch(Bs, w["D"], w["T"], 1, seed=seed)
+    if Ds < w["D"]:
+        case = dict(case)
+        for k in ("mean", "g_z"):
+            case[k] = case[k][:, :Ds].contiguous()
+        case["eps"] = case["eps"][:, :Ds].contiguous()
+        case["ell_q"], case["ell_p"] = case["ell_q"][:Ds].contiguous(), case["ell_p"][:Ds].contiguous()
+    return case
+
+
+def _cpu_call(orc, case, w):
+    orc.gp_prior_kl_grads(case["mean"], case["times"], case["lengths"], case["ell_q"], case["ell_p"], case["eps"],
+                          case["g_z"], kernel=w["kernel"])
+
+
+def _cpu_plan(orc, w, per_call_budget_s):
+    """Probe with a tiny sample (2 pairs at large T), then size (Bs, Ds) so that one call takes about per_call_budget_s."""
+    T, D, B = w["T"], w["D"], w["B"]
+    Bs, Ds = (1, min(D, 2)) if T >= 128 else (min(B, 2), D)
+    case = _cpu_sample(orc, w, Bs, Ds)
+    t0 = time.perf_counter()
+    _cpu_call(orc, case, w)
+    per_pair = max(time.perf_counter() - t0, 1e-4) / (Bs * Ds)
+    pairs = max(1, int(per_call_budget_s / per_pair))
+    pairs = min(pairs, max(1, (1 << 28) // (T * T)))  # the float64 oracle keeps ~10 T x T matrices per pair alive
+    if pairs >= D:
+        Ds, Bs = D, max(1, min(B, pairs // D))
+    else:
+        Ds, Bs = max(1, pairs), 1
+    return Bs, Ds
+
+
 def cpu_port_throughput(w, budget_s, threads, seed=1234):
     """Oracle (float64 port of the reference's algorithm) forward+backward on a bounded sample of the
     workload, on the host cores.  Returns (seq/s, description of the sample)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import gp_kl_oracle as orc
-    torch.set_num_threads(threads)
     T, D = w["T"], w["D"]
-    # size the sample from a quick probe so the whole measurement stays near budget_s
-    Bs = max(1, min(w["B"], 8 if T <= 64 else 1))  # long sequences: probe with one sequence (D pairs)
-    case = orc.synthetic_batch(Bs, D, T, 1, seed=seed)
-    t0 = time.perf_counter()
-    orc.gp_prior_kl_grads(case["mean"], case["times"], case["lengths"], case["ell_q"], case["ell_p"], case["eps"],
-                          case["g_z"], kernel=w["kernel"])
-    probe = max(time.perf_counter() - t0, 1e-4)
-    per_seq = probe / Bs
-    Bs = int(max(1, min(w["B"], (budget_s / 4.0) / per_seq)))
-    case = orc.synthetic_batch(Bs, D, T, 1, seed=seed)
+    Bs, Ds = _cpu_plan(orc, w, budget_s / 6.0)
+    case = _cpu_sample(orc, w, Bs, Ds, seed)
     times = []
     t_start = time.perf_counter()
     for _ in range(5):
         t0 = time.perf_counter()
-        orc.gp_prior_kl_grads(case["mean"], case["times"], case["lengths"], case["ell_q"], case["ell_p"], case["eps"],
-                              case["g_z"], kernel=w["kernel"])
+        _cpu_call(orc, case, w)
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_start > budget_s and len(times) >= 2:
             break
     times.sort()
     med = times[len(times) // 2]
-    return Bs / med, "%d of %d sequences (T=%d, D=%d), %d reps, median" % (Bs, w["B"], T, D, len(times)), Bs, med
+    val = Bs * (Ds / float(D)) / med
+    return val, "%d sequence(s) x %d of %d latent dims (T=%d) of the %d-sequence batch, %d reps, median" % (
+        Bs, Ds, D, T, w["B"], len(times)), Bs, med
 
 
 def run_reference(args, w, rank, world):
@@ -154,29 +187,22 @@ def run_reference(args, w, rank, world):
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import gp_kl_oracle as orc
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = torch.get_num_threads()
     T, D = w["T"], w["D"]
-    case = orc.synthetic_batch(min(w["B"], 4), D, T, 1, seed=1234)
-    t0 = time.perf_counter()
-    orc.gp_prior_kl_grads(case["mean"], case["times"], case["lengths"], case["ell_q"], case["ell_p"], case["eps"],
-                          case["g_z"], kernel=w["kernel"])
-    per_seq = max(time.perf_counter() - t0, 1e-4) / min(w["B"], 4)
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    Bs = int(max(1, min(w["B"], budget / per_seq)))
-    case = orc.synthetic_batch(Bs, D, T, 1, seed=1234)
+    budget = 100.0 / max(1, args.steps + args.warmup)
+    Bs, Ds = _cpu_plan(orc, w, budget)
+    case = _cpu_sample(orc, w, Bs, Ds)
 
     def step():
-        orc.gp_prior_kl_grads(case["mean"], case["times"], case["lengths"], case["ell_q"], case["ell_p"], case["eps"],
-                              case["g_z"], kernel=w["kernel"])
+        _cpu_call(orc, case, w)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
-    val = Bs / dt
-    sample = "%d of %d sequences per step" % (Bs, w["B"])
+    val = Bs * (Ds / float(D)) / dt
+    sample = "%d sequence(s) x %d of %d latent dims per step (of %d sequences; pairs are independent)" % (Bs, Ds, D, w["B"])
     print(json.dumps({
         "impl": "reference", "metric": "GP-prior KL fwd+bwd sequences/s", "value": val, "unit": "sequences/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -207,7 +233,7 @@ def verbatim_reference_timing():
             orc.gp_prior_kl_grads(*a)
             ts.append(time.perf_counter() - t0)
         ts.sort()
-        rec["oracle_port_same_config_this_box"] = {"value": 5 / ts[2], "unit": "sequences/s", "cores": os.cpu_count() or 1}
+        rec["oracle_port_same_config_this_box"] = {"value": 5 / ts[2], "unit": "sequences/s", "cores": torch.get_num_threads()}
     except Exception:
         pass
     return rec
@@ -417,6 +443,15 @@ def elbo_step_bench(gpkl, w, dev, world, steps=3, warmup=2):
                                           "Bernoulli recon + KL, Adam(2e-4)" % (F, D, D, F)}
 
 
+_T0 = time.perf_counter()
+
+
+def note(msg):
+    """Progress line on stderr (the JSON line on stdout stays the only stdout output)."""
+    sys.stderr.write("[bench %7.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -478,6 +513,7 @@ def main():
         if i >= 2:
             best_peak = max(best_peak, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
 
+    note("FP32 peak %.1f TFLOP/s; timing %s" % (best_peak, args.workload))
     # ---- device-resident timed region ----------------------------------------------------------------
     m = measure_device(gpkl, L, w, dev, args.steps, warmup, cfg, world=world, flush=flush, grad_ell_p=args.grad_ell_p)
     case = m["case"]
@@ -495,6 +531,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    note("device-resident: %.2f ms/step" % ms_per_step)
     # ---- end-to-end: host (pinned) buffers in, EVERY result out (z, KL per pair, d/d mean, d/d ell), copies timed -----
     total_T = case["mean"].shape[0]
     hs = gpkl.HostStep(B, D, T, 1, total_T, kernel=w["kernel"], grad_ell_p=args.grad_ell_p, tier=args.tier,
@@ -535,6 +572,7 @@ def main():
     e2e_val = B * world / (float(t2) / n_e2e * 1e-3)
     del hs
 
+    note("end to end: %.2f ms/step" % (float(t2) / n_e2e))
     # ---- roofline of the dominant kernel (backward) -------------------------------------------------
     peaks = {}
     try:
@@ -573,6 +611,7 @@ def main():
             out["elbo_step"] = elbo_step_bench(gpkl, w, dev, world)
         except Exception as ex:  # never lose the headline line to the auxiliary measurement
             out["elbo_step"] = {"error": repr(ex)[:200]}
+        note("elbo step done")
     # ---- secondary workloads (N=1): the other single-GPU BASELINE configs, eager and CUDA-graph replay ---------------
     if world == 1 and not args.no_secondary:
         sec = []
@@ -592,6 +631,7 @@ def main():
                     row["roofline"]["forward_frac"] = rf["forward"]["frac"]
                     row["roofline"]["forward_launch_ms"] = rf["forward"]["launch_ms"]
             sec.append(row)
+            note("secondary %s done" % name)
         out["secondary"] = sec
     # ---- short T-sweep (N=1): FP32 fraction of the forward / backward kernels at T >= 128 --------------------------------
     if world == 1 and not args.no_sweep:
@@ -628,10 +668,12 @@ def main():
                           "fwd_model_frac": pairs * ff / (fm * 1e-3) / 1e12 / best_peak,
                           "bwd_model_frac": pairs * fb / (bm * 1e-3) / 1e12 / best_peak})
         out["roofline"]["sweep"] = sweep
+        note("T sweep done")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        val, sample, _, _ = cpu_port_throughput(w, args.cpu_budget, os.cpu_count() or 1)
-        out["cpu_baseline"] = {"value": val, "unit": "sequences/s", "cores": os.cpu_count() or 1, "kind": "port",
+        val, sample, _, _ = cpu_port_throughput(w, args.cpu_budget, torch.get_num_threads())
+        out["cpu_baseline"] = {"value": val, "unit": "sequences/s", "cores": torch.get_num_threads(), "kind": "port",
                                "sample": sample}
+        note("cpu baseline done")
         vb = verbatim_reference_timing()
         if vb is not None:
             out["cpu_baseline"]["verbatim"] = vb
