@@ -226,13 +226,17 @@ __device__ __forceinline__ void sub_rowmajor(float* __restrict__ dst, const floa
 // Staged contraction of one job: n chunks; issue(c, stage, bar) is executed by lanes 0..7 of the warp (lane passed in) and
 // starts the bulk copies of chunk c into `stage` (A chunk at stage, B chunk at stage + CH), lane 0 arming `bar` with their
 // byte count.  B_RES: the B operand is resident in shared memory, bres(c) returns its chunk.
-template <bool B_RES, class IssueF, class BresF>
-__device__ __forceinline__ void run_chunks(float (&acc)[8][16], WCtx& W, int n, IssueF issue, BresF bres) {
+template <class IssueF>
+__device__ __forceinline__ void prime_chunks(WCtx& W, int n, IssueF issue) {
   if (W.lane < 8) {
     if (n > 0) issue(0, W.stg, &W.bar[0], W.lane);
     if (n > 1) issue(1, W.stg + STAGE_F, &W.bar[1], W.lane);
   }
   __syncwarp();
+}
+template <bool B_RES, class IssueF, class BresF>
+__device__ __forceinline__ void run_chunks(float (&acc)[8][16], WCtx& W, int n, IssueF issue, BresF bres, bool primed = false) {
+  if (!primed) prime_chunks(W, n, issue);
   for (int c = 0; c < n; ++c) {
     const int s = c & 1;
     long long t0 = 0, t1 = 0, t2 = 0;
@@ -255,7 +259,7 @@ __device__ __forceinline__ void run_chunks(float (&acc)[8][16], WCtx& W, int n, 
 // exclusive access to the tile) through a shared-memory counter per tile.  Every lane calls both.
 __device__ __forceinline__ void flush_begin(volatile int* cnt, int part) {
   if (part > 0) {
-    while (*cnt < part) {}
+    while (*cnt < part) __nanosleep(40);  // (a tight spin of up to seven warps on one word starves the flushing warp's loads)
   }
   __threadfence_block();
 }
@@ -271,6 +275,18 @@ __device__ __forceinline__ int first_warp_after(int U, int off) {
   while (((w + 1) * U) / NW <= off) ++w;
   return w;
 }
+// Chunk ranges when warps 6 and 7 (the "diagonal team") join a phase late: they get `st` chunks each at the END of the
+// sequence, warps 0..5 share the rest evenly.  Range of warp w is [team_bound(w), team_bound(w + 1)).
+__device__ __forceinline__ int team_bound(int U, int st, int w) {
+  const int R = U - 2 * st;
+  return w <= 6 ? (w * R) / 6 : (w == 7 ? R + st : U);
+}
+__device__ __forceinline__ int team_first_after(int U, int st, int off) {
+  int w = 0;
+  while (team_bound(U, st, w + 1) <= off) ++w;
+  return w;
+}
+__device__ __forceinline__ void team_sync() { asm volatile("bar.sync 5, 64;" ::: "memory"); }
 
 // Phase clock (developer aid, tools/tile_trace.py): thread 0 of CTA 0 accumulates the cycles between ticks into
 // dbg[48 + k]; a no-op (NULL) for every other thread and whenever no trace buffer is set.
@@ -345,22 +361,26 @@ struct Pair {
 //   (2) rows below the diagonal block are solved one per thread, and AT THE SAME TIME other threads solve the inverse's
 //       block row,  Linv[P, :] = L_PP^-1 [R | I]  (one column per thread)
 //   (3) the trailing columns are updated in 4 x 4 tiles.
+// TEAM: the routine is run by warps 6 and 7 alone (64 threads, named barrier 5) while the other warps update the panel.
+template <bool TEAM>
 __device__ __forceinline__ void factor_invert64(float* __restrict__ D, float* __restrict__ dgl, float* __restrict__ rdl, int Tl,
                                                 int* bad, float* __restrict__ LT, float* __restrict__ Lrm,
                                                 float* __restrict__ tmpR) {
-  const int tid = threadIdx.x;
-  for (int e = tid * 4; e < TF; e += NTHR * 4) {
+  constexpr int NT = TEAM ? 64 : NTHR;
+  const int tid = TEAM ? (int)threadIdx.x - (NTHR - 64) : (int)threadIdx.x;
+  auto sync = [] { if (TEAM) team_sync(); else __syncthreads(); };
+  for (int e = tid * 4; e < TF; e += NT * 4) {
     *reinterpret_cast<float4*>(LT + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     *reinterpret_cast<float4*>(Lrm + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   }
-  __syncthreads();
+  sync();
   for (int P = 0; P < 4; ++P) {
     const int jl = 16 * P;
     if (tid < 32) {
       diag_factor<false>(D, TS, jl, Tl, D + (size_t)jl * TS, TS, dgl, rdl, bad);
     } else {
       // R[r][col] = -sum_{k = col..jl-1} L[jl + r][k] Linv[k][col], col < jl: 4 row groups x (jl/4) column groups
-      for (int id = tid - 32; id < jl; id += NTHR - 32) {
+      for (int id = tid - 32; id < jl; id += NT - 32) {
         const int r4 = id & 3, c4 = id >> 2;
         float acc[4][4];
 #pragma unroll
@@ -381,7 +401,7 @@ __device__ __forceinline__ void factor_invert64(float* __restrict__ D, float* __
           *reinterpret_cast<float4*>(tmpR + (size_t)(4 * c4 + c) * 16 + 4 * r4) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
       }
     }
-    __syncthreads();
+    sync();
     const int nbelow = TS - jl - 16;
     if (tid < nbelow) {
       const int i = jl + 16 + tid;
@@ -391,8 +411,11 @@ __device__ __forceinline__ void factor_invert64(float* __restrict__ D, float* __
       diag_solve16(b, D, TS, jl, rdl);
 #pragma unroll
       for (int c = 0; c < 16; ++c) D[(size_t)(jl + c) * TS + i] = b[c];
-    } else if (tid >= 64 && tid < 64 + jl + 16) {
-      const int col = tid - 64;
+    }
+    // (with 256 threads the two solves run side by side on different threads; the team of 64 does them one after the other)
+    const int ctid = TEAM ? tid : tid - 64;
+    if (ctid >= 0 && ctid < jl + 16) {
+      const int col = ctid;
       float b[16];
       if (col < jl) {
 #pragma unroll
@@ -411,9 +434,9 @@ __device__ __forceinline__ void factor_invert64(float* __restrict__ D, float* __
 #pragma unroll
       for (int r = 0; r < 16; ++r) Lrm[(size_t)(jl + r) * TS + col] = b[r];
     }
-    __syncthreads();
+    sync();
     const int nt4 = nbelow >> 2;
-    for (int id = tid; id < nt4 * nt4; id += NTHR) {
+    for (int id = tid; id < nt4 * nt4; id += NT) {
       const int rt = id / nt4, ct = id - rt * nt4;
       if (rt < ct) continue;
       const int rb = jl + 16 + 4 * rt, cb = jl + 16 + 4 * ct;
@@ -437,26 +460,72 @@ __device__ __forceinline__ void factor_invert64(float* __restrict__ D, float* __
       for (int c = 0; c < 4; ++c)
         *reinterpret_cast<float4*>(D + (size_t)(cb + c) * TS + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
     }
-    if (nt4 > 0) __syncthreads();
+    if (nt4 > 0) sync();
   }
+}
+
+// Publish the factored diagonal block: the global L tile (column-major, zeros above the diagonal) and, in place, the
+// ROW-major copy (zeros above the diagonal) -- the transposition goes through an XOR-swizzled scratch tile so that both
+// passes are conflict-free.  Thread set as factor_invert64.
+template <bool TEAM>
+__device__ __forceinline__ void publish_diag(float* __restrict__ D, float* __restrict__ gt, float* __restrict__ tmp) {
+  constexpr int NT = TEAM ? 64 : NTHR;
+  const int tid = TEAM ? (int)threadIdx.x - (NTHR - 64) : (int)threadIdx.x;
+  for (int e = tid * 4; e < TF; e += NT * 4) {
+    const int c = e >> 6, i = e & 63;
+    const float4 d4 = *reinterpret_cast<const float4*>(D + e);
+    const float o[4] = {i >= c ? d4.x : 0.0f, i + 1 >= c ? d4.y : 0.0f, i + 2 >= c ? d4.z : 0.0f, i + 3 >= c ? d4.w : 0.0f};
+    *reinterpret_cast<float4*>(gt + e) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  for (int e = tid; e < TF; e += NT) {
+    const int c = e >> 6, i = e & 63;
+    tmp[i * TS + (c ^ (i & 31))] = (i >= c) ? D[e] : 0.0f;
+  }
+  if (TEAM) team_sync(); else __syncthreads();
+  for (int e = tid; e < TF; e += NT) {
+    const int i = e >> 6, c = e & 63;
+    D[e] = tmp[i * TS + (c ^ (i & 31))];
+  }
+  fence_async();  // the scratch is a stage area (thread writes); bulk copies overwrite it next
+  if (TEAM) team_sync(); else __syncthreads();
 }
 
 // ---- the factorisation of K_q by 64-column panels -------------------------------------------------------------------------
 // Lg: this CTA's tile-packed triangle in global memory (L tiles column-major).  After panel J: panel tiles I >= J hold the
 // finished columns of the panel ROW-major (zeros above the diagonal), LinvT = L_JJ^-T operand, dgq[64J..] = diag.  hook(J)
 // runs with the panel in place (all threads; the loop issues the CTA barrier behind it).
-// Panel update: the m (nTb - J) tiles x 8J chunks of the panel form ONE chunk sequence that is cut into 8 equal ranges, one
-// per warp; a warp walks its range from the last tile to the first (so the tile it shares with its predecessor is flushed
-// late and the one it shares with its successor early) and subtracts each finished segment from the tile, which all threads
-// pre-filled with the generated kernel matrix, in part order (flush_begin / flush_end).
+// Panel update: a tile's 8J chunks (64 x 64 x 8 contraction steps each) are dealt to the warps as contiguous ranges of ONE
+// chunk sequence; a warp walks its range from the last tile to the first (so the tile it shares with its predecessor is
+// flushed late and the one it shares with its successor early) and subtracts each finished segment from the tile, which
+// all threads pre-filled with the generated kernel matrix, in part order (flush_begin / flush_end).
+// The diagonal tile is updated first, by all warps; then warps 6-7 factor and invert it (the serial chain of the panel,
+// ~20 K cycles) WHILE the other warps update the tiles below it, and join them for a smaller share when they are done.
+constexpr int kDiagChunks = 10;  // the team's factor + invert + publish, in units of one warp's chunk time (~2.3 K cycles)
+
 template <int KERNEL, class HookF>
 __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* __restrict__ Lg, Sm& s, WCtx& W, int* bad,
                                                  PhClock& pc, HookF hook) {
   const int tid = threadIdx.x;
   const int nTb = pr.nTb;
+  const float* Arow = nullptr;  // operands of the current segment (bulk-copy sources)
+  const float* Brow = nullptr;
+  auto issue = [&](int c, float* st, uint64_t* bar, int lane) {
+    if (lane == 0) {
+      mbar_expect_tx(bar, 2 * CH * 4);
+      bulk_g2s(st, Arow + (size_t)c * CH, CH * 4, bar);
+      bulk_g2s(st + CH, Brow + (size_t)c * CH, CH * 4, bar);
+    }
+  };
+  auto nobres = [](int) { return (const float*)nullptr; };
   for (int J = 0; J < nTb; ++J) {
     const int m = nTb - J;  // tiles I = J .. nTb-1 of this panel
-    // ---- (1) raw panel, column-major per tile: K(I,J) - sum_{K<J} L(I,K) L(J,K)^T ------------------------------------
+    const int n = UC * J;   // chunks per tile
+    // ---- (1a) diagonal tile: K(J,J) - sum_{K<J} L(J,K) L(J,K)^T, all warps -------------------------------------------------
+    const int dlo = (W.w * n) / NW, dhi = ((W.w + 1) * n) / NW;
+    if (dhi > dlo) {  // the first copies fly while the kernel matrix is generated
+      Arow = Brow = Lg + (size_t)tri(J, 0) * TF + (size_t)dlo * CH;
+      prime_chunks(W, dhi - dlo, issue);
+    }
     if (tid < NW) s.cnt[tid] = 0;
     for (int ti = 0; ti < m; ++ti) {
       float* dst = s.panel + (size_t)(J + ti) * TF;
@@ -466,58 +535,55 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
       }
     }
     __syncthreads();
-    if (J > 0) {
-      const int n = UC * J, U = m * n;  // chunks per tile, chunks of the panel
-      const int lo = (W.w * U) / NW, hi = ((W.w + 1) * U) / NW;
+    pc.tick(11);
+    if (dhi > dlo) {
+      float acc[8][16];
+      acc_zero(acc);
+      run_chunks<false>(acc, W, dhi - dlo, issue, nobres, true);
+      pc.tick(12);
+      const int part = W.w - first_warp_after(n, 0);
+      volatile int* cnt = s.cnt;
+      flush_begin(cnt, part);
+      sub_colmajor(s.panel + (size_t)J * TF, acc, W.ty, W.tx);
+      flush_end(cnt, part, W.lane);
+      pc.tick(13);
+    }
+    if (J > 0) __syncthreads();
+    pc.tick(1);
+    // ---- (1b) + (2): the tiles below the diagonal one || the diagonal block factored, inverted, published ---------------------
+    float* D = s.panel + (size_t)J * TF;
+    float* gdiag = Lg + (size_t)tri(J, J) * TF;
+    const bool team = J > 0 && m > 1;
+    if (!team) {
+      factor_invert64<false>(D, s.dgq + TS * J, s.rdl, pr.T - TS * J, bad, s.linv, s.stg, s.stg + TF);
+      __syncthreads();
+      publish_diag<false>(D, gdiag, s.stg);
+    } else {
+      const int U = (m - 1) * n;  // chunks of the tiles below the diagonal one
+      int st = (U + 2 * kDiagChunks) / NW - kDiagChunks;  // the team's share once it has finished the diagonal block
+      if (st < 0) st = 0;
+      if (W.w >= 6) {
+        float* mine = s.stg + (size_t)6 * WSTG_F;  // the team's own stage areas (one tile) as scratch; panel tile 0 is free (J > 0)
+        factor_invert64<true>(D, s.dgq + TS * J, s.rdl, pr.T - TS * J, bad, s.linv, s.panel, mine);
+        team_sync();
+        publish_diag<true>(D, gdiag, mine);
+      }
+      const int lo = team_bound(U, st, W.w), hi = team_bound(U, st, W.w + 1);
       if (hi > lo) {
         for (int ti = (hi - 1) / n; ti >= lo / n; --ti) {
           const int c0 = (lo > ti * n ? lo : ti * n) - ti * n, c1 = (hi < (ti + 1) * n ? hi : (ti + 1) * n) - ti * n;
           float acc[8][16];
           acc_zero(acc);
-          const float* Arow = Lg + (size_t)tri(J + ti, 0) * TF + (size_t)c0 * CH;  // chunk (K, q) of a row of tiles: contiguous
-          const float* Brow = Lg + (size_t)tri(J, 0) * TF + (size_t)c0 * CH;
-          run_chunks<false>(acc, W, c1 - c0,
-                            [&](int c, float* st, uint64_t* bar, int lane) {
-                              if (lane == 0) {
-                                mbar_expect_tx(bar, 2 * CH * 4);
-                                bulk_g2s(st, Arow + (size_t)c * CH, CH * 4, bar);
-                                bulk_g2s(st + CH, Brow + (size_t)c * CH, CH * 4, bar);
-                              }
-                            },
-                            [](int) { return (const float*)nullptr; });
-          const int part = W.w - first_warp_after(U, ti * n);
-          volatile int* cnt = s.cnt + ti;
+          Arow = Lg + (size_t)tri(J + 1 + ti, 0) * TF + (size_t)c0 * CH;  // chunk (K, q) of a row of tiles: contiguous
+          Brow = Lg + (size_t)tri(J, 0) * TF + (size_t)c0 * CH;
+          run_chunks<false>(acc, W, c1 - c0, issue, nobres);
+          const int part = W.w - team_first_after(U, st, ti * n);
+          volatile int* cnt = s.cnt + 1 + ti;
           flush_begin(cnt, part);
-          sub_colmajor(s.panel + (size_t)(J + ti) * TF, acc, W.ty, W.tx);
+          sub_colmajor(s.panel + (size_t)(J + 1 + ti) * TF, acc, W.ty, W.tx);
           flush_end(cnt, part, W.lane);
         }
       }
-      __syncthreads();
-    }
-    pc.tick(1);
-    // ---- (2) diagonal block: factor in place (column-major), invert, publish -------------------------------------------
-    float* D = s.panel + (size_t)J * TF;
-    factor_invert64(D, s.dgq + TS * J, s.rdl, pr.T - TS * J, bad, s.linv, s.stg, s.stg + TF);
-    __syncthreads();
-    {
-      float* gt = Lg + (size_t)tri(J, J) * TF;
-      float* tmp = s.stg;  // one tile of scratch: the transposed copy, XOR-swizzled so that both passes are conflict-free
-      for (int e = tid * 4; e < TF; e += NTHR * 4) {
-        const int c = e >> 6, i = e & 63;
-        const float4 d4 = *reinterpret_cast<const float4*>(D + e);
-        const float o[4] = {i >= c ? d4.x : 0.0f, i + 1 >= c ? d4.y : 0.0f, i + 2 >= c ? d4.z : 0.0f, i + 3 >= c ? d4.w : 0.0f};
-        *reinterpret_cast<float4*>(gt + e) = make_float4(o[0], o[1], o[2], o[3]);
-      }
-      for (int e = tid; e < TF; e += NTHR) {
-        const int c = e >> 6, i = e & 63;
-        tmp[i * TS + (c ^ (i & 31))] = (i >= c) ? D[e] : 0.0f;
-      }
-      __syncthreads();
-      for (int e = tid; e < TF; e += NTHR) {
-        const int i = e >> 6, c = e & 63;
-        D[e] = tmp[i * TS + (c ^ (i & 31))];
-      }
-      fence_async();  // the stage areas served as scratch (thread writes); bulk copies overwrite them next
       __syncthreads();
     }
     pc.tick(2);
@@ -1003,11 +1069,20 @@ size_t tile_slot_floats(const GpklDesc& d) {
 
 // The shared-prior kernel of the tile tier; the caller has launched the block tier's pre-pass (records in P.prior) before
 // it and launches the per-pair kernel (skip_if_shared) behind it.
-cudaError_t launch_tile(const Params& P, bool backward, cudaStream_t st) {
+// The slots are compact (576 KB per CTA at T = 512 in forward, 148 CTAs -> 85 MB; backward 1.28 MB per CTA) and reused pair
+// after pair: DRAM READS of the forward kernel are down to the inputs and the prior records (21 KB per pair at T = 512, ncu).
+// DRAM WRITES are not: the L2 of this part writes every dirty tile back once (596 KB per pair in forward -- exactly the
+// bytes the kernel stores), with or without a persisting access-policy window over the slots (tried: no change), so
+// "nothing T x T reaches HBM" holds for reads only; keeping writes on chip needs the triangle in shared memory / DSMEM.
+cudaError_t launch_tile(const Params& P_in, bool backward, cudaStream_t st) {
+  Params P = P_in;
   const size_t smem = tile_smem_bytes(P.d);
   if (!P.scratch || P.scratch_stride < tile_slot_floats(P.d)) return cudaErrorInvalidValue;
   const int npairs = P.d.B * P.d.D;
   const int grid = npairs < kNumSMs ? npairs : kNumSMs;
+  // compact slots: this tier's own stride inside the block tier's slot area (forward needs the L triangle only)
+  const TLay L(P.d.T_max, P.d.S);
+  P.scratch_stride = backward ? tile_slot_floats(P.d) : (size_t)L.ntri() * TF;
   void (*kern)(Params);
   if (P.d.kernel == GPKL_KERNEL_RBF) kern = backward ? bwd_tile<GPKL_KERNEL_RBF> : fwd_tile<GPKL_KERNEL_RBF>;
   else kern = backward ? bwd_tile<GPKL_KERNEL_CAUCHY> : fwd_tile<GPKL_KERNEL_CAUCHY>;

@@ -9,8 +9,8 @@ L = gpkl._lib.lib()
 buf = torch.zeros(64, dtype=torch.int64, device=dev)
 NB = int(os.environ.get("TRACE_B", "37"))
 ND = int(os.environ.get("TRACE_D", "16"))
-FW = ['load+a', 'chol.gemm', 'chol.diag', 'chol.rows', 'hook(z+product)', 'final']
-BW = ['load', 'chol.gemm', 'chol.diag', 'chol.rows', 'hook(w)', 'final-unused', 'inv.diag', 'inv.gemm', 'inv.store+Cprime', 'alpha', 'contraction+final']
+FW = ['load+a', 'chol.diagtile', 'chol.gemm||diag', 'chol.rows', 'hook(z+product)', 'final']
+BW = ['load', 'chol.diagtile', 'chol.gemm||diag', 'chol.rows', 'hook(w)', 'final-unused', 'inv.diag', 'inv.gemm', 'inv.store+Cprime', 'alpha', 'contraction+final']
 for T in [int(a) for a in sys.argv[1:]] or [512]:
     case = orc.synthetic_batch(NB, ND, T, 1, seed=1)
     c = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
@@ -27,6 +27,7 @@ for T in [int(a) for a in sys.argv[1:]] or [512]:
         tot = sum(t[48:48 + len(labels)]) / n
         print('T=%d %s: %d pairs by CTA 0, %.0f cycles/pair: ' % (T, name, t[63], tot) +
               ' | '.join('%s %.0f' % (lab, t[48 + i] / n) for i, lab in enumerate(labels)), flush=True)
+        print('      diag-tile phase split: prefill %.0f | warp 0 k-loop %.0f | warp 0 flush %.0f' % (t[59] / n, t[60] / n, t[61] / n), flush=True)
         if t[35]:
             print('      staged loops of warp 0 (cycles per chunk of 8 steps, %d chunks): wait %.0f | compute %.0f | issue %.0f' % (
                 t[35], t[32] / t[35], t[33] / t[35], t[34] / t[35]), flush=True)
