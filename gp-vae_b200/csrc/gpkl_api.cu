@@ -1,6 +1,7 @@
 // C ABI of libgpkl.so (include/gpkl.h): argument checking, workspace carving, tier dispatch, the small
 // prologue (row offsets) and epilogue (deterministic reductions) kernels, and the host-buffer step.
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -21,10 +22,10 @@ struct ProfState {
   int n[2] = {0, 0};
 };
 ProfState g_prof;
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};  // kernel launches issued by this library (bench.py: gpu_launches)
 }  // namespace
 
-void note_launch(int n) { g_launches += n; }
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("GPKL_PDL"); return !(e && e[0] == '0'); }();
   return on;
@@ -338,7 +339,7 @@ extern "C" int gpkl_backward(const GpklDesc* desc, const float* mean, const floa
 // internal, not declared in include/gpkl.h: device buffer (>= 64 int64) receiving CTA 0's phase clocks
 extern "C" void gpkl_debug_set_trace(void* dev_buf) { g_dbg = static_cast<long long*>(dev_buf); }
 
-extern "C" int64_t gpkl_launch_count(void) { return g_launches; }
+extern "C" int64_t gpkl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int gpkl_profile_enable(int on) {
   if (on && !g_prof.created) {
@@ -586,6 +587,31 @@ extern "C" int gpkl_collate(int32_t N, int32_t F, int32_t T_full, int32_t B, int
     return GPKL_ERR_CUDA;
   if (total_T) cudaMemcpyAsync(total_T, w.offsets + B, sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
   return cudaGetLastError() == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
+}
+
+// ---- GP posterior imputation -----------------------------------------------------------------
+extern "C" size_t gpkl_impute_workspace_bytes(int32_t B) {
+  return B < 0 ? 0 : align_up(((size_t)B + 1) * sizeof(int64_t));
+}
+
+extern "C" int gpkl_impute(int32_t B, int32_t D, int32_t n_obs_max, int32_t n_full, int32_t kernel, float ell, float noise,
+                           const float* z_obs, const float* t_obs, const int32_t* n_obs, const float* t_full,
+                           const float* eps, float* out, int32_t* status, void* workspace, size_t ws_bytes, void* stream) {
+  if (B < 0 || D <= 0 || n_obs_max < 0 || n_full < 0) return GPKL_ERR_DESC;
+  if (kernel != GPKL_KERNEL_RBF && kernel != GPKL_KERNEL_CAUCHY) return GPKL_ERR_DESC;
+  if (!(ell > 0.0f) || !(noise >= 0.0f) || !(noise < 1.0f)) return GPKL_ERR_DESC;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (status) cudaMemsetAsync(status, 0, sizeof(int32_t), st);
+  if (B == 0 || n_full == 0) return GPKL_OK;
+  if (!z_obs || !t_obs || !n_obs || !t_full || !out || !workspace) return GPKL_ERR_NULL;
+  if (ws_bytes < gpkl_impute_workspace_bytes(B)) return GPKL_ERR_WORKSPACE;
+  if (impute_smem_bytes(n_obs_max, n_full) > kMaxDynSmem) return GPKL_ERR_UNSUPPORTED;
+  int64_t* off = static_cast<int64_t*>(workspace);
+  offsets_kernel<<<1, 1024, 0, st>>>(n_obs, B, off);
+  note_launch();
+  const cudaError_t e = launch_impute(kernel, B, D, n_obs_max, n_full, z_obs, t_obs, n_obs, t_full, eps,
+                                      reinterpret_cast<const long long*>(off), ell, noise, out, status, st);
+  return e == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
 }
 
 // ---- host-buffer step ---------------------------------------------------------------------------

@@ -69,4 +69,10 @@ cudaError_t launch_collate_scan(const float* data, const float* grid, const int3
 cudaError_t launch_collate_gather(const float* data, const int32_t* index, const long long* off, int B, int F, int T_full,
                                   int max_time, float* x, cudaStream_t st);
 
+// GP posterior imputation (gpkl_impute.cu), SURVEY.md S8(f) row 2
+size_t impute_smem_bytes(int nd_max, int ns);
+cudaError_t launch_impute(int kernel, int B, int D, int nd_max, int ns, const float* z_obs, const float* t_obs,
+                          const int32_t* n_obs, const float* t_full, const float* eps, const long long* off, float ell,
+                          float noise, float* out, int32_t* status, cudaStream_t st);
+
 }  // namespace gpkl

@@ -11,7 +11,7 @@ bool warp_tier_supports(const GpklDesc& d, bool backward) {
   if (d.T_max > 64 || d.T_max < 1) return false;
   if (backward && (d.flags & GPKL_FLAG_GRAD_ELL_P)) return false;  // d/d ell_p is served by the generic tier
   if (d.posterior != GPKL_POST_GP && d.posterior != GPKL_POST_DIAG) return false;
-  if (d.S > 8) return false;
+  if (d.S > 8) return false;  // S samples per pair live in registers; more than 8 are served by the block / generic tiers
   return true;
 }
 

@@ -33,35 +33,6 @@ namespace {
 #endif
 constexpr int WPC = GPKL_WPC;  // warps per CTA
 
-// Instruction-fetch lockstep (EXPERIMENT, off by default).  The fully unrolled phases below are straight-line
-// code of 100-300 KB that every warp executes exactly once; ncu shows the warps stalled on no_instruction at
-// the first instruction of almost every 128-byte line.  Hypothesis tested: a CTA barrier every few hundred
-// instructions keeps the WPC warps inside the same window of the 32 KB instruction cache so that one fetched
-// line serves all of them.  Measured on c2 (T=48): no change at all (fwd 0.416 ms, bwd 0.806 ms either way) --
-// the stall is the per-warp demand-fetch latency of each line, not L2 instruction bandwidth; what helps is
-// fewer instructions (coarser guards, packed FFMA2) and more resident warps.
-// nl = number of live threads in the CTA (warps with no work have exited); barrier 1 is used for this only.
-#ifndef GPKL_LOCKSTEP
-#define GPKL_LOCKSTEP 0  // barrier every this many unrolled column steps; 0 disables
-#endif
-__device__ __forceinline__ void lockstep(int nl) {
-  if (GPKL_LOCKSTEP > 0) asm volatile("bar.sync 1, %0;" ::"r"(nl));
-}
-template <int STEP>
-__device__ __forceinline__ void lockstep_at(int idx, int nl) {  // idx is a compile-time value after unrolling
-  if (GPKL_LOCKSTEP > 0 && (idx % (STEP * (GPKL_LOCKSTEP > 0 ? GPKL_LOCKSTEP : 1))) == 0) lockstep(nl);
-}
-// Count the live threads of the CTA (called by every thread before any warp exits).
-__device__ __forceinline__ int live_threads(bool warp_has_work) {
-  if (GPKL_LOCKSTEP == 0) return 0;
-  __shared__ int s_live;
-  if (threadIdx.x == 0) s_live = 0;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0 && warp_has_work) atomicAdd(&s_live, 32);
-  __syncthreads();
-  return s_live;
-}
-
 // Packed lower-triangular storage with 16-byte aligned rows: row i has capacity 4*(i/4+1) floats.
 __host__ __device__ constexpr int poff(int i) { return 8 * (i >> 2) * ((i >> 2) + 1) + (i & 3) * 4 * ((i >> 2) + 1); }
 
@@ -106,12 +77,11 @@ struct Smem {
 // Rows of K(t, ell) (lower triangle incl. diagonal, zeros above; identity on padded rows/cols).
 template <int LP, int R, int KERNEL>
 __device__ __forceinline__ void build_rows(float (&a)[R][LP * R], const float (&trow)[R], const float* __restrict__ ts,
-                                           int lig, int T, int Tw, float ell, float sig, float noise, int nl) {
+                                           int lig, int T, int Tw, float ell, float sig, float noise) {
   constexpr int TM = LP * R;
   const KernC<KERNEL> kc(ell, sig);
 #pragma unroll
   for (int k4 = 0; k4 < TM; k4 += 4) {
-    lockstep_at<4>(k4, nl);
     if (k4 < Tw) {
       const float4 t4 = *reinterpret_cast<const float4*>(ts + k4);
       const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
@@ -142,13 +112,12 @@ __device__ __forceinline__ void build_rows(float (&a)[R][LP * R], const float (&
 // Right-looking Cholesky on register rows.  col: 2*TM floats of shared memory (double buffered).
 template <int LP, int R>
 __device__ __forceinline__ void chol_rows(float (&a)[R][LP * R], int lig, int T, int Tw, float* __restrict__ col,
-                                          float* __restrict__ dg, int& bad, int nl) {
+                                          float* __restrict__ dg, int& bad) {
   constexpr int TM = LP * R;
   // (column steps are guarded in groups of 4: a padded column inside a live group is an identity column and
   //  factors to itself)
 #pragma unroll
   for (int j = 0; j < TM; ++j) {
-    lockstep_at<1>(j, nl);
     if ((j & ~3) < Tw) {
       float* cb = col + (j & 1) * TM;
 #pragma unroll
@@ -205,11 +174,10 @@ __device__ __forceinline__ void chol_rows(float (&a)[R][LP * R], int lig, int T,
 // b <- L^-1 b by a column sweep over register rows; solution also written to out[] (shared).
 template <int LP, int R>
 __device__ __forceinline__ void sweep_vec(const float (&a)[R][LP * R], float (&b)[R], int lig, int Tw,
-                                          const float* __restrict__ dinv, float* __restrict__ out, int nl) {
+                                          const float* __restrict__ dinv, float* __restrict__ out) {
   constexpr int TM = LP * R;
 #pragma unroll
   for (int k = 0; k < TM; ++k) {
-    lockstep_at<16>(k, nl);
     {  // (no guard: padded rows/columns are identity and b is zero there, so the sweep is a no-op on them)
       const float cand = b[k / LP] * dinv[k];
       const float xk = __shfl_sync(0xffffffffu, cand, k % LP, LP);
@@ -252,11 +220,10 @@ __device__ __forceinline__ void load_cols(float (&x)[R][LP * R], int lig, const 
 // In place forward substitution on register columns: x <- L^-1 x, L packed lower in shared memory.
 template <int LP, int R>
 __device__ __forceinline__ void solve_cols(float (&x)[R][LP * R], const float* __restrict__ Lpk,
-                                           const float* __restrict__ dinv, int Tw, int nl) {
+                                           const float* __restrict__ dinv, int Tw) {
   constexpr int TM = LP * R;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
-    lockstep_at<1>(i, nl);
     if ((i & ~3) < Tw) {  // groups of 4 rows: a padded row inside a live group is an identity row
       const float* row = Lpk + poff(i);
       float acc[R][2];
@@ -471,8 +438,8 @@ __global__ void __launch_bounds__(WPC * 32) prior_warp(Params P, int group_float
   __syncwarp();
   int bad = 0;
   float a[R][TM];
-  build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise, 0);
-  chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad, 0);
+  build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise);
+  chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad);
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
@@ -483,7 +450,7 @@ __global__ void __launch_bounds__(WPC * 32) prior_warp(Params P, int group_float
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
-  solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, 0);
+  solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
   // columns -> packed rows (entries above the diagonal inside the last 4-group of a row are exact zeros)
 #pragma unroll
   for (int i = 0; i < TM; ++i)
@@ -562,7 +529,6 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
   Smem<LP, R> sm(smem_f + (size_t)gslot * group_floats, S);
   const int T = pi.T, lig = pi.lig;
   const int Tw = warp_max(T);
-  const int nl = live_threads(Tw > 0);
   if (Tw == 0) {
     if (pi.active && lig == 0) {
       P.kl_pairs[pi.p] = 0.0f;
@@ -588,8 +554,8 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
   const bool shared = (POST == GPKL_POST_GP) && P.prior != nullptr && *P.prior_flag != 0;
   if (!shared) {
     const float lp = pi.active ? P.ell_p[pi.d] : 1.0f;
-    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise, nl);
-    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad, nl);
+    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise);
+    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad);
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
@@ -597,15 +563,15 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
     float bvec[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) bvec[j] = mrow[j];
-    sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as, nl);
+    sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as);
     store_rows<LP, R>(a, lig, sm.bufA);
     __syncwarp();
   }
   double part = 0.0, ldp = 0.0, ldq = 0.0;
   if (POST == GPKL_POST_GP) {
     const float lq = pi.active ? P.ell_q[pi.d] : 1.0f;
-    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise, nl);
-    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad, nl);
+    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise);
+    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad);
     float dgp_rec[R] = {};
     if (shared) {
       // The record is first needed after the K_q chain, so the pre-pass overlaps it (griddep_wait); its packed
@@ -648,7 +614,7 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
     load_cols<LP, R>(x, lig, sm.bufB);
     float ssq = 0.0f;
     if (!shared) {
-      solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, nl);
+      solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -705,7 +671,7 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
     for (int i = 0; i < TM; ++i)
 #pragma unroll
       for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
-    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, nl);
+    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) {
       const int c = lig + LP * jj;
@@ -748,7 +714,6 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
   Smem<LP, R> sm(smem_f + (size_t)gslot * group_floats, S);
   const int T = pi.T, lig = pi.lig;
   const int Tw = warp_max(T);
-  const int nl = live_threads(Tw > 0);
   if (Tw == 0) {
     if (pi.active && lig == 0 && P.gq_pairs) P.gq_pairs[pi.p] = 0.0f;
     return;
@@ -781,8 +746,8 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
   const bool shared = (POST == GPKL_POST_GP) && P.prior != nullptr && *P.prior_flag != 0;
   if (!shared) {
     const float lp = pi.active ? P.ell_p[pi.d] : 1.0f;
-    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise, nl);
-    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad, nl);
+    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise);
+    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad);
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
@@ -790,7 +755,7 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
     float bvec[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) bvec[j] = mrow[j];
-    sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as, nl);
+    sweep_vec<LP, R>(a, bvec, lig, Tw, sm.dinv, sm.as);
     store_rows<LP, R>(a, lig, sm.bufA);
     __syncwarp();
     // X_p = L_p^-1 as register columns
@@ -798,7 +763,7 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
     for (int i = 0; i < TM; ++i)
 #pragma unroll
       for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
-    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, nl);
+    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
     // alpha_c = <X_p[:,c], a> ; g_mean = g alpha + sum_s g_z
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) {
@@ -844,8 +809,8 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
       __syncwarp();
     }
     // factor K_q
-    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise, nl);
-    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad, nl);
+    build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise);
+    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad);
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgq[lig + LP * j];
@@ -874,7 +839,7 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
     for (int i = 0; i < TM; ++i)
 #pragma unroll
       for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
-    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw, nl);
+    solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
     // C'[:,l] = pd .* X_q[:,l] + sum_s w_s .* prefix(eps_s .* X_q[:,l]) -> reversed-packed rows of bufB
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) {
@@ -883,7 +848,6 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
       float cum = 0.0f;  // sample 0 fused; further samples are added below
 #pragma unroll
       for (int i = 0; i < TM; ++i) {
-        lockstep_at<16>(i, nl);
         {  // (no guard: on padded steps eps = w = 0 and X_q is the identity, every term stays finite and is
            //  multiplied by a zero of X_q in the contraction)
           const float xi = x[jj][i];

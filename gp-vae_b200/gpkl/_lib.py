@@ -17,7 +17,7 @@ SYMBOLS = ("gpkl_version", "gpkl_strerror", "gpkl_workspace_bytes", "gpkl_forwar
            "gpkl_step_host_bytes", "gpkl_step_host", "gpkl_launch_count", "gpkl_profile_enable",
            "gpkl_profile_read", "gpkl_fp32_peak_launch", "gpkl_recon_workspace_bytes", "gpkl_recon_forward",
            "gpkl_recon_backward", "gpkl_recog_workspace_bytes", "gpkl_recog_forward", "gpkl_recog_backward",
-           "gpkl_collate_workspace_bytes", "gpkl_collate")
+           "gpkl_collate_workspace_bytes", "gpkl_collate", "gpkl_impute_workspace_bytes", "gpkl_impute")
 
 
 class GpklDesc(ctypes.Structure):
@@ -80,6 +80,10 @@ def lib():
     L.gpkl_collate_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
     L.gpkl_collate.restype = i32
     L.gpkl_collate.argtypes = [ctypes.c_int32] * 5 + [vp] * 7 + [vp, sz, vp]
+    L.gpkl_impute_workspace_bytes.restype = sz
+    L.gpkl_impute_workspace_bytes.argtypes = [ctypes.c_int32]
+    L.gpkl_impute.restype = i32
+    L.gpkl_impute.argtypes = [ctypes.c_int32] * 5 + [ctypes.c_float] * 2 + [vp] * 7 + [vp, sz, vp]
     _lib = L
     return L
 

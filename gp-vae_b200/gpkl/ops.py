@@ -13,7 +13,15 @@ import torch
 from . import _lib
 from ._lib import GpklDesc, KERNELS, POSTERIORS, TIERS, FLAG_GRAD_ELL_P, FLAG_PER_PAIR_PRIOR
 
+# One workspace per (device, stream): the C ABI takes a caller-owned workspace and two launches on different streams must
+# not share one.  The cache keeps the largest workspace ever requested per stream; release_workspaces() drops them all
+# (e.g. between experiments with very different sizes: the C4 workspace is 2.9 GB).
 _WS = {}
+
+
+def release_workspaces():
+    """Free every cached workspace (they are re-created on demand)."""
+    _WS.clear()
 
 
 def _ptr(t):
@@ -368,3 +376,30 @@ def collate_batch(data, time_grid, index=None, max_time=None, batch_size=None):
     _lib.check(_lib.lib().gpkl_collate(N, F, T_full, B, max_time, _ptr(data), _ptr(time_grid), _ptr(index), _ptr(x),
                                        _ptr(times), _ptr(lengths), _ptr(total), _ptr(ws), n, _stream(dev)))
     return x[: int(total.item())], times, lengths
+
+
+# ---- GP posterior imputation ----------------------------------------------------------------
+def gp_posterior_impute(z_obs, t_obs, n_obs, t_full, eps=None, *, kernel="rbf", ell=1.0, noise=1e-3, want_status=False):
+    """Predictive mean (eps=None) or one sample (eps [B, D, n_full]) of every latent row of every sequence on the full time
+    grid t_full [B, n_full], given the rows' values z_obs [sum n_obs, D] at the observed times t_obs [B, n_obs_max]
+    (n_obs [B] int32 valid per sequence): sample_given_part_latent / post_gp_sample of the reference
+    (FullGP_and_GPdecoder_dynamic_time_analysis.py:40-56, :96-111) for a whole batch.  Returns out [B*n_full, D]
+    (and the device status counter: > 0 when the posterior covariance was not positive definite, where the reference raises)."""
+    if not z_obs.is_cuda:
+        raise RuntimeError("gpkl: tensors must live on a CUDA device (there is no CPU implementation)")
+    B, nd_max = t_obs.shape
+    Bf, ns = t_full.shape
+    D = z_obs.shape[1]
+    assert Bf == B and n_obs.shape == (B,) and n_obs.dtype == torch.int32
+    for t in (z_obs, t_obs, t_full, eps):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous()), "float32 contiguous tensors required"
+    assert eps is None or eps.shape == (B, D, ns)
+    dev = z_obs.device
+    out = torch.empty(B * ns, D, dtype=torch.float32, device=dev)
+    status = torch.zeros((), dtype=torch.int32, device=dev)
+    n = _lib.lib().gpkl_impute_workspace_bytes(B)
+    ws = _named_ws("impute", n, dev)
+    _lib.check(_lib.lib().gpkl_impute(B, D, nd_max, ns, KERNELS[kernel], float(ell), float(noise), _ptr(z_obs), _ptr(t_obs),
+                                      _ptr(n_obs), _ptr(t_full), _ptr(eps), _ptr(out), _ptr(status), _ptr(ws), n,
+                                      _stream(dev)))
+    return (out, status) if want_status else out

@@ -147,3 +147,36 @@ class SyntheticDataHandlerGPU:
         index = self.order[self.counter:self.counter + self.batch_size].contiguous()
         self.counter += self.batch_size
         return collate_batch(self.x, self.time, index, self.max_time)
+
+
+# ---- GP posterior imputation by the reference's names (FullGP_and_GPdecoder_dynamic_time_analysis.py) -------------------
+def post_gp_sample(t_s_matrix, sequence_times, full_sequence_times, mean=False, *, eps=None, device="cuda:0"):
+    """post_gp_sample (:96-111): t_s_matrix is a list of [D, n_obs_b] arrays (one per sequence, latent rows x kept time
+    points), sequence_times the kept time stamps per sequence, full_sequence_times the grid to fill in.  Returns the
+    reference's [B*n_full, D] array (numpy, float32).  eps [B, D, n_full] replaces np.random.normal (:51) for reproducible
+    runs; mean=True returns the predictive mean."""
+    import numpy as np
+    from .ops import gp_posterior_impute
+    dev = torch.device(device)
+    B = len(t_s_matrix)
+    D = int(np.asarray(t_s_matrix[0]).shape[0])
+    n_obs = [len(t) for t in sequence_times]
+    nd_max, ns = max(n_obs), len(full_sequence_times)
+    t_obs = torch.zeros(B, nd_max, dtype=torch.float32)
+    for b, t in enumerate(sequence_times):
+        t_obs[b, : n_obs[b]] = torch.as_tensor(np.asarray(t, dtype=np.float32))
+    z = torch.cat([torch.as_tensor(np.asarray(m, dtype=np.float32)).t() for m in t_s_matrix], 0).contiguous()  # [sum n_obs, D]
+    t_full = torch.as_tensor(np.asarray(full_sequence_times, dtype=np.float32)).repeat(B, 1).contiguous()
+    if not mean and eps is None:
+        eps = torch.randn(B, D, ns)
+    e = None if mean else torch.as_tensor(np.asarray(eps, dtype=np.float32)).contiguous().to(dev)
+    out = gp_posterior_impute(z.to(dev), t_obs.to(dev), torch.tensor(n_obs, dtype=torch.int32, device=dev), t_full.to(dev), e)
+    return out.cpu().numpy()
+
+
+def sample_given_part_latent(z_d, z_d_times, full_seq_times, mean=False, *, eps=None, device="cuda:0"):
+    """sample_given_part_latent (:40-56) for ONE latent row: returns [1, n_full]."""
+    import numpy as np
+    e = None if eps is None else np.asarray(eps, dtype=np.float32).reshape(1, 1, -1)
+    out = post_gp_sample([np.asarray(z_d, dtype=np.float32).reshape(1, -1)], [z_d_times], full_seq_times, mean, eps=e, device=device)
+    return out.reshape(1, -1)

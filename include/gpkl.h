@@ -13,7 +13,10 @@
  * Conventions
  *   - plain C: POD descriptor, raw pointers, sizes; no C++/torch types, no exceptions.
  *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all buffers,
- *     including the workspace; the library allocates nothing and keeps no global state.
+ *     including the workspace; the library allocates nothing on the data path.  The only process-global state is
+ *     measurement-side and none of it influences results: an atomic launch counter (gpkl_launch_count), the CUDA
+ *     events of the optional kernel profiler (gpkl_profile_enable / _read, off by default and NOT thread-safe: one
+ *     measuring thread) and the internal phase-trace pointer of the developer tools.
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation, no
  *     allocation => CUDA-graph capturable and re-entrant.
  *   - outputs are fully overwritten (no caller zero-fill needed); reductions are deterministic.
@@ -161,6 +164,24 @@ size_t gpkl_collate_workspace_bytes(int32_t B, int32_t max_time);
 int gpkl_collate(int32_t N, int32_t F, int32_t T_full, int32_t B, int32_t max_time, const float* data,
                  const float* time_grid, const int32_t* index, float* x, float* times, int32_t* lengths,
                  int64_t* total_T, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- GP posterior conditioning / imputation -------------------------------------------------
+ * Replaces sample_given_part_latent / post_gp_sample (src/Models/FullGP_and_GPdecoder_dynamic_time_analysis.py:40-56,
+ * :96-111) for a whole batch: the latent values z_obs [sum n_obs, D] (rows sequence-major then time, the layout of `mean`)
+ * at the observed time points t_obs [B, n_obs_max] (n_obs [B] valid per sequence) are conditioned on, and the predictive
+ * mean (eps == NULL) or one sample (eps [B, D, n_full] N(0,1), the np.random.normal of :51 made explicit) on the full
+ * grid t_full [B, n_full] is written to out [B*n_full, D] (per sequence n_full rows, post_gp_sample's concatenation
+ * :108-110).  Kernel as kernel_function :8-14: (1-noise) k + noise wherever two time stamps coincide exactly, entries
+ * rounded to float32; the reference fixes ell = 1, noise = 1e-3, RBF.  Matrices are factored once per SEQUENCE (they do
+ * not depend on the latent row) in shared memory; n_obs_max and n_full are limited by it (about 110 each) ->
+ * GPKL_ERR_UNSUPPORTED beyond.  The posterior covariance K_ss + 1e-15 I - Lk^T Lk is factored even for the mean, as the
+ * reference does (:50 precedes :53): if it is not positive definite -- always the case when an observed time point
+ * coincides with a full-grid point, where the reference raises LinAlgError -- *status is incremented; the mean is still
+ * written, sample rows are NaN. */
+size_t gpkl_impute_workspace_bytes(int32_t B);
+int gpkl_impute(int32_t B, int32_t D, int32_t n_obs_max, int32_t n_full, int32_t kernel, float ell, float noise,
+                const float* z_obs, const float* t_obs, const int32_t* n_obs, const float* t_full, const float* eps,
+                float* out, int32_t* status, void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- measurement hooks (bench.py; not part of the data path) ------------------------------------
  * These are the only process-global state in the library and are not thread safe.

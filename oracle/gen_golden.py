@@ -220,6 +220,43 @@ def run_collate(name):
     _save(name, variant="collate", data=x, time_grid=grid, max_time=max_time, **out)
 
 
+def run_impute(name, seed):
+    """GP posterior imputation: sample_given_part_latent (FullGP_and_GPdecoder_dynamic_time_analysis.py:40-56) called for
+    every latent row of every sequence exactly as post_gp_sample (:96-111) does, with np.random.normal replaced by recorded
+    draws.  Observed time stamps sit BETWEEN the points of the full grid (the reference's own subset-of-grid input makes
+    its posterior covariance singular and it raises LinAlgError -- recorded in the fixture as `coincident_raises`)."""
+    import FullGP_and_GPdecoder_dynamic_time_analysis as ana  # noqa: E402  (reference, unmodified)
+    rng = np.random.RandomState(seed)
+    full = [float(i) + 1 for i in range(20)]                                   # x_space of the reference (:25)
+    obs_times = [sorted(rng.choice(np.arange(1, 20), size=n, replace=False) + 0.5) for n in (7, 10, 4)]
+    B, D = len(obs_times), 6
+    t_s_matrix = [rng.randn(D, len(t)).astype(np.float32) for t in obs_times]
+    eps = rng.randn(B, D, len(full)).astype(np.float32)
+    draws = []
+    old = np.random.normal
+    np.random.normal = lambda *a, **k: draws.pop(0)
+    try:
+        draws[:] = [np.zeros((len(full), 1)) for _ in range(B * D)]
+        mean = ana.post_gp_sample(t_s_matrix, obs_times, full, mean=True)
+        draws[:] = [eps[b, d].reshape(-1, 1).astype(np.float64) for b in range(B) for d in range(D)]
+        sample = ana.post_gp_sample(t_s_matrix, obs_times, full, mean=False)
+    finally:
+        np.random.normal = old
+    raised = False
+    try:
+        ana.sample_given_part_latent(t_s_matrix[0][0][:5], [1.0, 3.0, 4.0, 8.0, 10.0], full, mean=True)
+    except np.linalg.LinAlgError:
+        raised = True
+    nd_max = max(len(t) for t in obs_times)
+    t_obs = np.zeros((B, nd_max), np.float32)
+    for b, t in enumerate(obs_times):
+        t_obs[b, : len(t)] = t
+    z_obs = np.concatenate([m.T for m in t_s_matrix], 0)
+    _save(name, variant="impute", t_obs=t_obs, n_obs=np.asarray([len(t) for t in obs_times], np.int32),
+          t_full=np.tile(np.asarray(full, np.float32), (B, 1)), z_obs=z_obs, eps=eps, mean_out=mean, sample_out=sample,
+          coincident_raises=np.asarray(raised))
+
+
 def main():
     torch.manual_seed(0)
     # G1 -- SURVEY.md Appendix B golden case (regular grid, B=3 D=4 T=6)
@@ -272,6 +309,8 @@ def main():
               torch.randn(B * T, D, generator=g), 0.3 * torch.randn(B * T, D, generator=g) - 1.0, torch.ones(D), S=1, seed=16)
     # G9 -- ragged batch producer (S8(f) row 4)
     run_collate("g9_collate")
+    # G10 -- GP posterior imputation (S8(f) row 2): the reference's sample_given_part_latent / post_gp_sample
+    run_impute("g10_impute", 23)
 
 
 if __name__ == "__main__":

@@ -294,6 +294,48 @@ def collate_batch(data, time_grid, index, max_time):
         np.asarray(ls, np.int32)
 
 
+
+def posterior_impute(z_obs, t_obs, n_obs, t_full, eps=None, *, kernel=RBF, ell=1.0, noise=1e-3):
+    """GP posterior conditioning of FullGP_and_GPdecoder_dynamic_time_analysis.py (sample_given_part_latent :40-56 looped
+    as post_gp_sample :96-111), restated with numpy in the reference's own precisions: kernel entries float32 with the
+    nugget wherever two time stamps coincide exactly (:8-22); L, Lk, mu float32 (:43-48); the posterior covariance
+    K_ss + 1e-15 I - Lk^T Lk and its Cholesky float64 (:49-50).  z_obs [sum n_obs, D], t_obs [B, n_obs_max],
+    n_obs [B], t_full [B, n_full], eps [B, D, n_full] or None (mean).  Returns (out [B*n_full, D] float64,
+    failed [B] bool: covariance not positive definite -- the reference raises LinAlgError there)."""
+    z_obs = np.asarray(z_obs, dtype=np.float32)
+    t_obs, t_full = np.asarray(t_obs, dtype=np.float32), np.asarray(t_full, dtype=np.float32)
+    n_obs = [int(x) for x in np.asarray(n_obs).tolist()]
+    B, ns = t_full.shape
+    D = z_obs.shape[1]
+    offs = np.concatenate([[0], np.cumsum(n_obs)]).astype(np.int64)
+
+    def kmat(a, b):
+        d = a.astype(np.float64)[:, None] - b.astype(np.float64)[None, :]
+        k = np.exp(-(d * d) / (2.0 * ell * ell)) if kernel == RBF else 1.0 / (1.0 + d * d / (ell * ell))
+        nz = np.where(a[:, None] == b[None, :], noise, 0.0)
+        return ((1.0 - nz) * k + nz).astype(np.float32)
+
+    out = np.zeros((B * ns, D), dtype=np.float64)
+    failed = np.zeros(B, dtype=bool)
+    for b in range(B):
+        td, tf = t_obs[b, : n_obs[b]], t_full[b]
+        L = np.linalg.cholesky(kmat(td, td))                       # float32, :43-44
+        Lk = np.linalg.solve(L, kmat(td, tf))                      # :46-47
+        C = kmat(tf, tf) + 1e-15 * np.eye(ns) - np.dot(Lk.T, Lk)   # float64, :49-50
+        try:
+            Lc = np.linalg.cholesky(C)
+        except np.linalg.LinAlgError:
+            failed[b] = True
+            Lc = np.full((ns, ns), np.nan)
+        zb = z_obs[offs[b]: offs[b + 1]]                           # [n_obs, D]
+        mu = np.dot(Lk.T, np.linalg.solve(L, zb))                  # [n_full, D], :48
+        f = mu.astype(np.float64)
+        if eps is not None:
+            f = f + np.dot(Lc, np.asarray(eps[b], dtype=np.float64).T)   # :51
+        out[b * ns: (b + 1) * ns] = f
+    return out, failed
+
+
 def gp_kl_div_numpy(m, Kq, Kp):
     """Single-pair numpy float64 transcription of gp_kl_div (Full_GP_VAE_dynamic_time.py:242-260),
     independent of torch -- second opinion for the golden tests."""

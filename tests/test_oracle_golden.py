@@ -143,3 +143,21 @@ def test_collate_oracle_matches_reference():
         assert (x == g["x%d" % k].numpy()).all() and x.shape == tuple(g["x%d" % k].shape)
         assert (times == g["times%d" % k].numpy()).all()
         assert (lengths == g["lengths%d" % k].numpy()).all()
+
+
+def test_oracle_posterior_impute_matches_reference_g10():
+    """G10 = the reference's sample_given_part_latent / post_gp_sample executed verbatim
+    (FullGP_and_GPdecoder_dynamic_time_analysis.py:40-56, :96-111) with recorded normal draws."""
+    g = load_golden("g10_impute")
+    assert bool(g["coincident_raises"])   # the reference raises LinAlgError when an observed point lies ON the full grid
+    mean, failed = orc.posterior_impute(g["z_obs"].numpy(), g["t_obs"].numpy(), g["n_obs"].numpy(), g["t_full"].numpy())
+    assert not failed.any()
+    assert rel_err(mean, g["mean_out"]) < 2e-6
+    samp, failed = orc.posterior_impute(g["z_obs"].numpy(), g["t_obs"].numpy(), g["n_obs"].numpy(), g["t_full"].numpy(),
+                                        g["eps"].numpy())
+    assert not failed.any()
+    assert rel_err(samp, g["sample_out"]) < 2e-5   # the covariance carries float32 rounding noise of Lk^T Lk (:50)
+    # coincident grids: the restatement reports the failure the reference raises
+    _, failed = orc.posterior_impute(g["z_obs"].numpy()[:7], np.array([[1., 3., 4., 8., 10., 13., 17.]], np.float32),
+                                     np.array([7]), g["t_full"].numpy()[:1])
+    assert failed.all()
