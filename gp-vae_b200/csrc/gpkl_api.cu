@@ -265,6 +265,7 @@ extern "C" int gpkl_forward(const GpklDesc* desc, const float* mean, const float
   memset(&P, 0, sizeof(P));
   P.d = d;
   P.mean = mean; P.times = times; P.lengths = lengths; P.ell_q = ell_q; P.ell_p = ell_p; P.aux = aux; P.eps = eps;
+  if (d.flags & GPKL_FLAG_PHILOX_EPS) { P.eps = nullptr; P.eps_seed = reinterpret_cast<const unsigned long long*>(eps); }
   P.z = z; P.kl_pairs = kl_pairs; P.logdets = logdets; P.status = status;
   P.offsets = w.offsets;
   P.scratch = w.scratch_stride ? w.scratch : nullptr;
@@ -313,6 +314,7 @@ extern "C" int gpkl_backward(const GpklDesc* desc, const float* mean, const floa
   memset(&P, 0, sizeof(P));
   P.d = d;
   P.mean = mean; P.times = times; P.lengths = lengths; P.ell_q = ell_q; P.ell_p = ell_p; P.aux = aux; P.eps = eps;
+  if (d.flags & GPKL_FLAG_PHILOX_EPS) { P.eps = nullptr; P.eps_seed = reinterpret_cast<const unsigned long long*>(eps); }
   P.g_z = g_z; P.g_kl_sum = g_kl_sum; P.g_kl_pairs = g_kl_pairs;
   P.g_mean = g_mean; P.g_aux = g_aux; P.gq_pairs = w.gq_pairs; P.gp_pairs = w.gp_pairs; P.status = status;
   P.offsets = w.offsets;
@@ -490,6 +492,7 @@ extern "C" int gpkl_recog_forward(const GpklDesc* desc, const float* mean, const
   const GpklDesc in = recog_inner_desc(*desc);
   int rc = check_desc(&in);
   if (rc != GPKL_OK) return rc;
+  if (in.flags & GPKL_FLAG_PHILOX_EPS) return GPKL_ERR_UNSUPPORTED;  // the epilogue kernel reads eps
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!kl_sum) return GPKL_ERR_NULL;
   if (in.B == 0 || in.total_T == 0) {
@@ -521,6 +524,7 @@ extern "C" int gpkl_recog_backward(const GpklDesc* desc, const float* mean, cons
   const GpklDesc in = recog_inner_desc(*desc);
   int rc = check_desc(&in);
   if (rc != GPKL_OK) return rc;
+  if (in.flags & GPKL_FLAG_PHILOX_EPS) return GPKL_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (in.B == 0 || in.total_T == 0) {
     if (g_ell) cudaMemsetAsync(g_ell, 0, sizeof(float) * in.D, st);
@@ -586,6 +590,26 @@ extern "C" int gpkl_collate(int32_t N, int32_t F, int32_t T_full, int32_t B, int
   if (launch_collate_gather(data, index, reinterpret_cast<const long long*>(w.offsets), B, F, T_full, max_time, x, st) != cudaSuccess)
     return GPKL_ERR_CUDA;
   if (total_T) cudaMemcpyAsync(total_T, w.offsets + B, sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
+  return cudaGetLastError() == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
+}
+
+// ---- the GPKL_FLAG_PHILOX_EPS noise stream, materialised ---------------------------------------------------------------
+namespace gpkl {
+static __global__ void philox_fill_kernel(const unsigned long long* __restrict__ seed, long long n, float* __restrict__ eps) {
+  const unsigned long long sd = *seed;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    eps[e] = philox_normal(sd, (unsigned long long)e);
+}
+}  // namespace gpkl
+
+extern "C" int gpkl_philox_normal(const uint64_t* seed_dev, int64_t n, float* eps, void* stream) {
+  if (n < 0) return GPKL_ERR_DESC;
+  if (n == 0) return GPKL_OK;
+  if (!seed_dev || !eps) return GPKL_ERR_NULL;
+  const int grid = (int)((n + 255) / 256 < (int64_t)kNumSMs * 8 ? (n + 255) / 256 : (int64_t)kNumSMs * 8);
+  philox_fill_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(seed_dev), (long long)n, eps);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? GPKL_OK : GPKL_ERR_CUDA;
 }
 
@@ -686,7 +710,7 @@ extern "C" int gpkl_step_host(const GpklDesc* desc, const float* mean_host, cons
   h2d(s.ell_q, ell_q_host, (size_t)d.D * 4);
   h2d(s.ell_p, ell_p_host, (size_t)d.D * 4);
   h2d(s.aux, aux_host, rows * d.D * auxw * 4);
-  h2d(s.eps, eps_host, P * d.S * d.T_max * 4);
+  h2d(s.eps, eps_host, (d.flags & GPKL_FLAG_PHILOX_EPS) ? sizeof(uint64_t) : P * d.S * d.T_max * 4);
   h2d(s.g_z, g_z_host, rows * d.S * d.D * 4);
   rc = gpkl_forward(desc, s.mean, s.times, s.lengths, ell_q_host ? s.ell_q : nullptr, s.ell_p,
                     aux_host ? s.aux : nullptr, s.eps, s.z, s.kl_pairs, s.kl_sum, nullptr, nullptr, s.ws, s.ws_bytes,

@@ -1010,7 +1010,7 @@ __device__ __forceinline__ void load_pair(const Params& P, int p, int b, int dd,
       s.gzs[i] = gs;
     }
     for (int sx = 0; sx < S; ++sx)
-      s.v[(size_t)sx * TP + i] = (i < T) ? P.eps[((size_t)p * S + sx) * d.T_max + i] : 0.0f;
+      s.v[(size_t)sx * TP + i] = (i < T) ? eps_value(P, ((size_t)p * S + sx) * d.T_max + i) : 0.0f;
   }
 }
 

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(NT) fwd_generic(Params P, int Tcap, int ld_cap
     }
     for (int e = threadIdx.x; e < S * T; e += NT) {
       const int sidx = e / T, i = e - sidx * T;
-      s.v[e] = P.eps[((size_t)p * S + sidx) * d.T_max + i];
+      s.v[e] = eps_value(P, ((size_t)p * S + sidx) * d.T_max + i);
     }
     __syncthreads();
     const float lp = P.ell_p[dd];
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(NT) bwd_generic(Params P, int Tcap, int ld_cap
     }
     for (int e = threadIdx.x; e < S * T; e += NT) {
       const int sidx = e / T, i = e - sidx * T;
-      s.v[e] = P.eps[((size_t)p * S + sidx) * d.T_max + i];
+      s.v[e] = eps_value(P, ((size_t)p * S + sidx) * d.T_max + i);
     }
     __syncthreads();
     const float lp = P.ell_p[dd];

@@ -616,7 +616,7 @@ __device__ __forceinline__ void load_vectors(const Params& P, int p, int b, int 
     s.ts[i] = (i < T) ? P.times[(size_t)b * d.T_max + i] : 0.0f;
     s.mm[i] = (i < T) ? P.mean[(size_t)(r0 + i) * d.D + dd] : 0.0f;
     for (int sx = 0; sx < S; ++sx) {
-      s.eps[(size_t)sx * TP + i] = (i < T) ? P.eps[((size_t)p * S + sx) * d.T_max + i] : 0.0f;
+      s.eps[(size_t)sx * TP + i] = (i < T) ? eps_value(P, ((size_t)p * S + sx) * d.T_max + i) : 0.0f;
       if (!backward) s.zacc[(size_t)sx * TP + i] = s.mm[i];
     }
     if (backward) {  // S == 1

@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
     trow[j] = ok ? P.times[(size_t)pi.b * d.T_max + r] : 0.0f;
     mrow[j] = ok ? P.mean[(size_t)(pi.r0 + r) * d.D + pi.d] : 0.0f;
     sm.ts[r] = trow[j];
-    for (int s = 0; s < S; ++s) sm.vS[s * TM + r] = ok ? P.eps[((size_t)pi.p * S + s) * d.T_max + r] : 0.0f;
+    for (int s = 0; s < S; ++s) sm.vS[s * TM + r] = ok ? eps_value(P, ((size_t)pi.p * S + s) * d.T_max + r) : 0.0f;
   }
   __syncwarp();
   int bad = 0;
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
     sm.ts[r] = trow[j];
     float gs = 0.0f;
     for (int s = 0; s < S; ++s) {
-      sm.vS[s * TM + r] = ok ? P.eps[((size_t)pi.p * S + s) * d.T_max + r] : 0.0f;
+      sm.vS[s * TM + r] = ok ? eps_value(P, ((size_t)pi.p * S + s) * d.T_max + r) : 0.0f;
       const float gz = (ok && P.g_z) ? P.g_z[((size_t)S * pi.r0 + (size_t)s * T + r) * d.D + pi.d] : 0.0f;
       sm.uS[s * TM + r] = gz;
       gs += gz;

@@ -11,13 +11,14 @@ POSTERIORS = {"gp": 0, "diag": 1, "bidiag": 2}
 TIERS = {"auto": 0, "generic": 1, "warp": 2, "block": 3}
 FLAG_GRAD_ELL_P = 1
 FLAG_PER_PAIR_PRIOR = 2
+FLAG_PHILOX_EPS = 4
 
 # every symbol include/gpkl.h declares (tests check the library exports exactly these)
 SYMBOLS = ("gpkl_version", "gpkl_strerror", "gpkl_workspace_bytes", "gpkl_forward", "gpkl_backward",
            "gpkl_step_host_bytes", "gpkl_step_host", "gpkl_launch_count", "gpkl_profile_enable",
            "gpkl_profile_read", "gpkl_fp32_peak_launch", "gpkl_recon_workspace_bytes", "gpkl_recon_forward",
            "gpkl_recon_backward", "gpkl_recog_workspace_bytes", "gpkl_recog_forward", "gpkl_recog_backward",
-           "gpkl_collate_workspace_bytes", "gpkl_collate", "gpkl_impute_workspace_bytes", "gpkl_impute")
+           "gpkl_collate_workspace_bytes", "gpkl_collate", "gpkl_impute_workspace_bytes", "gpkl_impute", "gpkl_philox_normal")
 
 
 class GpklDesc(ctypes.Structure):
@@ -80,6 +81,8 @@ def lib():
     L.gpkl_collate_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
     L.gpkl_collate.restype = i32
     L.gpkl_collate.argtypes = [ctypes.c_int32] * 5 + [vp] * 7 + [vp, sz, vp]
+    L.gpkl_philox_normal.restype = i32
+    L.gpkl_philox_normal.argtypes = [vp, i64, vp, vp]
     L.gpkl_impute_workspace_bytes.restype = sz
     L.gpkl_impute_workspace_bytes.argtypes = [ctypes.c_int32]
     L.gpkl_impute.restype = i32

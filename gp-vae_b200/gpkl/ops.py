@@ -11,7 +11,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import GpklDesc, KERNELS, POSTERIORS, TIERS, FLAG_GRAD_ELL_P, FLAG_PER_PAIR_PRIOR
+from ._lib import GpklDesc, KERNELS, POSTERIORS, TIERS, FLAG_GRAD_ELL_P, FLAG_PER_PAIR_PRIOR, FLAG_PHILOX_EPS
 
 # One workspace per (device, stream): the C ABI takes a caller-owned workspace and two launches on different streams must
 # not share one.  The cache keeps the largest workspace ever requested per stream; release_workspaces() drops them all
@@ -54,13 +54,22 @@ def _workspace(desc, device):
     return ws, n
 
 
+def _is_seed(eps):
+    """eps given as a seed (0-d / 1-element int64 CUDA tensor): the kernels generate the noise (GPKL_FLAG_PHILOX_EPS)."""
+    return isinstance(eps, torch.Tensor) and eps.dtype == torch.int64
+
+
 def _check_inputs(mean, times, lengths, ell_q, ell_p, eps, aux, posterior, S):
     if not mean.is_cuda:
         raise RuntimeError("gpkl: tensors must live on a CUDA device (there is no CPU implementation)")
     B, T_max = times.shape
     total_T, D = mean.shape
     assert lengths.shape == (B,) and lengths.dtype == torch.int32, "lengths must be int32 [B]"
-    assert eps.shape == (B, D, S, T_max), "eps must be [B, D, S, T_max]"
+    if _is_seed(eps):
+        assert eps.numel() == 1 and eps.is_cuda, "the seed is one int64 on the device"
+        eps = None
+    else:
+        assert eps.shape == (B, D, S, T_max), "eps must be [B, D, S, T_max]"
     assert ell_p.shape == (D,)
     if posterior == "gp":
         assert ell_q is not None and ell_q.shape == (D,)
@@ -78,7 +87,8 @@ def gp_prior_kl_forward(mean, times, lengths, ell_q, ell_p, eps, *, aux=None, ke
     factors K_p once per sequence when it finds ell_p identical for all latent dims (the reference's prior)."""
     B, D, T_max, total_T = _check_inputs(mean, times, lengths, ell_q, ell_p, eps, aux, posterior, S)
     dev = mean.device
-    desc = _make_desc(B, D, T_max, S, total_T, kernel, posterior, noise, 0 if shared_prior else FLAG_PER_PAIR_PRIOR, tier)
+    desc = _make_desc(B, D, T_max, S, total_T, kernel, posterior, noise,
+                      (0 if shared_prior else FLAG_PER_PAIR_PRIOR) | (FLAG_PHILOX_EPS if _is_seed(eps) else 0), tier)
     ws, n = _workspace(desc, dev)
     z = torch.empty(S * total_T, D, dtype=torch.float32, device=dev)
     kl_pairs = torch.empty(B * D, dtype=torch.float32, device=dev)
@@ -105,7 +115,8 @@ def gp_prior_kl_backward(mean, times, lengths, ell_q, ell_p, eps, g_z, g_kl_sum=
     B, D, T_max, total_T = _check_inputs(mean, times, lengths, ell_q, ell_p, eps, aux, posterior, S)
     dev = mean.device
     desc = _make_desc(B, D, T_max, S, total_T, kernel, posterior, noise,
-                      (FLAG_GRAD_ELL_P if grad_ell_p else 0) | (0 if shared_prior else FLAG_PER_PAIR_PRIOR), tier)
+                      (FLAG_GRAD_ELL_P if grad_ell_p else 0) | (0 if shared_prior else FLAG_PER_PAIR_PRIOR) |
+                      (FLAG_PHILOX_EPS if _is_seed(eps) else 0), tier)
     ws, n = _workspace(desc, dev)
     out = dict(out or {})
     g_mean = out.get("g_mean")
@@ -163,15 +174,27 @@ class GpPriorKL(torch.autograd.Function):
                 None, None, None, None, None)
 
 
+def philox_normal(seed, n, device="cuda:0"):
+    """The first n draws of the GPKL_FLAG_PHILOX_EPS stream for `seed`, materialised (gpkl_philox_normal)."""
+    dev = torch.device(device)
+    sd = seed if isinstance(seed, torch.Tensor) else torch.tensor([int(seed)], dtype=torch.int64, device=dev)
+    out = torch.empty(int(n), dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib().gpkl_philox_normal(_ptr(sd), int(n), _ptr(out), _stream(dev)))
+    return out
+
+
 def gp_prior_kl(mean, times, lengths, ell_q, ell_p, eps=None, *, aux=None, kernel="rbf", posterior="gp", noise=1e-3,
-                S=1, tier="auto", generator=None):
+                S=1, tier="auto", generator=None, seed=None):
     """Fused GP-prior path.  Returns (z [S*sum_T, D] f32, kl_sum f64 scalar, kl_pairs [B*D] f32).
 
-    eps=None draws the N(0,1) noise on the device (the reference's tf.random_normal inside tf_kernel,
-    Full_GP_VAE_dynamic_time.py:166); pass eps [B, D, S, T_max] explicitly for reproducible parity runs."""
+    eps [B, D, S, T_max]: explicit N(0,1) noise (reproducible parity runs).  eps=None: the noise of the reference's
+    tf.random_normal inside tf_kernel (Full_GP_VAE_dynamic_time.py:166) is generated INSIDE the kernels from a 64-bit seed
+    (Philox4x32-10 + Box-Muller, no eps tensor in HBM; forward and backward regenerate the same values): `seed` (int or
+    1-element int64 CUDA tensor), else one drawn from `generator` / torch's default generator."""
     if eps is None:
-        B, T_max = times.shape
-        eps = torch.randn(B, mean.shape[1], S, T_max, device=mean.device, dtype=torch.float32, generator=generator)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator).item())
+        eps = seed if isinstance(seed, torch.Tensor) else torch.tensor([int(seed)], dtype=torch.int64, device=mean.device)
     if posterior != "gp" and ell_q is None:
         ell_q = ell_p
     return GpPriorKL.apply(mean, times, lengths, ell_q, ell_p, eps, aux, kernel, posterior, float(noise), int(S), tier)

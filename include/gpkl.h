@@ -55,7 +55,16 @@ enum {
    * sequence is the same matrix for its D pairs ("each batch has the SAME matrix", :108-109).  When the device
    * finds ell_p[0] == ... == ell_p[D-1] the hot tiers factor K_p once per SEQUENCE (a small pre-pass into the
    * workspace) instead of once per pair.  This flag forces the per-pair factorisation (A/B tests). */
-  GPKL_FLAG_PER_PAIR_PRIOR = 2
+  GPKL_FLAG_PER_PAIR_PRIOR = 2,
+  /* Production-mode noise: no eps tensor exists.  The `eps` argument of gpkl_forward / gpkl_backward is then a DEVICE
+   * pointer to ONE uint64 seed (read by the kernels at run time, so a captured CUDA graph can be replayed with a new
+   * seed), and element ((b*D + d)*S + s)*T_max + t of the virtual eps tensor is generated in the kernels with
+   * Philox4x32-10 + cuRAND's Box-Muller (definition: gpkl_common.cuh, "counter-based N(0,1) noise"; host restatement
+   * pinned to the Random123 known-answer vectors: tests/test_philox_cpu.py).  It replaces tf.random_normal inside
+   * tf_kernel (Full_GP_VAE_dynamic_time.py:166) without the HBM round trip of an explicit eps.  (gpkl_step_host: eps_host
+   * points to the seed on the host; gpkl_recog_*: not supported, their epilogue kernels read eps.)
+   * gpkl_philox_normal writes the same stream into memory (tests, callers that want to see the draws). */
+  GPKL_FLAG_PHILOX_EPS = 4
 };
 
 enum {
@@ -178,6 +187,9 @@ int gpkl_collate(int32_t N, int32_t F, int32_t T_full, int32_t B, int32_t max_ti
  * reference does (:50 precedes :53): if it is not positive definite -- always the case when an observed time point
  * coincides with a full-grid point, where the reference raises LinAlgError -- *status is incremented; the mean is still
  * written, sample rows are NaN. */
+/* eps[e] = the e-th N(0,1) draw of the GPKL_FLAG_PHILOX_EPS stream for *seed_dev (device uint64), e in [0, n). */
+int gpkl_philox_normal(const uint64_t* seed_dev, int64_t n, float* eps, void* stream);
+
 size_t gpkl_impute_workspace_bytes(int32_t B);
 int gpkl_impute(int32_t B, int32_t D, int32_t n_obs_max, int32_t n_full, int32_t kernel, float ell, float noise,
                 const float* z_obs, const float* t_obs, const int32_t* n_obs, const float* t_full, const float* eps,
