@@ -396,12 +396,13 @@ def elbo_step_bench(gpkl, w, dev, world, steps=3, warmup=2):
     ell_p = case["ell_p"].to(dev)
     params = list(enc.parameters()) + list(dec.parameters()) + [ell_q]
     opt = torch.optim.Adam(params, lr=2e-4)
-    eps = case["eps"].to(dev)
+    step_no = [0]
 
     def one():
         opt.zero_grad(set_to_none=True)
         mean = enc(x)
-        z, kl_sum, _ = gpkl.gp_prior_kl(mean, times, lengths, ell_q, ell_p, eps, kernel=w["kernel"])
+        step_no[0] += 1  # production mode: the noise is drawn inside the kernels from a per-step seed (no eps tensor)
+        z, kl_sum, _ = gpkl.gp_prior_kl(mean, times, lengths, ell_q, ell_p, None, kernel=w["kernel"], seed=1000 + step_no[0])
         xd = dec(z)
         loss = gpkl.elbo_loss(x, xd, lengths, kl_sum, beta=1.0)
         loss.backward()

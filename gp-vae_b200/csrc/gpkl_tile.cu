@@ -592,11 +592,13 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
       float* tile = s.panel + (size_t)(J + ti) * TF;
       float acc[8][16];
       acc_zero(acc);
+      // operands swapped (acc[c][i] = L(i,c)): the conflict-free "column-major" store pattern then writes the ROW-major
+      // tile the product / z / w read, and the global column-major L tile takes the strided pattern (no banks there)
 #pragma unroll 1
-      for (int q = 0; q < UC; ++q) mk_chunk(acc, tile + q * CH, s.linv + q * CH, W.ty, W.tx);
-      store_colmajor<1>(Lg + (size_t)tri(J + ti, J) * TF, acc, W.ty, W.tx);
+      for (int q = 0; q < UC; ++q) mk_chunk(acc, s.linv + q * CH, tile + q * CH, W.ty, W.tx);
+      store_rowmajor<1>(Lg + (size_t)tri(J + ti, J) * TF, acc, W.ty, W.tx);
       __syncwarp();  // the warp has read the whole raw tile
-      store_rowmajor<1>(tile, acc, W.ty, W.tx);
+      store_colmajor<1>(tile, acc, W.ty, W.tx);
     }
     fence_async();  // the L tiles written above are read by bulk copies from the next panel on
     __syncthreads();
@@ -932,32 +934,33 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
                               [&](int c, float* st, uint64_t* bar, int lane) {
                                 if (lane == 0) {
                                   const int cc = c0 + c, K = C + cc / UC, qq = cc % UC;
-                                  mbar_expect_tx(bar, 2 * CH * 4);
-                                  bulk_g2s(st, Arow + (size_t)cc * CH, CH * 4, bar);
-                                  bulk_g2s(st + CH, Lg + (size_t)tri(K, C) * TF + (size_t)qq * CH, CH * 4, bar);
+                                  mbar_expect_tx(bar, 2 * CH * 4);  // operands swapped: acc[c][i] = sum_k X(k,c) L(i,k)
+                                  bulk_g2s(st + CH, Arow + (size_t)cc * CH, CH * 4, bar);
+                                  bulk_g2s(st, Lg + (size_t)tri(K, C) * TF + (size_t)qq * CH, CH * 4, bar);
                                 }
                               },
                               [](int) { return (const float*)nullptr; });
             const int part = W.w - first_warp_after(U, off);
             volatile int* cnt = s.cnt + C;
             float* Y = s.panel + (size_t)C * TF;
-            flush_begin(cnt, part);
-            if (part == 0) store_rowmajor<-1>(Y, acc, W.ty, W.tx);
-            else sub_rowmajor(Y, acc, W.ty, W.tx);
+            flush_begin(cnt, part);  // (the transposed accumulators land ROW-major through the conflict-free pattern)
+            if (part == 0) store_colmajor<-1>(Y, acc, W.ty, W.tx);
+            else sub_colmajor(Y, acc, W.ty, W.tx);
             flush_end(cnt, part, W.lane);
           }
         }
       }
       __syncthreads();
+      pc.tick(14);
       // X(I,C) = L_II^-1 Y(C), one tile per warp, operands resident
       for (int C = W.w; C < I; C += NW) {
         float* Y = s.panel + (size_t)C * TF;
         float acc[8][16];
         acc_zero(acc);
 #pragma unroll 1
-        for (int q = 0; q < UC; ++q) mk_chunk(acc, s.linv + q * CH, Y + q * CH, W.ty, W.tx);
+        for (int q = 0; q < UC; ++q) mk_chunk(acc, Y + q * CH, s.linv + q * CH, W.ty, W.tx);  // acc[c][r] = X(r,c)
         __syncwarp();  // the warp has read all of Y
-        store_rowmajor<1>(Y, acc, W.ty, W.tx);
+        store_colmajor<1>(Y, acc, W.ty, W.tx);
       }
       fence_async();  // panel tiles (X row block I) are read by the bulk stores below
       __syncthreads();

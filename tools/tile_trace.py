@@ -28,6 +28,8 @@ for T in [int(a) for a in sys.argv[1:]] or [512]:
         print('T=%d %s: %d pairs by CTA 0, %.0f cycles/pair: ' % (T, name, t[63], tot) +
               ' | '.join('%s %.0f' % (lab, t[48 + i] / n) for i, lab in enumerate(labels)), flush=True)
         print('      diag-tile phase split: prefill %.0f | warp 0 k-loop %.0f | warp 0 flush %.0f' % (t[59] / n, t[60] / n, t[61] / n), flush=True)
+        if name == "bwd":
+            print('      inverse: staged products %.0f (the rest of inv.gemm is the L_II^-1 multiply)' % (t[62] / n), flush=True)
         if t[35]:
             print('      staged loops of warp 0 (cycles per chunk of 8 steps, %d chunks): wait %.0f | compute %.0f | issue %.0f' % (
                 t[35], t[32] / t[35], t[33] / t[35], t[34] / t[35]), flush=True)
