@@ -293,6 +293,7 @@ __device__ __forceinline__ void team_sync() { asm volatile("bar.sync 5, 64;" :::
 struct PhClock {
   long long t0;
   long long* dbg;
+  long long* dbg2;  // the trace buffer for every thread of CTA 0 (the diagonal team clocks itself)
   __device__ __forceinline__ void start() { if (dbg) t0 = clock64(); }
   __device__ __forceinline__ void tick(int k) {
     if (dbg) { const long long t = clock64(); dbg[48 + k] += t - t0; t0 = t; }
@@ -500,7 +501,7 @@ __device__ __forceinline__ void publish_diag(float* __restrict__ D, float* __res
 // all threads pre-filled with the generated kernel matrix, in part order (flush_begin / flush_end).
 // The diagonal tile is updated first, by all warps; then warps 6-7 factor and invert it (the serial chain of the panel,
 // ~20 K cycles) WHILE the other warps update the tiles below it, and join them for a smaller share when they are done.
-constexpr int kDiagChunks = 10;  // the team's factor + invert + publish, in units of one warp's chunk time (~2.3 K cycles)
+constexpr int kDiagChunks = 15;  // the team's factor + invert + publish, in units of one warp's chunk time (~2.3 K cycles)
 
 template <int KERNEL, class HookF>
 __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* __restrict__ Lg, Sm& s, WCtx& W, int* bad,
@@ -564,9 +565,11 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
       if (st < 0) st = 0;
       if (W.w >= 6) {
         float* mine = s.stg + (size_t)6 * WSTG_F;  // the team's own stage areas (one tile) as scratch; panel tile 0 is free (J > 0)
+        const long long tt0 = (pc.dbg2 && tid == NTHR - 64) ? clock64() : 0;
         factor_invert64<true>(D, s.dgq + TS * J, s.rdl, pr.T - TS * J, bad, s.linv, s.panel, mine);
         team_sync();
         publish_diag<true>(D, gdiag, mine);
+        if (pc.dbg2 && tid == NTHR - 64) pc.dbg2[57] += clock64() - tt0;
       }
       const int lo = team_bound(U, st, W.w), hi = team_bound(U, st, W.w + 1);
       if (hi > lo) {
@@ -699,6 +702,7 @@ __global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
   float* aa = s.v1;
   PhClock pc;
   pc.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
+  pc.dbg2 = (P.dbg && blockIdx.x == 0) ? P.dbg : nullptr;
   pc.start();
   for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
@@ -847,6 +851,7 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
   float* cum = s.v3;  // running column sums  sum_{j < i} eps_j X(j, l)
   PhClock pc;
   pc.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
+  pc.dbg2 = (P.dbg && blockIdx.x == 0) ? P.dbg : nullptr;
   pc.start();
   for (int p = blockIdx.x; p < d.B * d.D; p += gridDim.x) {
     const int b = p / d.D, dd = p - b * d.D;
@@ -1022,14 +1027,25 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
 #pragma unroll
       for (int c = 0; c < 16; ++c) tl[c] = s.ts[TS * lt + mcol(W.tx, c)];
       float part = 0.0f;
+      // K_p^-1 rows: the loads of row r+1 are issued before row r is consumed (each is an L2 round trip)
+      float4 kn[4];
+      {
+        const float* krow = kinv + (size_t)(TS * kt + mrow(W.ty, 0)) * ldr + TS * lt + 4 * W.tx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) kn[j] = __ldg(reinterpret_cast<const float4*>(krow + 16 * j));
+      }
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const int k = TS * kt + mrow(W.ty, r);
         const float tk = s.ts[k];
-        const float* krow = kinv + (size_t)k * ldr + TS * lt + 4 * W.tx;
         float4 kq[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) kq[j] = __ldg(reinterpret_cast<const float4*>(krow + 16 * j));
+        for (int j = 0; j < 4; ++j) kq[j] = kn[j];
+        if (r + 1 < 8) {
+          const float* krow = kinv + (size_t)(TS * kt + mrow(W.ty, r + 1)) * ldr + TS * lt + 4 * W.tx;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) kn[j] = __ldg(reinterpret_cast<const float4*>(krow + 16 * j));
+        }
         const float kv[16] = {kq[0].x, kq[0].y, kq[0].z, kq[0].w, kq[1].x, kq[1].y, kq[1].z, kq[1].w,
                               kq[2].x, kq[2].y, kq[2].z, kq[2].w, kq[3].x, kq[3].y, kq[3].z, kq[3].w};
 #pragma unroll

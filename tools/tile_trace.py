@@ -28,6 +28,7 @@ for T in [int(a) for a in sys.argv[1:]] or [512]:
         print('T=%d %s: %d pairs by CTA 0, %.0f cycles/pair: ' % (T, name, t[63], tot) +
               ' | '.join('%s %.0f' % (lab, t[48 + i] / n) for i, lab in enumerate(labels)), flush=True)
         print('      diag-tile phase split: prefill %.0f | warp 0 k-loop %.0f | warp 0 flush %.0f' % (t[59] / n, t[60] / n, t[61] / n), flush=True)
+        print('      diagonal team (warps 6-7): %.0f cycles per pair in factor + invert + publish (6 panels)' % (t[57] / n), flush=True)
         if name == "bwd":
             print('      inverse: staged products %.0f (the rest of inv.gemm is the L_II^-1 multiply)' % (t[62] / n), flush=True)
         if t[35]:
