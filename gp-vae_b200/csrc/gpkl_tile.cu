@@ -41,7 +41,7 @@
 #include <string.h>
 
 #include "gpkl_common.cuh"
-#include "gpkl_diag.cuh"
+#include "gpkl_diag64.cuh"
 #include "gpkl_launch.h"
 
 namespace gpkl {
@@ -69,7 +69,7 @@ struct TLay {
   __host__ __device__ int ntri() const { return nT * (nT + 1) / 2; }
   __host__ __device__ size_t nvec() const { return (size_t)NVEC + 2 * (size_t)(S > 1 ? S - 1 : 0); }
   __host__ __device__ size_t floats() const {
-    return 64 /*red*/ + 32 /*mbarriers*/ + 16 /*flush counters*/ + 64 /*rdl*/ + (size_t)nT * TF + (size_t)NW * WSTG_F + TF +
+    return 64 /*red*/ + 32 /*mbarriers*/ + 16 /*flush counters*/ + 64 /*rdl*/ + 576 /*diag-block scratch*/ + (size_t)nT * TF + (size_t)NW * WSTG_F + TF +
            nvec() * TP;
   }
 };
@@ -305,13 +305,14 @@ struct Sm {
   double* red;
   uint64_t* bars;
   int* cnt;
-  float *rdl, *panel, *stg, *linv;
+  float *rdl, *dsm, *panel, *stg, *linv;
   float *ts, *mm, *dgq, *v0, *v1, *v2, *v3, *v4, *eps, *zacc;  // v0..v4: direction-specific vectors (see kernels)
   __device__ Sm(float* base, const TLay& L) {
     red = reinterpret_cast<double*>(base); base += 64;
     bars = reinterpret_cast<uint64_t*>(base); base += 32;
     cnt = reinterpret_cast<int*>(base); base += 16;
     rdl = base; base += 64;
+    dsm = base; base += 576;
     panel = base; base += (size_t)L.nT * TF;
     stg = base; base += (size_t)NW * WSTG_F;
     linv = base; base += TF;
@@ -351,144 +352,23 @@ struct Pair {
   }
 };
 
-// ---- the 64 x 64 diagonal block: Cholesky + inverse in shared memory, all 256 threads ------------------------------------
-// D: the block, column-major (D[c*64 + i], i >= c valid), factored in place.  dgl: diag(L) out (64), rdl: 1/diag(L) out (64).
-// Tl: number of real rows of the block (may exceed 64).  Output LT[c'][c] = Linv[c][c'] (the contraction-major operand of
-// both uses: rows-below = raw Linv^T and X = Linv Y), zeros where c < c'.  Lrm (scratch, one tile): Linv row-major, the
-// contraction-major operand of the inverse's own products; tmpR: >= 768 floats of scratch.
-// By 16-column sub-panels P = 0..3, three barriers each:
-//   (1) warp 0 factors the 16 x 16 diagonal block in registers (diag_factor, the serial chain: ~2.4 K cycles) WHILE the other
-//       warps form the right-hand side of the inverse's block row P,  R = -L[P, 0:16P] Linv[0:16P, 0:16P]  (4 x 4 register tiles)
-//   (2) rows below the diagonal block are solved one per thread, and AT THE SAME TIME other threads solve the inverse's
-//       block row,  Linv[P, :] = L_PP^-1 [R | I]  (one column per thread)
-//   (3) the trailing columns are updated in 4 x 4 tiles.
-// TEAM: the routine is run by warps 6 and 7 alone (64 threads, named barrier 5) while the other warps update the panel.
-template <bool TEAM>
-__device__ __forceinline__ void factor_invert64(float* __restrict__ D, float* __restrict__ dgl, float* __restrict__ rdl, int Tl,
-                                                int* bad, float* __restrict__ LT, float* __restrict__ Lrm,
-                                                float* __restrict__ tmpR) {
-  constexpr int NT = TEAM ? 64 : NTHR;
-  const int tid = TEAM ? (int)threadIdx.x - (NTHR - 64) : (int)threadIdx.x;
-  auto sync = [] { if (TEAM) team_sync(); else __syncthreads(); };
-  for (int e = tid * 4; e < TF; e += NT * 4) {
-    *reinterpret_cast<float4*>(LT + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    *reinterpret_cast<float4*>(Lrm + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+// ---- the 64 x 64 diagonal block: factor + invert + publish by the DIAGONAL TEAM (warps 6 and 7, named barrier 5) ----------
+// D: the block, column-major (D[c*64 + i], i >= c valid).  Out: dgl = diag(L), rdl = 1/diag(L); gt = the global L tile
+// (column-major, zeros above the diagonal); D = L ROW-major (zeros above the diagonal); LT[c'][c] = Linv[c][c'] (the
+// contraction-major operand of both uses: rows-below = raw Linv^T and X = Linv Y), zeros where c < c'.  Rsw, Xsw: one
+// tile of scratch each.  Tl: number of real rows of the block (may exceed 64).  See gpkl_diag64.cuh for the algorithm.
+__device__ __forceinline__ void diag_block64(float* __restrict__ D, float* __restrict__ gt, float* __restrict__ dgl,
+                                             float* __restrict__ rdl, int Tl, int* bad, float* __restrict__ LT,
+                                             float* __restrict__ Rsw, float* __restrict__ Xsw, float* __restrict__ small) {
+  const int t = (int)threadIdx.x - (NTHR - 64);  // 0..63
+  factor_invert64_rows(D, gt, dgl, rdl, Tl, bad, Rsw, Xsw, small, small + 64, t, [] { team_sync(); });
+  for (int e = t; e < TF / 4; e += 64) {
+    const int i = e >> 4, g = e & 15;
+    *reinterpret_cast<float4*>(D + i * TS + 4 * g) = *reinterpret_cast<const float4*>(Rsw + swz64(i, g));
+    *reinterpret_cast<float4*>(LT + i * TS + 4 * g) = *reinterpret_cast<const float4*>(Xsw + swz64(i, g));
   }
-  sync();
-  for (int P = 0; P < 4; ++P) {
-    const int jl = 16 * P;
-    if (tid < 32) {
-      diag_factor<false>(D, TS, jl, Tl, D + (size_t)jl * TS, TS, dgl, rdl, bad);
-    } else {
-      // R[r][col] = -sum_{k = col..jl-1} L[jl + r][k] Linv[k][col], col < jl: 4 row groups x (jl/4) column groups
-      for (int id = tid - 32; id < jl; id += NT - 32) {
-        const int r4 = id & 3, c4 = id >> 2;
-        float acc[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
-        for (int k = 4 * c4; k < jl; ++k) {
-          const float4 u4 = *reinterpret_cast<const float4*>(D + (size_t)k * TS + jl + 4 * r4);
-          const float4 v4 = *reinterpret_cast<const float4*>(Lrm + (size_t)k * TS + 4 * c4);
-          const float u[4] = {u4.x, u4.y, u4.z, u4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(-u[r], v[c], acc[r][c]);
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<float4*>(tmpR + (size_t)(4 * c4 + c) * 16 + 4 * r4) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
-      }
-    }
-    sync();
-    const int nbelow = TS - jl - 16;
-    if (tid < nbelow) {
-      const int i = jl + 16 + tid;
-      float b[16];
-#pragma unroll
-      for (int c = 0; c < 16; ++c) b[c] = D[(size_t)(jl + c) * TS + i];
-      diag_solve16(b, D, TS, jl, rdl);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) D[(size_t)(jl + c) * TS + i] = b[c];
-    }
-    // (with 256 threads the two solves run side by side on different threads; the team of 64 does them one after the other)
-    const int ctid = TEAM ? tid : tid - 64;
-    if (ctid >= 0 && ctid < jl + 16) {
-      const int col = ctid;
-      float b[16];
-      if (col < jl) {
-#pragma unroll
-        for (int r = 0; r < 16; r += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(tmpR + (size_t)col * 16 + r);
-          b[r] = t4.x; b[r + 1] = t4.y; b[r + 2] = t4.z; b[r + 3] = t4.w;
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) b[r] = (r == col - jl) ? 1.0f : 0.0f;
-      }
-      diag_solve16(b, D, TS, jl, rdl);
-#pragma unroll
-      for (int r = 0; r < 16; r += 4)
-        *reinterpret_cast<float4*>(LT + (size_t)col * TS + jl + r) = make_float4(b[r], b[r + 1], b[r + 2], b[r + 3]);
-#pragma unroll
-      for (int r = 0; r < 16; ++r) Lrm[(size_t)(jl + r) * TS + col] = b[r];
-    }
-    sync();
-    const int nt4 = nbelow >> 2;
-    for (int id = tid; id < nt4 * nt4; id += NT) {
-      const int rt = id / nt4, ct = id - rt * nt4;
-      if (rt < ct) continue;
-      const int rb = jl + 16 + 4 * rt, cb = jl + 16 + 4 * ct;
-      float acc[4][4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float4 a4 = *reinterpret_cast<const float4*>(D + (size_t)(cb + c) * TS + rb);
-        acc[0][c] = a4.x; acc[1][c] = a4.y; acc[2][c] = a4.z; acc[3][c] = a4.w;
-      }
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float4 u4 = *reinterpret_cast<const float4*>(D + (size_t)(jl + k) * TS + rb);
-        const float4 v4 = *reinterpret_cast<const float4*>(D + (size_t)(jl + k) * TS + cb);
-        const float u[4] = {u4.x, u4.y, u4.z, u4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(-u[r], v[c], acc[r][c]);
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<float4*>(D + (size_t)(cb + c) * TS + rb) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
-    }
-    if (nt4 > 0) sync();
-  }
-}
-
-// Publish the factored diagonal block: the global L tile (column-major, zeros above the diagonal) and, in place, the
-// ROW-major copy (zeros above the diagonal) -- the transposition goes through an XOR-swizzled scratch tile so that both
-// passes are conflict-free.  Thread set as factor_invert64.
-template <bool TEAM>
-__device__ __forceinline__ void publish_diag(float* __restrict__ D, float* __restrict__ gt, float* __restrict__ tmp) {
-  constexpr int NT = TEAM ? 64 : NTHR;
-  const int tid = TEAM ? (int)threadIdx.x - (NTHR - 64) : (int)threadIdx.x;
-  for (int e = tid * 4; e < TF; e += NT * 4) {
-    const int c = e >> 6, i = e & 63;
-    const float4 d4 = *reinterpret_cast<const float4*>(D + e);
-    const float o[4] = {i >= c ? d4.x : 0.0f, i + 1 >= c ? d4.y : 0.0f, i + 2 >= c ? d4.z : 0.0f, i + 3 >= c ? d4.w : 0.0f};
-    *reinterpret_cast<float4*>(gt + e) = make_float4(o[0], o[1], o[2], o[3]);
-  }
-  for (int e = tid; e < TF; e += NT) {
-    const int c = e >> 6, i = e & 63;
-    tmp[i * TS + (c ^ (i & 31))] = (i >= c) ? D[e] : 0.0f;
-  }
-  if (TEAM) team_sync(); else __syncthreads();
-  for (int e = tid; e < TF; e += NT) {
-    const int i = e >> 6, c = e & 63;
-    D[e] = tmp[i * TS + (c ^ (i & 31))];
-  }
-  fence_async();  // the scratch is a stage area (thread writes); bulk copies overwrite it next
-  if (TEAM) team_sync(); else __syncthreads();
+  fence_async();  // the scratch tiles are stage areas (thread writes); bulk copies overwrite them next
+  team_sync();
 }
 
 // ---- the factorisation of K_q by 64-column panels -------------------------------------------------------------------------
@@ -501,7 +381,7 @@ __device__ __forceinline__ void publish_diag(float* __restrict__ D, float* __res
 // all threads pre-filled with the generated kernel matrix, in part order (flush_begin / flush_end).
 // The diagonal tile is updated first, by all warps; then warps 6-7 factor and invert it (the serial chain of the panel,
 // ~20 K cycles) WHILE the other warps update the tiles below it, and join them for a smaller share when they are done.
-constexpr int kDiagChunks = 15;  // the team's factor + invert + publish, in units of one warp's chunk time (~2.3 K cycles)
+constexpr int kDiagChunks = 4;  // the team's factor + invert + publish, in units of one warp's chunk time (~2.3 K cycles)
 
 template <int KERNEL, class HookF>
 __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* __restrict__ Lg, Sm& s, WCtx& W, int* bad,
@@ -555,10 +435,9 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
     float* D = s.panel + (size_t)J * TF;
     float* gdiag = Lg + (size_t)tri(J, J) * TF;
     const bool team = J > 0 && m > 1;
-    if (!team) {
-      factor_invert64<false>(D, s.dgq + TS * J, s.rdl, pr.T - TS * J, bad, s.linv, s.stg, s.stg + TF);
+    if (!team) {  // first panel (nothing to update) or last one (no tiles below): the team works alone, all stage areas are idle
+      if (W.w >= 6) diag_block64(D, gdiag, s.dgq + TS * J, s.rdl, pr.T - TS * J, bad, s.linv, s.stg, s.stg + TF, s.dsm);
       __syncthreads();
-      publish_diag<false>(D, gdiag, s.stg);
     } else {
       const int U = (m - 1) * n;  // chunks of the tiles below the diagonal one
       int st = (U + 2 * kDiagChunks) / NW - kDiagChunks;  // the team's share once it has finished the diagonal block
@@ -566,9 +445,7 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
       if (W.w >= 6) {
         float* mine = s.stg + (size_t)6 * WSTG_F;  // the team's own stage areas (one tile) as scratch; panel tile 0 is free (J > 0)
         const long long tt0 = (pc.dbg2 && tid == NTHR - 64) ? clock64() : 0;
-        factor_invert64<true>(D, s.dgq + TS * J, s.rdl, pr.T - TS * J, bad, s.linv, s.panel, mine);
-        team_sync();
-        publish_diag<true>(D, gdiag, mine);
+        diag_block64(D, gdiag, s.dgq + TS * J, s.rdl, pr.T - TS * J, bad, s.linv, mine, s.panel, s.dsm);
         if (pc.dbg2 && tid == NTHR - 64) pc.dbg2[57] += clock64() - tt0;
       }
       const int lo = team_bound(U, st, W.w), hi = team_bound(U, st, W.w + 1);
