@@ -1598,7 +1598,7 @@ cudaError_t launch_kp(const Params& P_in, bool backward, cudaStream_t st) {
   attr.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &attr;
   cfg.numAttrs = 0;
-  if (share) {
+  if (share && !(tile && !backward)) {  // (the tile tier's forward pass has a pre-pass of its own: float64 K_p^-1, gpkl_prior64.cu)
     void (*pk)(Params, int);
     if (!sh_resident) pk = backward ? prior_block<KERNEL, true, true> : prior_block<KERNEL, true, false>;
     else pk = backward ? prior_block<KERNEL, false, true> : prior_block<KERNEL, false, false>;

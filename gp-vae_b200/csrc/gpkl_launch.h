@@ -49,6 +49,10 @@ cudaError_t launch_block(const Params& P, bool backward, cudaStream_t st);
 bool tile_tier_supports(const GpklDesc& d, bool backward);
 size_t tile_slot_floats(const GpklDesc& d);
 cudaError_t launch_tile(const Params& P, bool backward, cudaStream_t st);
+// float64 per-sequence prior record of the tile tier's forward pass (gpkl_prior64.cu): K_p^-1 (lower triangle, column-major,
+// pitch TP = T_max rounded up to 64) followed by log|K_p|; fits the records sized by prior_record_floats
+size_t prior64_record_floats(int T_max);
+cudaError_t launch_prior_inv64(const Params& P, cudaStream_t st);
 
 // reconstruction term (gpkl_recon.cu), SURVEY.md S8(f) row 1
 int recon_grid(long long rows);

@@ -1,0 +1,205 @@
+// Per-SEQUENCE prior record of the tile tier's forward pass: K_p^-1 and log|K_p| in float64.
+//
+// The reference evaluates  tr(K_p^-1 K_q)  in float64 with an LU inverse of the float32-built K_p
+// (src/Models/Full_GP_VAE_dynamic_time.py:250-254), once per (sequence, latent-dim) pair although K_p is the same for the D
+// pairs of a sequence (prior_time_chars is one constant, :114).  Round 1 evaluated the trace as ||L_p^-1 L_q||_F^2 -- a
+// T^3/6-FMA triangular product PER PAIR, half of the forward pass at T = 512 -- because a float32 K_p^-1 loses
+// cond(K) * eps in the entrywise form.  With K_p^-1 in float64 the entrywise form is exact to ~1e-13 and costs O(T^2) per
+// pair:   tr(K_p^-1 (K_q + m m^T)) = sum_ij Kinv_ij (K_q,ij + m_i m_j),  fused into the pass that generates K_q (gpkl_tile.cu).
+// The float64 inverse costs T^3/2 DFMA per SEQUENCE (C4: 1,024 sequences against 65,536 pairs).
+//
+// Algorithm: blocked symmetric SWEEP operator, in place on the lower triangle (column-major, A[c*TP + i], i >= c), NB = 16
+// pivots at a time.  For the pivot block P = A_kk:  H = P^-1 (scalar sweeps in shared memory, the pivots give log|K_p|),
+// W = the block row/column (all other indices), V = W H, then ONE uniform rank-NB update of the whole lower triangle
+// A_ij -= V_i W_j^T (rows of the pivot block carry W = 0), A_ik <- V_i, A_kk <- -H.  After all blocks A = -K_p^-1 (negated at
+// the end).  Every pivot block is a Schur complement of an SPD matrix, so no pivoting is needed.  The update runs in 4 x 4
+// register tiles with both operands contraction-major in shared memory ([c][i]: a warp reads consecutive rows -- no bank
+// conflicts -- and the other operand is a broadcast), the next tile of A is prefetched while the current one is computed.
+// No tensor cores (north_star); DFMA on the FP64 pipe.
+#include "gpkl_common.cuh"
+#include "gpkl_launch.h"
+
+namespace gpkl {
+namespace {
+
+constexpr int NB = 16;
+constexpr int NT = 256;
+
+__host__ __device__ inline int p64_tp(int T_max) {
+  int TP = (T_max + 63) / 64 * 64;
+  return TP < 64 ? 64 : TP;
+}
+__host__ __device__ inline int p64_ldw(int TP) { return TP + 2; }  // operand row pitch (doubles): 16-byte aligned, rows 4 banks apart
+
+template <int KERNEL>
+__global__ void __launch_bounds__(NT, 1) prior_inv64_kernel(Params P) {
+  extern __shared__ __align__(16) double smd[];
+  if (*P.prior_flag == 0) return;  // ell_p differs between latent dims: the per-pair kernels take their per-pair path
+  const GpklDesc& d = P.d;
+  const int TP = p64_tp(d.T_max), ldw = p64_ldw(TP);
+  double* Wt = smd;
+  double* Vt = Wt + (size_t)NB * ldw;
+  double* Pm = Vt + (size_t)NB * ldw;  // [NB][NB + 1]
+  float* ts = reinterpret_cast<float*>(Pm + NB * (NB + 1));
+  const int tid = threadIdx.x;
+  const float noise = d.noise, sig = (float)(1.0 - (double)noise);
+  const KernC<KERNEL> kc(P.ell_p[0], sig);
+  for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
+    const int n = P.lengths[b];
+    double* A = reinterpret_cast<double*>(P.prior + (size_t)b * P.prior_stride);
+    __syncthreads();
+    if (n <= 0) {
+      if (tid == 0) A[(size_t)TP * TP] = 0.0;
+      continue;
+    }
+    for (int i = tid; i < n; i += NT) ts[i] = P.times[(size_t)b * d.T_max + i];
+    __syncthreads();
+    // K_p, lower triangle: the float32 kernel values (as every tier builds them) cast to float64
+    for (int c = 0; c < n; ++c) {
+      const float tc = ts[c];
+      for (int i = c + tid; i < n; i += NT) A[(size_t)c * TP + i] = (double)(kc.val(ts[i] - tc) + (i == c ? noise : 0.0f));
+    }
+    double logdet = 0.0;
+    int bad = 0;
+    const int n4 = (n + 3) >> 2;
+    for (int k0 = 0; k0 < n; k0 += NB) {
+      const int nb = n - k0 < NB ? n - k0 : NB;
+      __syncthreads();  // the previous panel's write-back (and the build) are visible
+      // ---- pivot block -> Pm (full symmetric; identity beyond nb) ----------------------------------------------------
+      {
+        const int r = tid >> 4, c = tid & 15;
+        const int hi = r > c ? r : c, lo = r > c ? c : r;
+        Pm[r * (NB + 1) + c] = (r < nb && c < nb) ? A[(size_t)(k0 + lo) * TP + k0 + hi] : (r == c ? 1.0 : 0.0);
+      }
+      // ---- W^T: the block row / column of every other index (zero for the block's own rows and beyond n) -----------------
+      for (int e = tid; e < k0 * NB; e += NT) {  // rows above the block: A(k0+c, i) stored as A[i*TP + k0 + c]
+        const int i = e >> 4, c = e & 15;
+        Wt[(size_t)c * ldw + i] = c < nb ? A[(size_t)i * TP + k0 + c] : 0.0;
+      }
+      for (int c = 0; c < NB; ++c)
+        for (int i = k0 + tid; i < 4 * n4; i += NT)
+          Wt[(size_t)c * ldw + i] = (c < nb && i >= k0 + nb && i < n) ? A[(size_t)(k0 + c) * TP + i] : 0.0;
+      __syncthreads();
+      // ---- H = P^-1 by scalar sweeps (Pm <- -P^-1); pivots -> log|K_p| --------------------------------------------------
+      {
+        const int r = tid >> 4, c = tid & 15;
+        for (int s = 0; s < nb; ++s) {
+          const double dv = Pm[s * (NB + 1) + s];
+          const double x = Pm[r * (NB + 1) + c], prs = Pm[r * (NB + 1) + s], psc = Pm[s * (NB + 1) + c];
+          __syncthreads();
+          const double inv = 1.0 / dv;
+          Pm[r * (NB + 1) + c] = (r == s) ? (c == s ? -inv : psc * inv) : (c == s ? prs * inv : x - prs * psc * inv);
+          if (tid == 0) {
+            logdet += log(dv);
+            if (!(dv > 0.0)) bad = 1;
+          }
+          __syncthreads();
+        }
+      }
+      // ---- V = W H = -W Pm ---------------------------------------------------------------------------------------------
+      for (int i = tid; i < 4 * n4; i += NT) {
+        double v[NB];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) v[c] = 0.0;
+#pragma unroll 4
+        for (int cp = 0; cp < NB; ++cp) {
+          const double wv = -Wt[(size_t)cp * ldw + i];
+#pragma unroll
+          for (int c = 0; c < NB; ++c) v[c] = fma(wv, Pm[cp * (NB + 1) + c], v[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NB; ++c) Vt[(size_t)c * ldw + i] = v[c];
+      }
+      __syncthreads();
+      // ---- A_ij -= V_i W_j^T over the lower triangle, 4 x 4 tiles walked column by column, next tile prefetched ----------
+      {
+        int J4 = 0, r = tid;
+        auto settle = [&]() {
+          while (J4 < n4 && r >= n4 - J4) { r -= n4 - J4; ++J4; }
+        };
+        settle();
+        double a[4][4];
+        auto load_tile = [&](int I4t, int J4t) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const double* ptr = A + (size_t)(4 * J4t + jj) * TP + 4 * I4t;
+            const double2 lo = *reinterpret_cast<const double2*>(ptr), hi = *reinterpret_cast<const double2*>(ptr + 2);
+            a[jj][0] = lo.x; a[jj][1] = lo.y; a[jj][2] = hi.x; a[jj][3] = hi.y;
+          }
+        };
+        if (J4 < n4) load_tile(J4 + r, J4);
+        while (J4 < n4) {
+          const int I4 = J4 + r, cJ4 = J4;
+          double cur[4][4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) cur[jj][ii] = a[jj][ii];
+          r += NT;
+          settle();
+          if (J4 < n4) load_tile(J4 + r, J4);
+          const double* vp = Vt + 4 * I4;
+          const double* wp = Wt + 4 * cJ4;
+#pragma unroll
+          for (int c = 0; c < NB; ++c) {
+            const double2 v0 = *reinterpret_cast<const double2*>(vp + (size_t)c * ldw), v1 = *reinterpret_cast<const double2*>(vp + (size_t)c * ldw + 2);
+            const double2 w0 = *reinterpret_cast<const double2*>(wp + (size_t)c * ldw), w1 = *reinterpret_cast<const double2*>(wp + (size_t)c * ldw + 2);
+            const double vv[4] = {v0.x, v0.y, v1.x, v1.y}, ww[4] = {w0.x, w0.y, w1.x, w1.y};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii) cur[jj][ii] = fma(-ww[jj], vv[ii], cur[jj][ii]);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            double* ptr = A + (size_t)(4 * cJ4 + jj) * TP + 4 * I4;
+            *reinterpret_cast<double2*>(ptr) = make_double2(cur[jj][0], cur[jj][1]);
+            *reinterpret_cast<double2*>(ptr + 2) = make_double2(cur[jj][2], cur[jj][3]);
+          }
+        }
+      }
+      __syncthreads();
+      // ---- write back: A_ik <- V_i (row part and column part), A_kk <- Pm = -H ---------------------------------------------
+      for (int e = tid; e < k0 * NB; e += NT) {
+        const int i = e >> 4, c = e & 15;
+        if (c < nb) A[(size_t)i * TP + k0 + c] = Vt[(size_t)c * ldw + i];
+      }
+      for (int c = 0; c < nb; ++c)
+        for (int i = k0 + nb + tid; i < n; i += NT) A[(size_t)(k0 + c) * TP + i] = Vt[(size_t)c * ldw + i];
+      {
+        const int r = tid >> 4, c = tid & 15;
+        if (r < nb && c <= r) A[(size_t)(k0 + c) * TP + k0 + r] = Pm[r * (NB + 1) + c];
+      }
+    }
+    __syncthreads();
+    // A = -K_p^-1 -> K_p^-1
+    for (int c = 0; c < n; ++c)
+      for (int i = c + tid; i < n; i += NT) A[(size_t)c * TP + i] = -A[(size_t)c * TP + i];
+    if (tid == 0) {
+      A[(size_t)TP * TP] = logdet;
+      if (bad && P.status) atomicAdd(P.status, 1);
+    }
+  }
+}
+
+}  // namespace
+
+size_t prior64_record_floats(int T_max) {
+  const size_t TP = p64_tp(T_max);
+  return 2 * (TP * TP + 2);
+}
+
+cudaError_t launch_prior_inv64(const Params& P, cudaStream_t st) {
+  const int TP = p64_tp(P.d.T_max);
+  const size_t smem = ((size_t)2 * NB * p64_ldw(TP) + NB * (NB + 1)) * sizeof(double) + (size_t)TP * sizeof(float);
+  if (smem > kMaxDynSmem || P.prior_stride < prior64_record_floats(P.d.T_max)) return cudaErrorInvalidValue;
+  void (*kern)(Params) = P.d.kernel == GPKL_KERNEL_RBF ? prior_inv64_kernel<GPKL_KERNEL_RBF> : prior_inv64_kernel<GPKL_KERNEL_CAUCHY>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int grid = P.d.B < kNumSMs ? P.d.B : kNumSMs;
+  kern<<<grid, NT, smem, st>>>(P);
+  note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace gpkl

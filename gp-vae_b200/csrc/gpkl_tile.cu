@@ -383,9 +383,13 @@ __device__ __forceinline__ void diag_block64(float* __restrict__ D, float* __res
 // ~20 K cycles) WHILE the other warps update the tiles below it, and join them for a smaller share when they are done.
 constexpr int kDiagChunks = 4;  // the team's factor + invert + publish, in units of one warp's chunk time (~2.3 K cycles)
 
+// kinv (forward only, else NULL): this sequence's K_p^-1 in float64 (lower triangle, column-major, pitch ldk; gpkl_prior64.cu);
+// the pass that generates K_q also accumulates  tr(K_p^-1 (K_q + m m^T)) = sum_ij Kinv_ij (K_q,ij + m_i m_j)  into tr (per
+// thread, float64; lower entries count twice) -- the reference's own float64 trace (Full_GP_VAE_dynamic_time.py:250-254).
 template <int KERNEL, class HookF>
 __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* __restrict__ Lg, Sm& s, WCtx& W, int* bad,
-                                                 PhClock& pc, HookF hook) {
+                                                 PhClock& pc, HookF hook, const double* __restrict__ kinv = nullptr, int ldk = 0,
+                                                 double* tr = nullptr) {
   const int tid = threadIdx.x;
   const int nTb = pr.nTb;
   const float* Arow = nullptr;  // operands of the current segment (bulk-copy sources)
@@ -408,12 +412,55 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
       prime_chunks(W, dhi - dlo, issue);
     }
     if (tid < NW) s.cnt[tid] = 0;
-    for (int ti = 0; ti < m; ++ti) {
-      float* dst = s.panel + (size_t)(J + ti) * TF;
-      for (int e = tid * 4; e < TF; e += NTHR * 4) {
-        const int c = e >> 6, i = e & 63;
-        *reinterpret_cast<float4*>(dst + e) = pr.kgen4(TS * J + c, TS * (J + ti) + i, s.ts);
+    if (!kinv) {
+      for (int ti = 0; ti < m; ++ti) {
+        float* dst = s.panel + (size_t)(J + ti) * TF;
+        for (int e = tid * 4; e < TF; e += NTHR * 4) {
+          const int c = e >> 6, i = e & 63;
+          *reinterpret_cast<float4*>(dst + e) = pr.kgen4(TS * J + c, TS * (J + ti) + i, s.ts);
+        }
       }
+    } else {
+      // each thread: four 4-row pieces per tile (columns c0 + 16 it, rows i0..i0+3); the K_p^-1 entries of the NEXT tile are
+      // in flight (L2 round trips) while the current one is generated and accumulated
+      constexpr int NIT = TF / (NTHR * 4);
+      const int c0 = (tid * 4) >> 6, i0 = (tid * 4) & 63;
+      double2 q[NIT][2];
+      auto fetch = [&](int ti) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const double* kp = kinv + (size_t)(TS * J + c0 + 16 * it) * ldk + TS * (J + ti) + i0;
+          q[it][0] = __ldg(reinterpret_cast<const double2*>(kp));
+          q[it][1] = __ldg(reinterpret_cast<const double2*>(kp + 2));
+        }
+      };
+      fetch(0);
+      double acc = 0.0;
+      for (int ti = 0; ti < m; ++ti) {
+        float* dst = s.panel + (size_t)(J + ti) * TF;
+        double2 qc[NIT][2];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) { qc[it][0] = q[it][0]; qc[it][1] = q[it][1]; }
+        if (ti + 1 < m) fetch(ti + 1);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int col = TS * J + c0 + 16 * it, row = TS * (J + ti) + i0;
+          const float4 kv = pr.kgen4(col, row, s.ts);
+          *reinterpret_cast<float4*>(dst + (c0 + 16 * it) * TS + i0) = kv;
+          const double mc = (double)s.mm[col];
+          const float kf[4] = {kv.x, kv.y, kv.z, kv.w};
+          const double kd[4] = {qc[it][0].x, qc[it][0].y, qc[it][1].x, qc[it][1].y};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = row + e;
+            if (i >= col && i < pr.T) {  // (col <= i < T)
+              const double term = kd[e] * fma((double)s.mm[i], mc, (double)kf[e]);
+              acc += (i == col) ? term : 2.0 * term;
+            }
+          }
+        }
+      }
+      *tr += acc;
     }
     __syncthreads();
     pc.tick(11);
@@ -573,10 +620,7 @@ __global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
   __syncthreads();
   const int S = d.S, TP = L.TP;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
-  const int ldr = TP + 4;  // row pitch of the block tier's prior records
   float* Lg = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
-  float* dgp = s.v0;
-  float* aa = s.v1;
   PhClock pc;
   pc.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
   pc.dbg2 = (P.dbg && blockIdx.x == 0) ? P.dbg : nullptr;
@@ -595,15 +639,12 @@ __global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
     }
     if (tid == 0) bad = 0;
     load_vectors(P, p, b, dd, T, r0, L, s, false);
-    const float* __restrict__ rec = P.prior + (size_t)b * P.prior_stride;
-    for (int i = tid; i < TP; i += NTHR) dgp[i] = __ldg(rec + (size_t)TP * ldr + i);
+    // this sequence's float64 record: K_p^-1 (lower, column-major, pitch TP) and log|K_p| (gpkl_prior64.cu)
+    const double* __restrict__ kinv = reinterpret_cast<const double*>(P.prior + (size_t)b * P.prior_stride);
     __syncthreads();
     const Pair<KERNEL> pr(T, P.ell_q[dd], sig, noise);
     const int nTb = pr.nTb;
-    // a = L_p^-1 m from the record (X_p column-major, X(i,k) at rec[k*ldr + i], exact zeros above the diagonal)
-    matvec_record(rec, ldr, s.mm, T, true, aa, s.stg);
-    float ssq = 0.0f;
-    __syncthreads();
+    double tr = 0.0;  // this thread's share of tr(K_p^-1 (K_q + m m^T))
     pc.tick(0);
     chol_panels_tile<KERNEL>(pr, Lg, s, W, &bad, pc, [&](int J) {
       const int m = nTb - J;
@@ -623,68 +664,17 @@ __global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
           s.zacc[(size_t)sx * TP + TS * J + idx] += a0 + a1;
         }
       }
-      // A(I,J) = sum_{K=J..I} X_p(I,K) L_q(K,J): tiles by decreasing length, dealt boustrophedon to the four warp PAIRS; the two
-      // warps of a pair split a tile's contraction in halves and the odd warp hands its partial tile over through the
-      // pair's stage areas (the sums must be complete before they are squared, and there is no destination tile to
-      // accumulate into)
-      const int q = W.w >> 1, odd = W.w & 1;
-      float* parea = s.stg + (size_t)q * TF;
-      for (int blk = 0; blk * 4 < m; ++blk) {
-        const int idx = blk * 4 + ((blk & 1) ? 3 - q : q);
-        if (idx >= m) continue;
-        const int I = nTb - 1 - idx;
-        const int n = UC * (I - J + 1), h = n >> 1;
-        const int c0 = odd ? h : 0, nc = odd ? n - h : h;
-        float acc[8][16];
-        acc_zero(acc);
-        const float* Abase = rec + (size_t)TS * I + (size_t)(TS * J + KC * c0) * ldr;  // rows k of X_p^T, 64 entries each
-        const float* Bbase = s.panel + (size_t)J * TF + (size_t)c0 * CH;
-        run_chunks<true>(acc, W, nc,
-                         [&](int c, float* st, uint64_t* bar, int lane) {
-                           if (lane == 0) mbar_expect_tx(bar, CH * 4);
-                           bulk_g2s(st + lane * TS, Abase + (size_t)(KC * c + lane) * ldr, TS * 4, bar);  // lanes 0..7: one row each
-                         },
-                         [&](int c) { return Bbase + (size_t)c * CH; });
-        pair_sync(q);  // both warps are done with their stages
-        if (odd) {
-          store_colmajor<1>(parea, acc, W.ty, W.tx);
-          fence_async();  // (the area is overwritten by bulk copies of the next job)
-        }
-        pair_sync(q);
-        if (!odd) {
-          add_colmajor(acc, parea, W.ty, W.tx);
-#pragma unroll
-          for (int r = 0; r < 8; ++r)
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const int i = TS * I + mrow(W.ty, r), cc = TS * J + mcol(W.tx, c);
-              const float v = (cc < i && i < T) ? acc[r][c] : 0.0f;
-              ssq = fmaf(v, v, ssq);
-            }
-        }
-        pair_sync(q);  // the partial has been read
-      }
-    });
-    // ---- z out, KL ----------------------------------------------------------------------------------------------------
+    }, kinv, TP, &tr);
+    // ---- z out, KL = 1/2 [tr(K_p^-1 (K_q + m m^T)) - T + log|K_p| - log|K_q|] ----------------------------------------------
     for (int i = tid; i < T; i += NTHR)
       for (int sx = 0; sx < S; ++sx) P.z[((size_t)S * r0 + (size_t)sx * T + i) * d.D + dd] = s.zacc[(size_t)sx * TP + i];
-    double part = (double)ssq, ldp = 0.0, ldq = 0.0;
-    for (int i = tid; i < T; i += NTHR) {
-      const double lpd = (double)dgp[i], lqd = (double)s.dgq[i];
-      const double av = (double)aa[i];
-      part += diag_term(lqd / lpd) + av * av;
-      if (P.logdets) {
-        ldp += 2.0 * log(lpd);
-        ldq += 2.0 * log(lqd);
-      }
-    }
-    part = block_sum(part, s.red);
-    if (P.logdets) {
-      ldp = block_sum(ldp, s.red);
-      ldq = block_sum(ldq, s.red);
-    }
+    double ldq = 0.0;
+    for (int i = tid; i < T; i += NTHR) ldq += 2.0 * log((double)s.dgq[i]);
+    const double trs = block_sum(tr, s.red);
+    ldq = block_sum(ldq, s.red);
     if (tid == 0) {
-      P.kl_pairs[p] = (float)(0.5 * part);
+      const double ldp = kinv[(size_t)TP * TP];
+      P.kl_pairs[p] = (float)(0.5 * (trs - (double)T + ldp - ldq));
       if (P.logdets) { P.logdets[2 * p] = (float)ldp; P.logdets[2 * p + 1] = (float)ldq; }
       if (bad && P.status) atomicAdd(P.status, 1);
     }
@@ -979,6 +969,10 @@ cudaError_t launch_tile(const Params& P_in, bool backward, cudaStream_t st) {
   // compact slots: this tier's own stride inside the block tier's slot area (forward needs the L triangle only)
   const TLay L(P.d.T_max, P.d.S);
   P.scratch_stride = backward ? tile_slot_floats(P.d) : (size_t)L.ntri() * TF;
+  if (!backward) {  // the forward pass reads float64 records of its own (the block tier's pre-pass is not launched for it)
+    const cudaError_t pe = launch_prior_inv64(P, st);
+    if (pe != cudaSuccess) return pe;
+  }
   void (*kern)(Params);
   if (P.d.kernel == GPKL_KERNEL_RBF) kern = backward ? bwd_tile<GPKL_KERNEL_RBF> : fwd_tile<GPKL_KERNEL_RBF>;
   else kern = backward ? bwd_tile<GPKL_KERNEL_CAUCHY> : fwd_tile<GPKL_KERNEL_CAUCHY>;
