@@ -9,8 +9,9 @@ cudaError_t launch_warp_inst(const Params& P, cudaStream_t st);
 
 bool warp_tier_supports(const GpklDesc& d, bool backward) {
   if (d.T_max > 64 || d.T_max < 1) return false;
-  if (backward && (d.flags & GPKL_FLAG_GRAD_ELL_P)) return false;  // d/d ell_p is served by the generic tier
   if (d.posterior != GPKL_POST_GP && d.posterior != GPKL_POST_DIAG) return false;
+  // d/d ell_p (trainable prior, Full_GP_VAE_fixed_for_MovMnist.py:96): GP posterior; its tables bound S by shared memory
+  if (backward && (d.flags & GPKL_FLAG_GRAD_ELL_P) && (d.posterior != GPKL_POST_GP || d.S > 4)) return false;
   if (d.S > 8) return false;  // S samples per pair live in registers; more than 8 are served by the block / generic tiers
   return true;
 }

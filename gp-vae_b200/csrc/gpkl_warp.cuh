@@ -349,6 +349,109 @@ __device__ __forceinline__ float contract_cols(const float (&x)[R][LP * R], cons
 }
 
 
+// ---- d/d ell_p in the warp tier (GPKL_FLAG_GRAD_ELL_P; trainable prior of Full_GP_VAE_fixed_for_MovMnist.py:96) ------------
+//   K_p-bar = g/2 (K_p^-1 - K_p^-1 (K_q + m m^T) K_p^-1),   d/d ell_p = <K_p-bar, dK_p/d ell_p> = g/2 (t1p - t3)
+//   t1p = <X_p^T X_p, dK_p>  (contract_cols with the prior's length scale),
+//   t3  = sum_j v_j^T dK_p v_j + alpha^T dK_p alpha,   V = K_p^-1 L_q = X_p^T A,  A = L_p^-1 L_q,  alpha = K_p^-1 m.
+// V(l, c) = <A_c, X_p,l> is the dot product contract_cols forms (register column x table column); its values are parked in a
+// TM x TM table, reloaded as register columns, and the quadratic forms run against a packed table of dK_p/d ell_p.
+
+// Vs[l*TM + c] = <x_c, M_l> for every l (0 for l >= T); M columns reversed-packed as for contract_cols.
+template <int LP, int R>
+__device__ __forceinline__ void dots_cols(const float (&x)[R][LP * R], const float* __restrict__ M, int lig, int T,
+                                          float* __restrict__ Vs) {
+  constexpr int TM = LP * R;
+#pragma unroll
+  for (int q = TM / 4 - 1; q >= 0; --q) {
+    const float* base = M + 8 * q * (q + 1);
+#pragma unroll 1
+    for (int r = 3; r >= 0; --r) {
+      const int l = TM - 1 - (4 * q + r);
+      const float* row = base + 4 * r * (q + 1);
+      float dot[R], dot1[R];
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) dot[jj] = dot1[jj] = 0.0f;
+#pragma unroll
+      for (int g = 0; g <= q; ++g) {
+        const float4 qv = *reinterpret_cast<const float4*>(row + 4 * g);
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+          fma2<Geo<LP, R>::PACK>(dot[jj], dot1[jj], qv.x, qv.y, x[jj][TM - 2 - 4 * g], x[jj][TM - 1 - 4 * g]);
+          fma2<Geo<LP, R>::PACK>(dot[jj], dot1[jj], qv.z, qv.w, x[jj][TM - 4 - 4 * g], x[jj][TM - 3 - 4 * g]);
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) Vs[l * TM + lig + LP * jj] = (l < T) ? dot[jj] + dot1[jj] : 0.0f;
+    }
+  }
+}
+
+// Packed lower table (poff rows, zero diagonal and padding) of dK(l,k)/d ell, rows dealt to the lanes; zero beyond T.
+template <int LP, int R, int KERNEL>
+__device__ __forceinline__ void dk_table(float* __restrict__ Kd, const float* __restrict__ ts, int lig, int T, float ell, float sig) {
+  constexpr int TM = LP * R;
+  const KernC<KERNEL> kc(ell, sig);
+  for (int l = lig; l < TM; l += LP) {
+    float* row = Kd + poff_dyn(l);
+    const float tl = ts[l];
+    const int cap = 4 * ((l >> 2) + 1);
+    for (int k = 0; k < cap; ++k) {
+      const float dt = tl - ts[k];
+      row[k] = (k < l && l < T) ? kc.dell(dt, kc.val_fast(dt)) : 0.0f;
+    }
+  }
+}
+
+// sum over this lane's columns c of  2 sum_{l > k} dK(l,k) V(l,c) V(k,c)
+template <int LP, int R>
+__device__ __forceinline__ float quad_cols(const float* __restrict__ Vs, const float* __restrict__ Kd, int lig) {
+  constexpr int TM = LP * R;
+  float v[R][TM];
+#pragma unroll
+  for (int l = 0; l < TM; ++l)
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) v[jj][l] = Vs[l * TM + lig + LP * jj];
+  float qf = 0.0f;
+#pragma unroll
+  for (int l = 1; l < TM; ++l) {
+    const float* row = Kd + poff(l);
+    float acc[R][2];
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) acc[jj][0] = acc[jj][1] = 0.0f;
+#pragma unroll
+    for (int k4 = 0; k4 <= l; k4 += 4) {  // (the diagonal entry and the padding of the row are zeros)
+      const float4 d4 = *reinterpret_cast<const float4*>(row + k4);
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) {
+        fma2<Geo<LP, R>::PACK>(acc[jj][0], acc[jj][1], d4.x, d4.y, v[jj][k4], v[jj][k4 + 1]);
+        fma2<Geo<LP, R>::PACK>(acc[jj][0], acc[jj][1], d4.z, d4.w, v[jj][k4 + 2], v[jj][k4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) qf = fmaf(v[jj][l], acc[jj][0] + acc[jj][1], qf);
+  }
+  return 2.0f * qf;
+}
+
+// this lane's share of  2 sum_{l > k} dK(l,k) al[l] al[k]  (rows l = the lane's columns)
+template <int LP, int R>
+__device__ __forceinline__ float quad_vec(const float* __restrict__ al, const float* __restrict__ Kd, int lig) {
+  float qf = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) {
+    const int l = lig + LP * jj;
+    const float* row = Kd + poff_dyn(l);
+    float acc = 0.0f;
+    for (int k4 = 0; k4 <= l; k4 += 4) {
+      const float4 d4 = *reinterpret_cast<const float4*>(row + k4);
+      const float4 a4 = *reinterpret_cast<const float4*>(al + k4);
+      acc = fmaf(d4.x, a4.x, fmaf(d4.y, a4.y, fmaf(d4.z, a4.z, fmaf(d4.w, a4.w, acc))));
+    }
+    qf = fmaf(al[l], acc, qf);
+  }
+  return 2.0f * qf;
+}
+
 __device__ __forceinline__ int warp_max(int v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -509,7 +612,7 @@ __device__ __forceinline__ PairInfo pair_info(const Params& P) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int G = 32 / LP;
   pi.lig = lane % LP;
-  pi.p = (blockIdx.x * WPC + warp) * G + lane / LP;
+  pi.p = (blockIdx.x * (blockDim.x >> 5) + warp) * G + lane / LP;  // (blockDim.x / 32 = WPC, fewer for the d/d ell_p variant)
   pi.active = pi.p < P.d.B * P.d.D;
   pi.b = pi.active ? pi.p / P.d.D : 0;
   pi.d = pi.active ? pi.p - pi.b * P.d.D : 0;
@@ -703,7 +806,9 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
   if (bad && P.status && (threadIdx.x & 31) == 0) atomicAdd(P.status, 1);
 }
 
-template <int LP, int R, int KERNEL, int POST>
+// GLP: also d/d ell_p (per-pair prior path only; extra shared memory behind the per-sample vectors: L_q rows, the dK_p table,
+// the V table, 1/diag L_p, alpha -- glp_floats())
+template <int LP, int R, int KERNEL, int POST, bool GLP = false>
 __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats) {
   constexpr int TM = LP * R;
   extern __shared__ __align__(16) float smem_f[];
@@ -716,8 +821,17 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
   const int Tw = warp_max(T);
   if (Tw == 0) {
     if (pi.active && lig == 0 && P.gq_pairs) P.gq_pairs[pi.p] = 0.0f;
+    if (GLP && pi.active && lig == 0) P.gp_pairs[pi.p] = 0.0f;
     return;
   }
+  // GLP extras
+  float* const bufC = sm.wS + S * TM;
+  float* const Kd = bufC + Geo<LP, R>::PK;
+  float* const Vs = Kd + Geo<LP, R>::PK;
+  float* const dinvp = Vs + TM * TM;
+  float* const alv = dinvp + TM;
+  float t1p = 0.0f, t3 = 0.0f;
+  const float lp = pi.active ? P.ell_p[pi.d] : 1.0f;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
   const float g = pi.active ? (float)((P.g_kl_sum ? *P.g_kl_sum : 1.0) + (P.g_kl_pairs ? (double)P.g_kl_pairs[pi.p] : 0.0)) : 0.0f;
   float trow[R], mrow[R], gzs[R];
@@ -745,12 +859,14 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
   // shared-prior fast path: the pre-pass found one ell_p for all latent dims and left this sequence's K_p^-1
   const bool shared = (POST == GPKL_POST_GP) && P.prior != nullptr && *P.prior_flag != 0;
   if (!shared) {
-    const float lp = pi.active ? P.ell_p[pi.d] : 1.0f;
     build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise);
     chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad);
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
+    for (int j = 0; j < R; ++j) {
+      sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
+      if (GLP) dinvp[lig + LP * j] = sm.dinv[lig + LP * j];
+    }
     __syncwarp();
     float bvec[R];
 #pragma unroll
@@ -784,6 +900,7 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
       al += al1;
       const int c = lig + LP * jj;
       if (c < T) P.g_mean[(size_t)(pi.r0 + c) * d.D + pi.d] = g * al + gzs[jj];
+      if (GLP) alv[c] = (c < T) ? al : 0.0f;
     }
   }
   if (POST == GPKL_POST_DIAG) {
@@ -806,6 +923,7 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
       store_cols_rev<LP, R>(x, lig, sm.bufB);
       __syncwarp();
       t1 = contract_cols<LP, R, KERNEL>(x, sm.bufB, sm.ts, trow, lig, T, lq, sig);
+      if (GLP) t1p = contract_cols<LP, R, KERNEL>(x, sm.bufB, sm.ts, trow, lig, T, lp, sig);
       __syncwarp();
     }
     // factor K_q
@@ -814,7 +932,23 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgq[lig + LP * j];
-    store_rows<LP, R>(a, lig, sm.bufA);
+    if (!GLP) {
+      store_rows<LP, R>(a, lig, sm.bufA);
+    } else {
+      // L_q rows parked in bufC (bufA still holds L_p, bufB the columns of X_p): A = L_p^-1 L_q as register columns,
+      // V = X_p^T A into the table, then the quadratic forms against dK_p/d ell_p
+      store_rows<LP, R>(a, lig, bufC);
+      dk_table<LP, R, KERNEL>(Kd, sm.ts, lig, T, lp, sig);
+      __syncwarp();
+      load_cols<LP, R>(x, lig, bufC);
+      solve_cols<LP, R>(x, sm.bufA, dinvp, Tw);
+      dots_cols<LP, R>(x, sm.bufB, lig, T, Vs);
+      __syncwarp();
+      t3 = quad_cols<LP, R>(Vs, Kd, lig) + quad_vec<LP, R>(alv, Kd, lig);
+      __syncwarp();
+      for (int e = lig * 4; e < Geo<LP, R>::PK; e += LP * 4)  // L_q rows -> bufA, where the rest of the kernel expects them
+        *reinterpret_cast<float4*>(sm.bufA + e) = *reinterpret_cast<const float4*>(bufC + e);
+    }
     __syncwarp();
     // w_s = L_q^T g_z,s (column reads of the packed rows) ; pd = 1/2 sum_s w_s eps_s - g/2
 #pragma unroll
@@ -890,24 +1024,34 @@ __global__ void __launch_bounds__(WPC * 32) bwd_warp(Params P, int group_floats)
     }
     const double gq = group_sum<LP>(0.5 * (double)g * (double)t1 + (double)t2);
     if (pi.active && lig == 0) P.gq_pairs[pi.p] = (float)gq;
+    if (GLP) {
+      const double gp = group_sum<LP>(0.5 * (double)g * ((double)t1p - (double)t3));
+      if (pi.active && lig == 0) P.gp_pairs[pi.p] = (float)gp;
+    }
   }
   bad = __any_sync(0xffffffffu, bad && pi.active) ? 1 : 0;
   if (bad && P.status && (threadIdx.x & 31) == 0) atomicAdd(P.status, 1);
 }
 
 template <int LP, int R>
-size_t warp_smem_bytes(int S) {
-  return (size_t)WPC * (32 / LP) * (Geo<LP, R>::fixed_floats() + 3 * S * LP * R) * sizeof(float);
+constexpr int glp_floats() { return 2 * Geo<LP, R>::PK + LP * R * LP * R + 2 * LP * R; }
+
+template <int LP, int R>
+size_t warp_smem_bytes(int S, bool glp = false, int wpc = WPC) {
+  return (size_t)wpc * (32 / LP) * (Geo<LP, R>::fixed_floats() + 3 * S * LP * R + (glp ? glp_floats<LP, R>() : 0)) * sizeof(float);
 }
 
 template <int LP, int R, int KERNEL, int POST, bool BWD>
 cudaError_t launch_cfg(const Params& P, cudaStream_t st) {
   const int S = P.d.S;
-  const int group_floats = Geo<LP, R>::fixed_floats() + 3 * S * LP * R;
-  const size_t smem = warp_smem_bytes<LP, R>(S);
+  const bool glp = BWD && POST == GPKL_POST_GP && (P.d.flags & GPKL_FLAG_GRAD_ELL_P) != 0;
+  const int group_floats = Geo<LP, R>::fixed_floats() + 3 * S * LP * R + (glp ? glp_floats<LP, R>() : 0);
+  int wpc = WPC;  // the d/d ell_p variant's tables may not leave room for WPC pairs' worth of shared memory per CTA
+  while (glp && wpc > 1 && warp_smem_bytes<LP, R>(S, glp, wpc) > kMaxDynSmem) wpc >>= 1;
+  const size_t smem = warp_smem_bytes<LP, R>(S, glp, wpc);
   if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
   const int npairs = P.d.B * P.d.D;
-  const int per_cta = WPC * (32 / LP);
+  const int per_cta = wpc * (32 / LP);
   const int grid = (npairs + per_cta - 1) / per_cta;
   cudaError_t e;
   bool pdl = false;
@@ -926,7 +1070,7 @@ cudaError_t launch_cfg(const Params& P, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(WPC * 32);
+  cfg.blockDim = dim3(wpc * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr;
@@ -941,7 +1085,10 @@ cudaError_t launch_cfg(const Params& P, cudaStream_t st) {
     e = cudaLaunchKernelEx(&cfg, kern, P, group_floats);
     prof_end(false, st);
   } else {
-    auto kern = bwd_warp<LP, R, KERNEL, POST>;
+    void (*kern)(Params, int) = bwd_warp<LP, R, KERNEL, POST>;
+    if constexpr (POST == GPKL_POST_GP) {
+      if (glp) kern = bwd_warp<LP, R, KERNEL, POST, true>;
+    }
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaLaunchKernelEx(&cfg, kern, P, group_floats);

@@ -10,7 +10,7 @@ from gpu_util import TOL_GRAD, TOL_KL, TOL_Z, assert_parity, compare, reference_
 
 pytestmark = pytest.mark.gpu
 
-TIERS = ["generic", "warp", "block"]   # warp: registers, T <= 64; block: shared memory, T <= 144; neither does d/d ell_p
+TIERS = ["generic", "warp", "block"]   # warp: registers, T <= 64 (d/d ell_p too); block: shared memory, T <= 144, no d/d ell_p
 
 
 def _tier_cfg(tier, T):
@@ -18,7 +18,7 @@ def _tier_cfg(tier, T):
     if tier == "warp":
         if T > 64:
             pytest.skip("warp tier covers T <= 64")
-        return dict(tier="warp", grad_ell_p=False)
+        return dict(tier="warp", grad_ell_p=True)
     if tier == "block":
         return dict(tier="block", grad_ell_p=False)
     return dict(tier=tier, grad_ell_p=True)
@@ -29,7 +29,7 @@ def _tier_cfg(tier, T):
 def test_golden_v1(cuda_device, name, tier):
     """Fixtures = outputs of Full_GP_VAE_dynamic_time / Full_GP_VAE_fixed_for_MovMnist run verbatim."""
     g = load_golden(name)
-    want_lp = tier == "generic"
+    want_lp = tier in ("generic", "warp")  # the trainable prior of the fixed-T model (T = 20) runs in the warp tier
     if not want_lp:
         g.pop("g_ell_p", None)
     fwd, bwd = run_cuda(g, cuda_device, S=g["S"], noise=g["noise"], tier=tier, grad_ell_p=want_lp)
@@ -376,3 +376,20 @@ def test_cuda_graph_capture(cuda_device):
         assert torch.equal(f["z"], ref_f["z"]) and torch.equal(f["kl_pairs"], ref_f["kl_pairs"])
         assert float(f["kl_sum"]) == float(ref_f["kl_sum"])
         assert torch.equal(b["g_mean"], ref_b["g_mean"]) and torch.equal(b["g_ell_q"], ref_b["g_ell_q"])
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "cauchy"])
+@pytest.mark.parametrize("T,S", [(5, 1), (8, 2), (13, 1), (16, 1), (20, 3), (32, 1), (33, 2), (48, 1), (57, 1), (64, 1)])
+def test_grad_ell_p_warp_tier(cuda_device, T, S, kernel):
+    """d/d ell_p in the register tier (every lane-group configuration), ragged lengths, non-uniform trainable prior length
+    scales (Full_GP_VAE_fixed_for_MovMnist.py:96), against float64 autograd of the oracle; and the same numbers as the
+    generic tier's."""
+    D = 5
+    case = orc.synthetic_batch(7, D, T, S, ragged=True, seed=100 + T)
+    case["ell_p"] = (1.0 + 0.15 * torch.arange(D, dtype=torch.float32) - 0.2).to(torch.float32)
+    errs = compare(case, cuda_device, floor=True, kernel=kernel, S=S, tier="warp", grad_ell_p=True)
+    assert_parity(errs, "warp tier d/d ell_p %s T=%d" % (kernel, T))
+    _, bw = run_cuda(case, cuda_device, kernel=kernel, S=S, tier="warp", grad_ell_p=True)
+    _, bg = run_cuda(case, cuda_device, kernel=kernel, S=S, tier="generic", grad_ell_p=True)
+    assert rel_err(bw["g_ell_p"], bg["g_ell_p"]) < 2e-4
+    assert rel_err(bw["g_ell_q"], bg["g_ell_q"]) < 2e-4
