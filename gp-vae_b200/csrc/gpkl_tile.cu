@@ -164,6 +164,34 @@ __device__ __forceinline__ void mk_chunk(float (&acc)[8][16], const float* __res
   }
 }
 
+// mk_chunk restricted to the accumulator rows r >= R0 (R0 = 0 or 4: the rows 32.. of the tile) and the column groups
+// c >> 2 >= C0 (columns 16 C0 ..): the other operand entries are structural zeros of a triangular factor (the inverse of a
+// diagonal block has no entries (k, c) with k > c), so neither their loads nor their FMAs are issued.
+template <int R0, int C0>
+__device__ __forceinline__ void mk_chunk_part(float (&acc)[8][16], const float* __restrict__ As, const float* __restrict__ Bs,
+                                              int ty, int tx) {
+  const float* ap = As + 4 * ty;
+  const float* bp = Bs + 4 * tx;
+#pragma unroll
+  for (int kk = 0; kk < KC; ++kk) {
+    float a[8], b[16];
+#pragma unroll
+    for (int h = R0 / 4; h < 2; ++h) {
+      const float4 v = *reinterpret_cast<const float4*>(ap + kk * TS + 32 * h);
+      a[4 * h] = v.x; a[4 * h + 1] = v.y; a[4 * h + 2] = v.z; a[4 * h + 3] = v.w;
+    }
+#pragma unroll
+    for (int g = C0; g < 4; ++g) {
+      const float4 v = *reinterpret_cast<const float4*>(bp + kk * TS + 16 * g);
+      b[4 * g] = v.x; b[4 * g + 1] = v.y; b[4 * g + 2] = v.z; b[4 * g + 3] = v.w;
+    }
+#pragma unroll
+    for (int r = R0; r < 8; ++r)
+#pragma unroll
+      for (int c = 4 * C0; c < 16; c += 2) fma2(acc[r][c], acc[r][c + 1], a[r], a[r], b[c], b[c + 1]);
+  }
+}
+
 __device__ __forceinline__ int mrow(int ty, int r) { return 4 * ty + (r & 3) + 32 * (r >> 2); }
 __device__ __forceinline__ int mcol(int tx, int c) { return 4 * tx + (c & 3) + 16 * (c >> 2); }
 
@@ -521,8 +549,12 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
       acc_zero(acc);
       // operands swapped (acc[c][i] = L(i,c)): the conflict-free "column-major" store pattern then writes the ROW-major
       // tile the product / z / w read, and the global column-major L tile takes the strided pattern (no banks there)
+      // (L_JJ^-T has no entries (k, c) with k > c: the contraction steps k >= 32 only reach the columns c >= 32, i.e. the
+      //  second half of the accumulator rows)
 #pragma unroll 1
-      for (int q = 0; q < UC; ++q) mk_chunk(acc, s.linv + q * CH, tile + q * CH, W.ty, W.tx);
+      for (int q = 0; q < UC / 2; ++q) mk_chunk(acc, s.linv + q * CH, tile + q * CH, W.ty, W.tx);
+#pragma unroll 1
+      for (int q = UC / 2; q < UC; ++q) mk_chunk_part<4, 0>(acc, s.linv + q * CH, tile + q * CH, W.ty, W.tx);
       store_rowmajor<1>(Lg + (size_t)tri(J + ti, J) * TF, acc, W.ty, W.tx);
       __syncwarp();  // the warp has read the whole raw tile
       store_colmajor<1>(tile, acc, W.ty, W.tx);
@@ -829,8 +861,16 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
         float* Y = s.panel + (size_t)C * TF;
         float acc[8][16];
         acc_zero(acc);
+        // acc[c][r] = X(r,c); L_II^-1 has no entries (r, k) with k > r: chunk q (k >= 8 q) only reaches the accumulator
+        // column groups r >= 16 g with 16 g + 15 >= 8 q
 #pragma unroll 1
-        for (int q = 0; q < UC; ++q) mk_chunk(acc, Y + q * CH, s.linv + q * CH, W.ty, W.tx);  // acc[c][r] = X(r,c)
+        for (int q = 0; q < 2; ++q) mk_chunk(acc, Y + q * CH, s.linv + q * CH, W.ty, W.tx);
+#pragma unroll 1
+        for (int q = 2; q < 4; ++q) mk_chunk_part<0, 1>(acc, Y + q * CH, s.linv + q * CH, W.ty, W.tx);
+#pragma unroll 1
+        for (int q = 4; q < 6; ++q) mk_chunk_part<0, 2>(acc, Y + q * CH, s.linv + q * CH, W.ty, W.tx);
+#pragma unroll 1
+        for (int q = 6; q < 8; ++q) mk_chunk_part<0, 3>(acc, Y + q * CH, s.linv + q * CH, W.ty, W.tx);
         __syncwarp();  // the warp has read all of Y
         store_colmajor<1>(Y, acc, W.ty, W.tx);
       }
