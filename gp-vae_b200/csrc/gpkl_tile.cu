@@ -262,8 +262,13 @@ __device__ __forceinline__ void prime_chunks(WCtx& W, int n, IssueF issue) {
   }
   __syncwarp();
 }
-template <bool B_RES, class IssueF, class BresF>
-__device__ __forceinline__ void run_chunks(float (&acc)[8][16], WCtx& W, int n, IssueF issue, BresF bres, bool primed = false) {
+struct NoPrep {
+  __device__ __forceinline__ void operator()(int, float*) const {}
+};
+// prep(c, Bs): every lane, after chunk c has landed and before it is multiplied (transforms the staged B chunk in place)
+template <bool B_RES, class IssueF, class BresF, class PrepF = NoPrep>
+__device__ __forceinline__ void run_chunks(float (&acc)[8][16], WCtx& W, int n, IssueF issue, BresF bres, bool primed = false,
+                                           PrepF prep = PrepF()) {
   if (!primed) prime_chunks(W, n, issue);
   for (int c = 0; c < n; ++c) {
     const int s = c & 1;
@@ -274,6 +279,7 @@ __device__ __forceinline__ void run_chunks(float (&acc)[8][16], WCtx& W, int n, 
     if (W.dbg) t1 = clock64();
     const float* As = W.stg + s * STAGE_F;
     const float* Bs = B_RES ? bres(c) : As + CH;
+    if (!B_RES) prep(c, W.stg + s * STAGE_F + CH);
     mk_chunk(acc, As, Bs, W.ty, W.tx);
     __syncwarp();  // every lane is done with stage s
     if (W.dbg) t2 = clock64();
@@ -742,8 +748,8 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
   const int ldr = TP + 4;
   const double g_sum = P.g_kl_sum ? *P.g_kl_sum : 1.0;
   float* Lg = P.scratch + (size_t)blockIdx.x * P.scratch_stride;  // L tiles, overwritten in place by X tiles
-  float* Cg = Lg + (size_t)L.ntri() * TF;                         // C' tiles
-  float* Vg = Cg + (size_t)L.ntri() * TF;                         // L_JJ^-T of the nT diagonal blocks
+  float* Vg = Lg + (size_t)L.ntri() * TF;                         // L_JJ^-T of the nT diagonal blocks
+  float* cumtab = Vg + (size_t)L.nT * TF;                         // [nT][TP]: column sums of eps .* X over the rows above a row block
   float* u = s.v0;    // g_z
   float* w = s.v1;    // L_q^T g_z
   float* pd = s.v2;   // 1/2 w eps - g/2
@@ -881,22 +887,17 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
         bulk_s2g(Lg + (size_t)tri(I, 0) * TF, s.panel, (unsigned)((I + 1) * TF * 4));
         bulk_commit();
       }
-      // C'(i,l) = w_i sum_{j<i} eps_j X(j,l) + pd_i X(i,l) down every column l <= 64 I + 63, straight to global (coalesced over l)
+      // C'(i,l) = w_i sum_{j<i} eps_j X(j,l) + pd_i X(i,l) is NOT stored: the contraction rebuilds its chunks from the X chunks
+      // it streams anyway (see below); all it needs from here are the column sums over the rows ABOVE each row block
       for (int l = tid; l < TS * (I + 1); l += NTHR) {
         const int Cb = l >> 6, lc = l & 63;
         const float* xs = s.panel + (size_t)Cb * TF + lc;
-        float* cg = Cg + (size_t)tri(I, Cb) * TF + lc;
         float cm = cum[l];
+        cumtab[(size_t)I * TP + l] = cm;
 #pragma unroll 8
-        for (int r = 0; r < TS; ++r) {
-          const int i = TS * I + r;
-          const float x = xs[r * TS];
-          cg[r * TS] = fmaf(w[i], cm, pd[i] * x);
-          cm = fmaf(s.eps[i], x, cm);
-        }
+        for (int r = 0; r < TS; ++r) cm = fmaf(s.eps[TS * I + r], xs[r * TS], cm);
         cum[l] = cm;
       }
-      fence_async();  // C' tiles (thread stores) are read by bulk copies in the contraction
       __syncthreads();
       pc.tick(8);
     }
@@ -920,16 +921,34 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
       const int kt = pos <= mx ? mx : pos - mx - 1, lt = pos <= mx ? pos : mx;
       float acc[8][16];
       acc_zero(acc);
+      // B operand: the chunk of X(Ib, lt) (rows i = 64 mx + 8 c .., columns l of tile lt) turned into the chunk of C' in place:
+      // C'(i,l) = w_i cs(l) + pd_i X(i,l),  cs(l) += eps_i X(i,l)  -- two columns per lane, the running sums carried in
+      // registers from chunk to chunk (they start at the table entry of row block mx).  No C' matrix exists in memory: the
+      // backward slot is the X triangle + the diagonal-block inverses (720 KB per CTA at T = 512, 107 MB for 148 CTAs: L2)
+      float2 cs = *reinterpret_cast<const float2*>(cumtab + (size_t)mx * TP + TS * lt + 2 * W.lane);
       run_chunks<false>(acc, W, UC * (nTb - mx),
                         [&](int c, float* st, uint64_t* bar, int lane) {
                           if (lane == 0) {
                             const int Ib = mx + c / UC, qq = c % UC;
                             mbar_expect_tx(bar, 2 * CH * 4);
                             bulk_g2s(st, Lg + (size_t)tri(Ib, kt) * TF + (size_t)qq * CH, CH * 4, bar);
-                            bulk_g2s(st + CH, Cg + (size_t)tri(Ib, lt) * TF + (size_t)qq * CH, CH * 4, bar);
+                            bulk_g2s(st + CH, Lg + (size_t)tri(Ib, lt) * TF + (size_t)qq * CH, CH * 4, bar);
                           }
                         },
-                        [](int) { return (const float*)nullptr; });
+                        [](int) { return (const float*)nullptr; }, false,
+                        [&](int c, float* Bs) {
+                          const int i0 = TS * mx + KC * c;
+                          float2* bp = reinterpret_cast<float2*>(Bs) + W.lane;
+#pragma unroll
+                          for (int r = 0; r < KC; ++r) {
+                            const float wi = w[i0 + r], pi = pd[i0 + r], ei = s.eps[i0 + r];
+                            const float2 x = bp[r * (TS / 2)];
+                            bp[r * (TS / 2)] = make_float2(fmaf(wi, cs.x, pi * x.x), fmaf(wi, cs.y, pi * x.y));
+                            cs.x = fmaf(ei, x.x, cs.x);
+                            cs.y = fmaf(ei, x.y, cs.y);
+                          }
+                          __syncwarp();
+                        });
       float tl[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) tl[c] = s.ts[TS * lt + mcol(W.tx, c)];
@@ -990,7 +1009,7 @@ bool tile_tier_supports(const GpklDesc& d, bool backward) {
 
 size_t tile_slot_floats(const GpklDesc& d) {
   const TLay L(d.T_max, d.S);
-  return (2 * (size_t)L.ntri() + (size_t)L.nT) * TF;  // L / X tiles, C' tiles, L_JJ^-T of the diagonal blocks
+  return ((size_t)L.ntri() + (size_t)L.nT) * TF + (size_t)L.nT * L.TP;  // L / X tiles, L_JJ^-T of the diagonal blocks, column-sum table
 }
 
 // The shared-prior kernel of the tile tier; the caller has launched the block tier's pre-pass (records in P.prior) before
