@@ -13,12 +13,12 @@ pytestmark = pytest.mark.gpu
 TIERS = ["generic", "warp", "block"]   # warp: registers, T <= 64 (d/d ell_p too); block: shared memory, T <= 144, no d/d ell_p
 
 
-def _tier_cfg(tier, T):
+def _tier_cfg(tier, T, posterior="gp"):
     """Explicit tier requests are honoured or refused by the library; skip what a tier does not cover."""
     if tier == "warp":
         if T > 64:
             pytest.skip("warp tier covers T <= 64")
-        return dict(tier="warp", grad_ell_p=True)
+        return dict(tier="warp", grad_ell_p=False)  # (the default, shared-prior kernels; d/d ell_p: test_grad_ell_p_warp_tier)
     if tier == "block":
         return dict(tier="block", grad_ell_p=False)
     return dict(tier=tier, grad_ell_p=True)
@@ -207,7 +207,7 @@ V2_GRID = [g for g in GRID if g[2] in (1, 7, 10, 20, 33, 48, 100, 160)]
 @pytest.mark.parametrize("B,D,T,S,ragged", V2_GRID)
 def test_v2_vs_oracle_reference_grid(cuda_device, B, D, T, S, ragged, kernel, tier):
     case = orc.synthetic_batch(B, D, T, S, ragged=ragged, seed=200 + T, posterior="diag", grid=True)
-    errs = compare(case, cuda_device, kernel=kernel, posterior="diag", S=S, **_tier_cfg(tier, T))
+    errs = compare(case, cuda_device, kernel=kernel, posterior="diag", S=S, **_tier_cfg(tier, T, "diag"))
     assert_parity(errs, "V2 grid %s T=%d" % (kernel, T))
 
 
@@ -216,7 +216,7 @@ def test_v2_vs_oracle_reference_grid(cuda_device, B, D, T, S, ragged, kernel, ti
 @pytest.mark.parametrize("B,D,T,S,ragged", V2_GRID)
 def test_v2_vs_oracle_irregular_times(cuda_device, B, D, T, S, ragged, kernel, tier):
     case = orc.synthetic_batch(B, D, T, S, ragged=ragged, seed=200 + T, posterior="diag")
-    errs = compare(case, cuda_device, floor=True, kernel=kernel, posterior="diag", S=S, **_tier_cfg(tier, T))
+    errs = compare(case, cuda_device, floor=True, kernel=kernel, posterior="diag", S=S, **_tier_cfg(tier, T, "diag"))
     assert_parity(errs, "V2 %s T=%d" % (kernel, T))
 
 
