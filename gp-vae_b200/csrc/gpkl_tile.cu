@@ -459,6 +459,7 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
       // in flight (L2 round trips) while the current one is generated and accumulated
       constexpr int NIT = TF / (NTHR * 4);
       const int c0 = (tid * 4) >> 6, i0 = (tid * 4) & 63;
+      const double* mm64 = reinterpret_cast<const double*>(s.v0);  // the mean as doubles (forward: v0 | v1, filled by the kernel)
       double2 q[NIT][2];
       auto fetch = [&](int ti) {
 #pragma unroll
@@ -469,31 +470,43 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
         }
       };
       fetch(0);
-      double acc = 0.0;
+      // FP64 is the scarce pipe here (measured ~16 DFMA per clock per SM on this part): three FP64 operations per entry -- one
+      // conversion and two DFMA, the means are kept as doubles in shared memory (mm64) -- and weight-2 / weight-1
+      // accumulators instead of a multiply; masks (diagonal tile, rows beyond T) are selects on the K_p^-1 entry
+      double acc2 = 0.0, acc1 = 0.0;
       for (int ti = 0; ti < m; ++ti) {
         float* dst = s.panel + (size_t)(J + ti) * TF;
         double2 qc[NIT][2];
 #pragma unroll
         for (int it = 0; it < NIT; ++it) { qc[it][0] = q[it][0]; qc[it][1] = q[it][1]; }
         if (ti + 1 < m) fetch(ti + 1);
+        const int row = TS * (J + ti) + i0;
+        const double mi[4] = {mm64[row], mm64[row + 1], mm64[row + 2], mm64[row + 3]};
+        const bool inner = ti > 0 && TS * (J + ti) + TS <= pr.T;  // (uniform) a tile below the diagonal one, all rows real
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-          const int col = TS * J + c0 + 16 * it, row = TS * (J + ti) + i0;
+          const int col = TS * J + c0 + 16 * it;
           const float4 kv = pr.kgen4(col, row, s.ts);
           *reinterpret_cast<float4*>(dst + (c0 + 16 * it) * TS + i0) = kv;
-          const double mc = (double)s.mm[col];
+          const double mc = mm64[col];
           const float kf[4] = {kv.x, kv.y, kv.z, kv.w};
-          const double kd[4] = {qc[it][0].x, qc[it][0].y, qc[it][1].x, qc[it][1].y};
+          double kd[4] = {qc[it][0].x, qc[it][0].y, qc[it][1].x, qc[it][1].y};
+          if (inner) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = row + e;
-            if (i >= col && i < pr.T) {  // (col <= i < T)
-              const double term = kd[e] * fma((double)s.mm[i], mc, (double)kf[e]);
-              acc += (i == col) ? term : 2.0 * term;
+            for (int e = 0; e < 4; ++e) acc2 = fma(kd[e], fma(mi[e], mc, (double)kf[e]), acc2);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = row + e;
+              const double k2 = (i > col && i < pr.T) ? kd[e] : 0.0, k1 = (i == col && i < pr.T) ? kd[e] : 0.0;
+              const double v = fma(mi[e], mc, (double)kf[e]);
+              acc2 = fma(k2, v, acc2);
+              acc1 = fma(k1, v, acc1);
             }
           }
         }
       }
+      const double acc = 2.0 * acc2 + acc1;
       *tr += acc;
     }
     __syncthreads();
@@ -677,6 +690,10 @@ __global__ void __launch_bounds__(NTHR, 1) fwd_tile(Params P) {
     }
     if (tid == 0) bad = 0;
     load_vectors(P, p, b, dd, T, r0, L, s, false);
+    {
+      double* mm64 = reinterpret_cast<double*>(s.v0);  // (v0 and v1 are adjacent: TP doubles)
+      for (int i = tid; i < TP; i += NTHR) mm64[i] = (i < T) ? (double)P.mean[(size_t)(r0 + i) * d.D + dd] : 0.0;
+    }
     // this sequence's float64 record: K_p^-1 (lower, column-major, pitch TP) and log|K_p| (gpkl_prior64.cu)
     const double* __restrict__ kinv = reinterpret_cast<const double*>(P.prior + (size_t)b * P.prior_stride);
     __syncthreads();
