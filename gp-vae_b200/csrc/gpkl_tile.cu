@@ -956,9 +956,15 @@ __global__ void __launch_bounds__(NTHR, 1) bwd_tile(Params P) {
                         [&](int c, float* Bs) {
                           const int i0 = TS * mx + KC * c;
                           float2* bp = reinterpret_cast<float2*>(Bs) + W.lane;
+                          const float4 w0 = *reinterpret_cast<const float4*>(w + i0), w1 = *reinterpret_cast<const float4*>(w + i0 + 4);
+                          const float4 p0 = *reinterpret_cast<const float4*>(pd + i0), p1 = *reinterpret_cast<const float4*>(pd + i0 + 4);
+                          const float4 e0 = *reinterpret_cast<const float4*>(s.eps + i0), e1 = *reinterpret_cast<const float4*>(s.eps + i0 + 4);
+                          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                          const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                          const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
                           for (int r = 0; r < KC; ++r) {
-                            const float wi = w[i0 + r], pi = pd[i0 + r], ei = s.eps[i0 + r];
+                            const float wi = wv[r], pi = pv[r], ei = ev[r];
                             const float2 x = bp[r * (TS / 2)];
                             bp[r * (TS / 2)] = make_float2(fmaf(wi, cs.x, pi * x.x), fmaf(wi, cs.y, pi * x.y));
                             cs.x = fmaf(ei, x.x, cs.x);

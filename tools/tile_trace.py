@@ -24,7 +24,7 @@ for T in [int(a) for a in sys.argv[1:]] or [512]:
         L.gpkl_debug_set_trace(None)
         t = buf.cpu().tolist()
         n = max(t[63], 1)
-        tot = sum(t[48:48 + len(labels)]) / n
+        tot = (sum(t[48:48 + len(labels)]) - (t[57] if name == 'bwd' else 0) + t[59] + t[60] + t[61] + (t[62] if name == 'bwd' else 0)) / n  # (+ the diag-tile phase and the staged inverse, clocked separately; slot 57 is the team's own clock)
         print('T=%d %s: %d pairs by CTA 0, %.0f cycles/pair: ' % (T, name, t[63], tot) +
               ' | '.join('%s %.0f' % (lab, t[48 + i] / n) for i, lab in enumerate(labels)), flush=True)
         print('      diag-tile phase split: prefill %.0f | warp 0 k-loop %.0f | warp 0 flush %.0f' % (t[59] / n, t[60] / n, t[61] / n), flush=True)
