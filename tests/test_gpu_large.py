@@ -59,11 +59,15 @@ def test_tile_tier_vs_oracle_reference_grid(cuda_device, B, D, T, S, ragged, ker
     assert_parity(errs, "tile tier grid %s T=%d" % (kernel, T))
 
 
+@pytest.mark.parametrize("kernel", ["rbf", "cauchy"])
 @pytest.mark.parametrize("B,D,T,S,ragged", TILE_GRID)
-def test_tile_tier_vs_oracle_irregular_times(cuda_device, B, D, T, S, ragged):
+def test_tile_tier_vs_oracle_irregular_times(cuda_device, B, D, T, S, ragged, kernel):
+    """SURVEY S8(d) stress inputs (times = cumsum(U(0.5, 1.5)), cond(K) ~ 1e3) at the STRICT 1e-5 / 1e-4: the forward's
+    float64 trace against the float64 K_p^-1 is the reference's own formula (no rounding-floor allowance needed here;
+    profiles/r02b_parity_residuals.txt: KL <= 5.6e-6, gradients <= 6e-5 over T = 209..512)."""
     case = orc.synthetic_batch(B, D, T, S, ragged=ragged, seed=6100 + T)
-    errs = compare(case, cuda_device, floor=True, kernel="rbf", S=S, tier="auto", grad_ell_p=False)
-    assert_parity(errs, "tile tier irregular T=%d" % T)
+    errs = compare(case, cuda_device, kernel=kernel, S=S, tier="auto", grad_ell_p=False)
+    assert_parity(errs, "tile tier irregular %s T=%d" % (kernel, T))
 
 
 @pytest.mark.parametrize("B,D,T,S,ragged", TILE_GRID)
