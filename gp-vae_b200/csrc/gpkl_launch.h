@@ -22,7 +22,9 @@ bool pdl_enabled();  // programmatic dependent launch of the per-pair kernels be
 inline size_t prior_record_floats(int T_max) {
   const size_t al = T_max > 208 ? 64 : 16;  // as Lay (gpkl_block.cu): 64 x 64 tiles beyond the resident sizes
   const size_t TP = ((size_t)(T_max < 1 ? 1 : T_max) + al - 1) / al * al;
-  return 2 * (TP + 1) * (TP + 4);
+  const size_t tp64 = ((size_t)(T_max < 1 ? 1 : T_max) + 63) / 64 * 64;  // float64 forward records (gpkl_prior64.cu): pitch 64 k
+  const size_t f32 = 2 * (TP + 1) * (TP + 4), f64 = 2 * (tp64 * tp64 + 2);
+  return f32 > f64 ? f32 : f64;
 }
 
 // generic tier (gpkl_generic.cu)
@@ -53,6 +55,7 @@ cudaError_t launch_tile(const Params& P, bool backward, cudaStream_t st);
 // pitch TP = T_max rounded up to 64) followed by log|K_p|; fits the records sized by prior_record_floats
 size_t prior64_record_floats(int T_max);
 cudaError_t launch_prior_inv64(const Params& P, cudaStream_t st);
+cudaError_t launch_prior_inv64_small(const Params& P, cudaStream_t st, int f32_off, int f32_tm);
 
 // reconstruction term (gpkl_recon.cu), SURVEY.md S8(f) row 1
 int recon_grid(long long rows);

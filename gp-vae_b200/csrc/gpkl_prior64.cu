@@ -239,6 +239,142 @@ __global__ void __launch_bounds__(NT, 1) prior_inv64_kernel(Params P) {
   }
 }
 
+// n scalar symmetric sweeps of the register-resident lower triangle (prior_inv64_small_kernel): QN entries per thread.
+// Pivot step s: the owners of sym(., s) publish the pivot column, one barrier, every entry takes
+//   x(r,c) -= col[r] col[c] / d      (r, c != s),      x(r,s) = col[r] / d,      x(s,s) = -1 / d
+// branch-free (the operand of the multiply and the result are selected), so the QN entries of a thread overlap.
+template <int QN, int Q, int TP>
+__device__ __forceinline__ void small_sweep(double (&x)[Q], const int (&rr)[Q], const int (&cc)[Q], int n,
+                                            double (*pc)[TP + 2], double* piv) {
+  static_assert(QN <= Q, "entries per thread");
+  for (int s = 0; s < n; ++s) {
+    double* col = pc[s & 1];
+#pragma unroll
+    for (int q = 0; q < QN; ++q) {
+      const bool rs = rr[q] == s, cs = cc[q] == s;
+      if (rs | cs) col[rs ? cc[q] : rr[q]] = x[q];
+    }
+    __syncthreads();
+    const double dv = col[s];
+    double inv = (double)__frcp_rn((float)dv);  // pivots of an SPD float32-built matrix: well inside the float range
+    const double e1 = fma(-dv, inv, 1.0);       // 1/d = inv (1 + e + e^2 + ...), |e| ~ 1e-7: two terms
+    inv = fma(inv, fma(e1, e1, e1), inv);
+    const double ninv = -inv;
+#pragma unroll
+    for (int q = 0; q < QN; ++q) {
+      const bool rs = rr[q] == s, cs = cc[q] == s;
+      const double psc = col[cc[q]], prs = col[rr[q]];
+      const double t = (rs ? psc : prs) * inv;
+      const double upd = fma(-t, psc, x[q]);
+      x[q] = (rs | cs) ? ((rs & cs) ? ninv : t) : upd;
+    }
+    if (threadIdx.x == 0) piv[s] = dv;
+  }
+}
+
+// T_max <= 64 (the register tier's sizes; consumers: fwd_warp / bwd_warp, gpkl_warp.cuh).  The lower triangle lives in
+// REGISTERS: the n(n+1)/2 entries are dealt to the 256 threads (<= 9 each, column-major packed so that the record is written
+// coalesced), and one scalar symmetric sweep per pivot needs only the pivot column sym(., s), which its owners publish through
+// a double-buffered shared vector: ONE barrier per pivot, 2 FP64 operations per entry and pivot, the pivot's reciprocal by
+// MUFU.RCP + two Newton steps.
+// Forward record (f32_tm == 0): -(sweep result) = K_p^-1 in float64, lower triangle column-major with pitch 64, THE DIAGONAL
+// HALVED (the consumer's trace is 2 * sum_{k <= r}), log|K_p| at [64 * 64].
+// Backward record (f32_tm = TM of the consumer's lane geometry): K_p^-1 rounded to float32, full symmetric TM x TM at float
+// offset f32_off (PriorRec::KI), identity on the padding.
+// Several CTAs per SM; the per-pair kernel launched behind it (programmatic dependent launch) starts at once and waits where
+// it first reads a record.
+template <int KERNEL>
+__global__ void __launch_bounds__(NT) prior_inv64_small_kernel(Params P, int f32_off, int f32_tm) {
+  constexpr int TP = 64, Q = (TP * (TP + 1) / 2 + NT - 1) / NT;
+  __shared__ double pc[2][TP + 2];
+  __shared__ double piv[TP];
+  __shared__ double red[32];
+  __shared__ float ts[TP];
+  griddep_launch_dependents();
+  if (*P.prior_flag == 0) return;
+  const GpklDesc& d = P.d;
+  const int tid = threadIdx.x;
+  const float noise = d.noise, sig = (float)(1.0 - (double)noise);
+  const KernC<KERNEL> kc(P.ell_p[0], sig);
+  if (tid < 2 * (TP + 2)) (&pc[0][0])[tid] = 0.0;
+  for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
+    const int n = P.lengths[b];
+    float* rec = P.prior + (size_t)b * P.prior_stride;
+    double* A = reinterpret_cast<double*>(rec);
+    __syncthreads();
+    if (f32_tm) {  // padding of the float32 record: identity
+      for (int e = tid; e < f32_tm * f32_tm; e += NT) {
+        const int r = e / f32_tm, c = e - r * f32_tm;
+        if (r >= n || c >= n) rec[f32_off + e] = r == c ? 1.0f : 0.0f;
+      }
+    }
+    if (n <= 0) {
+      if (tid == 0 && !f32_tm) A[(size_t)TP * TP] = 0.0;
+      continue;
+    }
+    if (tid < n) ts[tid] = P.times[(size_t)b * d.T_max + tid];
+    __syncthreads();
+    const int ne = n * (n + 1) / 2;
+    const int qn = (ne + NT - 1) / NT;  // entries per thread of this sequence (the last one may be a dummy)
+    int rr[Q], cc[Q];
+    double x[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int e = tid + q * NT;
+      rr[q] = cc[q] = TP;  // dummy entry: never a pivot row / column, reads the spare slot of the pivot vector
+      x[q] = 0.0;
+      if (e < ne) {
+        // column-major packed lower triangle = the row-major packed one read backwards and mirrored
+        const int f = ne - 1 - e;
+        int rp = (int)((sqrtf(8.0f * (float)f + 1.0f) - 1.0f) * 0.5f);
+        while (rp * (rp + 1) / 2 > f) --rp;
+        while ((rp + 1) * (rp + 2) / 2 <= f) ++rp;
+        const int cp = f - rp * (rp + 1) / 2;
+        rr[q] = n - 1 - cp;
+        cc[q] = n - 1 - rp;
+        x[q] = (double)(kc.val(ts[rr[q]] - ts[cc[q]]) + (rr[q] == cc[q] ? noise : 0.0f));
+      }
+    }
+    switch (qn) {  // (compile-time entry counts: no branch between the entries of a pivot step, their latencies overlap)
+      case 1: small_sweep<1, Q, TP>(x, rr, cc, n, pc, piv); break;
+      case 2: small_sweep<2, Q, TP>(x, rr, cc, n, pc, piv); break;
+      case 3: small_sweep<3, Q, TP>(x, rr, cc, n, pc, piv); break;
+      case 4: small_sweep<4, Q, TP>(x, rr, cc, n, pc, piv); break;
+      case 5: small_sweep<5, Q, TP>(x, rr, cc, n, pc, piv); break;
+      case 6: small_sweep<6, Q, TP>(x, rr, cc, n, pc, piv); break;
+      case 7: small_sweep<7, Q, TP>(x, rr, cc, n, pc, piv); break;
+      case 8: small_sweep<8, Q, TP>(x, rr, cc, n, pc, piv); break;
+      default: small_sweep<9, Q, TP>(x, rr, cc, n, pc, piv); break;
+    }
+    if (!f32_tm) {
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        if (rr[q] < TP) A[(size_t)cc[q] * TP + rr[q]] = (rr[q] == cc[q] ? -0.5 : -1.0) * x[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        if (rr[q] < TP) {
+          const float v = (float)(-x[q]);
+          rec[f32_off + cc[q] * f32_tm + rr[q]] = v;
+          rec[f32_off + rr[q] * f32_tm + cc[q]] = v;
+        }
+    }
+    __syncthreads();
+    double ld = 0.0;
+    int bad = 0;
+    if (tid < n) {
+      ld = log(piv[tid]);
+      if (!(piv[tid] > 0.0)) bad = 1;
+    }
+    ld = block_sum(ld, red);
+    bad = __syncthreads_or(bad);
+    if (tid == 0) {
+      if (!f32_tm) A[(size_t)TP * TP] = ld;
+      if (bad && P.status) atomicAdd(P.status, 1);
+    }
+  }
+}
+
 }  // namespace
 
 size_t prior64_record_floats(int T_max) {
@@ -246,7 +382,21 @@ size_t prior64_record_floats(int T_max) {
   return 2 * (TP * TP + 2);
 }
 
+// register tier's pre-pass; f32_tm == 0: float64 forward record, else the float32 backward record (see the kernel)
+cudaError_t launch_prior_inv64_small(const Params& P, cudaStream_t st, int f32_off, int f32_tm) {
+  if (P.d.T_max > 64 || f32_tm > 64) return cudaErrorInvalidValue;
+  const size_t need = f32_tm ? (size_t)f32_off + (size_t)f32_tm * f32_tm : prior64_record_floats(P.d.T_max);
+  if (P.prior_stride < need) return cudaErrorInvalidValue;
+  void (*ks)(Params, int, int) =
+      P.d.kernel == GPKL_KERNEL_RBF ? prior_inv64_small_kernel<GPKL_KERNEL_RBF> : prior_inv64_small_kernel<GPKL_KERNEL_CAUCHY>;
+  const int cap = 4 * kNumSMs;
+  ks<<<P.d.B < cap ? P.d.B : cap, NT, 0, st>>>(P, f32_off, f32_tm);
+  note_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_prior_inv64(const Params& P, cudaStream_t st) {
+  if (P.d.T_max <= 64) return launch_prior_inv64_small(P, st, 0, 0);
   const int TP = p64_tp(P.d.T_max);
   const size_t smem = ((size_t)2 * NB * p64_ldw(TP) + NB * (NB + 1) + TP) * sizeof(double) + (size_t)TP * sizeof(float);
   if (smem > kMaxDynSmem || P.prior_stride < prior64_record_floats(P.d.T_max)) return cudaErrorInvalidValue;

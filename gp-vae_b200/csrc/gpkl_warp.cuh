@@ -460,145 +460,18 @@ __device__ __forceinline__ int warp_max(int v) {
 
 // ---- shared-prior fast path ------------------------------------------------------------------------------------
 // The reference's prior length scales are one constant for all latent dims (prior_time_chars,
-// Full_GP_VAE_dynamic_time.py:114), so the D pairs of a sequence share K_p.  A pre-pass (prior_warp, one lane
-// group per SEQUENCE) factors it once and leaves a record in the workspace; the per-pair kernels then only
-// factor K_q:   forward   A = L_p^-1 L_q as a PRODUCT with the stored inverse (no substitution chain), a = L_p^-1 m
-//               backward  alpha = K_p^-1 m and t1 = <K_p^-1, dK_q/d ell> straight from the stored K_p^-1 rows.
-// Record (floats): [0, PK) L_p^-1 packed rows (poff layout) | [PK, PK+TM) diag L_p | [PK+TM, +TM*TM) K_p^-1.
+// Full_GP_VAE_dynamic_time.py:114), so the D pairs of a sequence share K_p.  A pre-pass (prior_inv64_small_kernel,
+// gpkl_prior64.cu: one CTA per SEQUENCE, float64 sweep inverse) leaves a record in the workspace; the per-pair kernels
+// then only factor K_q:
+//   forward   KL = 1/2 [tr(K_p^-1 (K_q + m m^T)) - T + log|K_p| - log|K_q|] with the trace taken entrywise against the
+//             FLOAT64 K_p^-1 while K_q is generated (the reference's own formula, :250-259)
+//   backward  alpha = K_p^-1 m and t1 = <K_p^-1, dK_q/d ell> straight from K_p^-1 rows rounded to float32.
+// Backward record (floats): [KI, KI + TM*TM) K_p^-1, full symmetric, identity on the padding ([0, KI) unused).
 template <int LP, int R>
 struct PriorRec {
   static constexpr int TM = LP * R, PK = Geo<LP, R>::PK;
-  static constexpr int XP = 0, DG = PK, KI = PK + TM, SIZE = PK + TM + TM * TM;
+  static constexpr int KI = PK + TM, SIZE = PK + TM + TM * TM;
 };
-
-// sum over i != c of A(i,c)^2, A = X_p L_q: X_p packed rows in shared memory (128-bit broadcast loads, zero padded
-// to the end of each 4-group), L_q as register columns (zero above the diagonal).
-template <int LP, int R>
-__device__ __forceinline__ float mul_cols_ssq(const float (&x)[R][LP * R], const float* __restrict__ Xpk, int lig,
-                                              int Tw) {
-  constexpr int TM = LP * R;
-  float ssq = 0.0f;
-#pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    if ((i & ~3) < Tw) {  // rows beyond the longest sequence of the warp are identity rows: no off-diagonal part
-      const float* row = Xpk + poff(i);
-      float acc[R][2];
-#pragma unroll
-      for (int jj = 0; jj < R; ++jj) acc[jj][0] = acc[jj][1] = 0.0f;
-#pragma unroll
-      for (int k4 = 0; k4 <= i; k4 += 4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(row + k4);
-#pragma unroll
-        for (int jj = 0; jj < R; ++jj) {
-          fma2<Geo<LP, R>::PACK>(acc[jj][0], acc[jj][1], l4.x, l4.y, x[jj][k4], x[jj][k4 + 1]);
-          fma2<Geo<LP, R>::PACK>(acc[jj][0], acc[jj][1], l4.z, l4.w, x[jj][k4 + 2], x[jj][k4 + 3]);
-        }
-      }
-#pragma unroll
-      for (int jj = 0; jj < R; ++jj) {
-        const float v = (i == lig + LP * jj) ? 0.0f : acc[jj][0] + acc[jj][1];
-        ssq = fmaf(v, v, ssq);
-      }
-    }
-  }
-  return ssq;
-}
-
-// Pre-pass: one lane group per sequence, ONE warp per CTA (the unrolled code is instruction-fetch bound per SM, so
-// the few warps of this grid are spread over as many SMs as possible).  If ell_p is one value for all latent dims
-// (device flag written by offsets_kernel; if not, the per-pair kernels take their per-pair path and nothing is
-// done here) it factors K_p(ell_p[0]) exactly as the per-pair path does (build_rows / chol_rows / solve_cols) and writes the record.  WANT_KINV: the backward
-// record (K_p^-1 rows); otherwise the forward record (L_p^-1 rows, diag L_p).
-template <int LP, int R, int KERNEL, bool WANT_KINV>
-__global__ void __launch_bounds__(WPC * 32) prior_warp(Params P, int group_floats) {
-  constexpr int TM = LP * R;
-  constexpr int G = 32 / LP;
-  using Rec = PriorRec<LP, R>;
-  extern __shared__ __align__(16) float smem_f[];
-  const GpklDesc& d = P.d;
-  // Let the per-pair kernel (launched with programmatic stream serialisation) start right away: it only reads the
-  // records after its own griddep_wait(), i.e. after this grid has completed.
-  griddep_launch_dependents();
-  if (*P.prior_flag == 0) return;  // ell_p differs between latent dims (offsets_kernel checked): per-pair path
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lig = lane % LP;
-  const int b = (blockIdx.x * (blockDim.x >> 5) + warp) * G + lane / LP;
-  const bool active = b < d.B;
-  const float lp = P.ell_p[0];
-  Smem<LP, R> sm(smem_f + (size_t)(warp * G + lane / LP) * group_floats, d.S);
-  const int T = active ? P.lengths[b] : 0;
-  const int Tw = warp_max(T);
-  // (no early exit for empty sequences: their record is the identity, and a pair of an empty sequence that shares
-  //  a warp with live pairs reads it)
-  const float noise = d.noise, sig = (float)(1.0 - (double)noise);
-  float trow[R];
-#pragma unroll
-  for (int j = 0; j < R; ++j) {
-    const int r = lig + LP * j;
-    trow[j] = (r < T) ? P.times[(size_t)b * d.T_max + r] : 0.0f;
-    sm.ts[r] = trow[j];
-  }
-  __syncwarp();
-  int bad = 0;
-  float a[R][TM];
-  build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lp, sig, noise);
-  chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgp, bad);
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < R; ++j) sm.dinv[lig + LP * j] = 1.0f / sm.dgp[lig + LP * j];
-  store_rows<LP, R>(a, lig, sm.bufA);
-  __syncwarp();
-  float (&x)[R][TM] = a;  // X_p = L_p^-1 as register columns
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int jj = 0; jj < R; ++jj) x[jj][i] = (i == lig + LP * jj) ? 1.0f : 0.0f;
-  solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
-  // columns -> packed rows (entries above the diagonal inside the last 4-group of a row are exact zeros)
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int jj = 0; jj < R; ++jj) {
-      const int c = lig + LP * jj;
-      if (c <= (i | 3)) sm.bufB[poff(i) + c] = x[jj][i];
-    }
-  __syncwarp();
-  float* rec = P.prior + (size_t)(active ? b : 0) * P.prior_stride;
-  if (!WANT_KINV) {
-    if (active) {
-      for (int q = lig; q < Rec::PK / 4; q += LP)
-        reinterpret_cast<float4*>(rec + Rec::XP)[q] = reinterpret_cast<const float4*>(sm.bufB)[q];
-#pragma unroll
-      for (int j = 0; j < R; ++j) rec[Rec::DG + lig + LP * j] = sm.dgp[lig + LP * j];
-    }
-  } else {
-    // K_p^-1(c, l) = <X_p[:, c], X_p[:, l]>, four l at a time; symmetric, so lane c stores element (l, c): coalesced
-    for (int l4 = 0; l4 < TM; l4 += 4) {
-      float dot[R][4];
-#pragma unroll
-      for (int jj = 0; jj < R; ++jj) dot[jj][0] = dot[jj][1] = dot[jj][2] = dot[jj][3] = 0.0f;
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        // row i holds columns 0..(i|3); for l4 > i the 4-group lies outside the row
-        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (l4 <= i) v = *reinterpret_cast<const float4*>(sm.bufB + poff(i) + l4);
-#pragma unroll
-        for (int jj = 0; jj < R; ++jj) {
-          fma2<Geo<LP, R>::PACK>(dot[jj][0], dot[jj][1], x[jj][i], x[jj][i], v.x, v.y);
-          fma2<Geo<LP, R>::PACK>(dot[jj][2], dot[jj][3], x[jj][i], x[jj][i], v.z, v.w);
-        }
-      }
-      if (active) {
-#pragma unroll
-        for (int jj = 0; jj < R; ++jj)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) rec[Rec::KI + (size_t)(l4 + e) * TM + lig + LP * jj] = dot[jj][e];
-      }
-    }
-  }
-  bad = __any_sync(0xffffffffu, bad && active) ? 1 : 0;
-  if (bad && P.status && (threadIdx.x & 31) == 0) atomicAdd(P.status, 1);
-}
 
 struct PairInfo {
   int p, b, d, T, lig;
@@ -674,19 +547,46 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
   if (POST == GPKL_POST_GP) {
     const float lq = pi.active ? P.ell_q[pi.d] : 1.0f;
     build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise);
-    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad);
-    float dgp_rec[R] = {};
+    double tr0 = 0.0, tr1 = 0.0, tr2 = 0.0, tr3 = 0.0, ldp_rec = 0.0;
     if (shared) {
-      // The record is first needed after the K_q chain, so the pre-pass overlaps it (griddep_wait); its packed
-      // L_p^-1 rows stream into bufA asynchronously while z, the transposition and a = L_p^-1 m's operands are done.
+      // Shared prior: the record of this sequence is K_p^-1 in FLOAT64 (lower triangle, column-major, pitch 64, diagonal
+      // halved) + log|K_p| (prior_inv64_small_kernel, gpkl_prior64.cu), and the KL is the reference's own formula
+      // (Full_GP_VAE_dynamic_time.py:250-259)
+      //     KL = 1/2 [ tr(K_p^-1 (K_q + m m^T)) - T + log|K_p| - log|K_q| ],   tr = 2 sum_{k<=r} Kinv'_rk (K_q,rk + m_r m_k),
+      // accumulated HERE from the rows of K_q this lane has just built (before the factorisation overwrites them): no
+      // triangular product A = L_p^-1 L_q, no transposition of L_q, no a = L_p^-1 m.  Three FP64 operations per entry.
       griddep_wait();
-      using Rec = PriorRec<LP, R>;
-      const float* __restrict__ rec = P.prior + (size_t)pi.b * P.prior_stride;
-      for (int q = lig; q < Rec::PK / 4; q += LP) cp_async16(sm.bufA + 4 * q, rec + Rec::XP + 4 * q, 16);
-      cp_async_commit();
+      const double* __restrict__ kinv = reinterpret_cast<const double*>(P.prior + (size_t)pi.b * P.prior_stride);
+      double* m64 = reinterpret_cast<double*>(sm.bufA);  // the mean as doubles (bufA is idle on this path)
+      constexpr int TRB = LP < 16 ? LP : 16;
 #pragma unroll
-      for (int j = 0; j < R; ++j) dgp_rec[j] = __ldg(rec + Rec::DG + lig + LP * j);
+      for (int j = 0; j < R; ++j) m64[lig + LP * j] = (double)mrow[j];
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int r = lig + LP * j;
+        const double mr = (double)mrow[j];
+        const bool rin = r < T;
+#pragma unroll
+        for (int kb = 0; kb < LP * j + LP; kb += TRB) {  // (columns up to the last row of this register slot)
+          if (kb < Tw) {
+            // one batch of record entries in flight per trip (no branch between the loads: the L2 round trips overlap)
+            double kd[TRB];
+#pragma unroll
+            for (int e = 0; e < TRB; ++e) kd[e] = (kb + e <= r && rin) ? __ldg(kinv + (size_t)(kb + e) * 64 + r) : 0.0;
+#pragma unroll
+            for (int e = 0; e < TRB; e += 4) {
+              tr0 = fma(kd[e], fma(mr, m64[kb + e], (double)a[j][kb + e]), tr0);
+              tr1 = fma(kd[e + 1], fma(mr, m64[kb + e + 1], (double)a[j][kb + e + 1]), tr1);
+              tr2 = fma(kd[e + 2], fma(mr, m64[kb + e + 2], (double)a[j][kb + e + 2]), tr2);
+              tr3 = fma(kd[e + 3], fma(mr, m64[kb + e + 3], (double)a[j][kb + e + 3]), tr3);
+            }
+          }
+        }
+      }
+      ldp_rec = __ldg(kinv + 64 * 64);
     }
+    chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad);
     // z_s = m + L_q eps_s from the register rows
     for (int s = 0; s < S; ++s) {
       float zz[R], zz1[R];
@@ -711,12 +611,12 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
         if (r < T) P.z[((size_t)S * pi.r0 + (size_t)s * T + r) * d.D + pi.d] = zz[j] + zz1[j];
       }
     }
-    store_rows<LP, R>(a, lig, sm.bufB);
-    __syncwarp();
-    float (&x)[R][TM] = a;  // reuse the registers: columns of L_q
-    load_cols<LP, R>(x, lig, sm.bufB);
-    float ssq = 0.0f;
     if (!shared) {
+      store_rows<LP, R>(a, lig, sm.bufB);
+      __syncwarp();
+      float (&x)[R][TM] = a;  // reuse the registers: columns of L_q
+      load_cols<LP, R>(x, lig, sm.bufB);
+      float ssq = 0.0f;
       solve_cols<LP, R>(x, sm.bufA, sm.dinv, Tw);
 #pragma unroll
       for (int i = 0; i < TM; ++i)
@@ -725,47 +625,37 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
           const float v = (i == lig + LP * jj) ? 0.0f : x[jj][i];
           ssq = fmaf(v, v, ssq);
         }
-    } else {
-      // bufA <- L_p^-1 packed rows (asynchronous copy issued above), dgp <- diag L_p, a = L_p^-1 m by row dot products
-      using Rec = PriorRec<LP, R>;
-      cp_async_wait<0>();
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        sm.dgp[lig + LP * j] = dgp_rec[j];
-        sm.col[lig + LP * j] = mrow[j];
-      }
-      __syncwarp();
+      part = (double)ssq;
 #pragma unroll
       for (int j = 0; j < R; ++j) {
         const int r = lig + LP * j;
-        const float* row = sm.bufA + poff_dyn(r);
-        float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-        for (int k4 = 0; k4 < LP * j + LP; k4 += 4) {
-          if (k4 <= r && k4 < Tw) {
-            const float4 l4 = *reinterpret_cast<const float4*>(row + k4);
-            const float4 m4 = *reinterpret_cast<const float4*>(sm.col + k4);
-            fma2<Geo<LP, R>::PACK>(s0, s1, l4.x, l4.y, m4.x, m4.y);
-            fma2<Geo<LP, R>::PACK>(s0, s1, l4.z, l4.w, m4.z, m4.w);
+        if (r < T) {
+          const double lpd = (double)sm.dgp[r], lqd = (double)sm.dgq[r];
+          const double av = (double)sm.as[r];
+          part += diag_term(lqd / lpd) + av * av;
+          if (P.logdets) {  // (float64 logarithms: only when the caller asked for the log-determinants)
+            ldp += 2.0 * log(lpd);
+            ldq += 2.0 * log(lqd);
           }
         }
-        sm.as[r] = s0 + s1;
       }
+    } else {
+      // log|K_q| = 2 log prod diag L_q: the product in float64 (<= 64 factors in (0.03, 2): no underflow), ONE logarithm per pair
       __syncwarp();
-      ssq = mul_cols_ssq<LP, R>(x, sm.bufA, lig, Tw);  // A = L_p^-1 L_q as a product with the stored inverse
-    }
-    part = (double)ssq;
+      double pq = 1.0;
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int r = lig + LP * j;
-      if (r < T) {
-        const double lpd = (double)sm.dgp[r], lqd = (double)sm.dgq[r];
-        const double av = (double)sm.as[r];
-        part += diag_term(lqd / lpd) + av * av;
-        if (P.logdets) {  // (float64 logarithms: only when the caller asked for the log-determinants)
-          ldp += 2.0 * log(lpd);
-          ldq += 2.0 * log(lqd);
-        }
+      for (int j = 0; j < R; ++j) {
+        const int r = lig + LP * j;
+        if (r < T) pq *= (double)sm.dgq[r];
+      }
+#pragma unroll
+      for (int o = LP / 2; o > 0; o >>= 1) pq *= __shfl_xor_sync(0xffffffffu, pq, o);
+      part = 2.0 * ((tr0 + tr1) + (tr2 + tr3));
+      if (lig == 0) {
+        const double lq2 = 2.0 * log(pq);
+        part += ldp_rec - lq2 - (double)T;
+        ldp = ldp_rec;
+        ldq = lq2;
       }
     }
   } else {  // diagonal posterior: X = L_p^-1 columns, h_c = |X[:,c]|^2
@@ -1059,10 +949,10 @@ cudaError_t launch_cfg(const Params& P, cudaStream_t st) {
   //  programmatic dependency and serialise them)
   prof_begin(BWD, st);
   if (POST == GPKL_POST_GP && P.prior != nullptr) {  // shared-prior pre-pass: one lane group per sequence
-    auto pk = prior_warp<LP, R, KERNEL, BWD>;
-    const int G = 32 / LP;
-    pk<<<(P.d.B + G - 1) / G, 32, (size_t)G * group_floats * sizeof(float), st>>>(P, group_floats);
-    note_launch();
+    // shared-prior pre-pass, one CTA per SEQUENCE (gpkl_prior64.cu): float64 K_p^-1 and log|K_p| for the forward's trace,
+    // K_p^-1 rounded to float32 (full rows) for the backward's contraction
+    e = BWD ? launch_prior_inv64_small(P, st, PriorRec<LP, R>::KI, LP * R) : launch_prior_inv64_small(P, st, 0, 0);
+    if (e != cudaSuccess) return e;
     pdl = pdl_enabled();
   }
   // With a pre-pass in front, the per-pair kernel is its programmatic dependent: it starts while the pre-pass
