@@ -1147,6 +1147,48 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) prior_block(Params P, int u
 // SH (resident sizes only): the shared-prior kernel proper.  It holds ONE work matrix in shared memory (two CTAs per
 // SM up to T = 144) and reads the prior record from global memory; it returns at once when the device flag says the
 // prior is not shared, and the ordinary kernel launched behind it (P.skip_if_shared) returns at once when it is.
+// Off-diagonal part of  tr(K_p^-1 (K_q + m m^T))  against the float64 record (fwd_block, shared-prior one-buffer path):
+// sum over i > j of Kinv(i,j) (K_q(i,j) + m_i m_j), K_q regenerated.  Columns j and T-1-j are paired (T-1 entries below the
+// diagonal together), one pair per warp trip, lanes along the rows (coalesced record reads), UB row trips (compile time: no
+// branch between them, so the kernel evaluations and the FP64 chains of a trip overlap).  All record entries of a column
+// pair are in flight before their first use, and the next pair's are issued before this pair's arithmetic.
+template <int KERNEL, int UB>
+__device__ __forceinline__ void trace_offdiag(const double* __restrict__ kinv, int ldk, int T, const float* __restrict__ ts,
+                                              const float* __restrict__ mm, const KernC<KERNEL>& kq, double& tro0, double& tro1) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int npair = (T + 1) / 2;
+  auto fetch = [&](int jj, double (&kd)[UB]) {
+    const int j2 = T - 1 - jj, n1 = T - 1 - jj, n2 = j2 != jj ? jj : 0;
+    const double* __restrict__ c1 = kinv + (size_t)jj * ldk + jj + 1;
+    const double* __restrict__ c2 = kinv + (size_t)j2 * ldk + j2 + 1 - n1;
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int r = lane + 32 * u;
+      kd[u] = (jj < npair && r < n1 + n2) ? __ldg((r < n1 ? c1 : c2) + r) : 0.0;
+    }
+  };
+  double kd[UB], kn[UB];
+  fetch(warp, kd);
+  for (int jj = warp; jj < npair; jj += nw) {
+    fetch(jj + nw, kn);
+    const int j2 = T - 1 - jj, n1 = T - 1 - jj;
+    const float t1 = ts[jj], t2 = ts[j2];
+    const double m1 = (double)mm[jj], m2 = (double)mm[j2];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int r = lane + 32 * u;
+      const bool first = r < n1;
+      int i = first ? jj + 1 + r : j2 + 1 + r - n1;
+      i = i < T ? i : T - 1;  // lanes beyond the pair: kd = 0
+      const double v = fma((double)mm[i], first ? m1 : m2, (double)kq.val(ts[i] - (first ? t1 : t2)));
+      if (u & 1) tro1 = fma(kd[u], v, tro1);
+      else tro0 = fma(kd[u], v, tro0);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) kd[u] = kn[u];
+  }
+}
+
 template <int KERNEL, int POST, bool DUAL, bool SLOT, bool SH = false>
 __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use_slot) {
   extern __shared__ __align__(16) float smem_f[];
@@ -1211,6 +1253,40 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
       phase_mark(P, 4);
       griddep_wait();  // the record is first needed here: the pre-pass overlaps the K_q factorisation
       const float* __restrict__ rec = P.prior + (size_t)b * P.prior_stride;
+      if (SH && (use_slot & 4)) {
+        // ---- float64 record (gpkl_prior64.cu): K_p^-1, lower triangle column-major with pitch ldk, log|K_p| behind it.
+        // The reference's own formula (Full_GP_VAE_dynamic_time.py:250-259)
+        //     KL = 1/2 [ tr(K_p^-1 (K_q + m m^T)) - T + log|K_p| - log|K_q| ],   tr = sum_ij Kinv_ij (K_q,ij + m_i m_j)
+        // with the K_q entries REGENERATED (T^2/2 kernel evaluations: nothing next to the factorisation): the T^3/3-flop
+        // triangular product A = L_p^-1 L_q and a = L_p^-1 m are gone.  Columns j and T-1-j are paired (T-1 entries below
+        // the diagonal together), one pair per warp trip, lanes along the rows: coalesced record reads.
+        phase_mark(P, 7);
+        const int ldk = (d.T_max + 63) / 64 * 64;
+        const double* __restrict__ kinv = reinterpret_cast<const double*>(rec);
+        const KernC<KERNEL> kq(P.ell_q[dd], sig);
+        double tro0 = 0.0, tro1 = 0.0, trd = 0.0;
+        switch ((d.T_max + 30) / 32) {  // row trips per column pair (grid-uniform; T_max <= 208 for the one-buffer sizes)
+          case 1: case 2: trace_offdiag<KERNEL, 2>(kinv, ldk, T, s.ts, s.mm, kq, tro0, tro1); break;
+          case 3: trace_offdiag<KERNEL, 3>(kinv, ldk, T, s.ts, s.mm, kq, tro0, tro1); break;
+          case 4: trace_offdiag<KERNEL, 4>(kinv, ldk, T, s.ts, s.mm, kq, tro0, tro1); break;
+          case 5: trace_offdiag<KERNEL, 5>(kinv, ldk, T, s.ts, s.mm, kq, tro0, tro1); break;
+          case 6: trace_offdiag<KERNEL, 6>(kinv, ldk, T, s.ts, s.mm, kq, tro0, tro1); break;
+          default: trace_offdiag<KERNEL, 7>(kinv, ldk, T, s.ts, s.mm, kq, tro0, tro1); break;
+        }
+        const float kdiag = kq.val(0.0f) + noise;
+        for (int i = threadIdx.x; i < T; i += blockDim.x) {
+          const double mi = (double)s.mm[i];
+          trd = fma(__ldg(kinv + (size_t)i * ldk + i), fma(mi, mi, (double)kdiag), trd);
+          ldq += 2.0 * log((double)s.dgq[i]);
+        }
+        part = trd + 2.0 * (tro0 + tro1) - ldq;
+        if (threadIdx.x == 0) {
+          ldp = __ldg(kinv + (size_t)ldk * ldk);
+          part += ldp - (double)T;
+        }
+        phase_mark(P, 8);
+        phase_mark(P, 5);
+      } else {
       for (int i = threadIdx.x; i < TP; i += blockDim.x) s.dgp[i] = __ldg(rec + rec_dg_offset(L) + i);
       phase_mark(P, 7);
       float ssq;
@@ -1258,6 +1334,7 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
           ldp += 2.0 * log(lpd);
           ldq += 2.0 * log(lqd);
         }
+      }
       }
     } else if (POST == GPKL_POST_GP) {
       if (gm) chol_gemm<KERNEL>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
@@ -1607,8 +1684,15 @@ cudaError_t launch_kp(const Params& P_in, bool backward, cudaStream_t st) {
     e = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
     if (e != cudaSuccess) return e;
     const int pgrid = sh_resident ? P.d.B : (P.d.B < kBlockSlots ? P.d.B : kBlockSlots);
-    pk<<<pgrid, 256, psmem, st>>>(P, !sh_resident ? 1 : (resident ? 0 : 2));
-    note_launch();
+    // forward of the one-buffer kernels (T > 64): float64 K_p^-1 records (gpkl_prior64.cu) and the entrywise trace
+    const bool rec64 = sh_resident && !backward && nt == 256 && POST == GPKL_POST_GP;
+    if (rec64) {
+      e = launch_prior_inv64(P, st);
+      if (e != cudaSuccess) return e;
+    } else {
+      pk<<<pgrid, 256, psmem, st>>>(P, !sh_resident ? 1 : (resident ? 0 : 2));
+      note_launch();
+    }
     if (sh_resident) {
       if (POST == GPKL_POST_GP) {  // (the SH instantiations exist for the GP posterior only)
         void (*sk)(Params, int) = backward ? bwd_block<KERNEL, GPKL_POST_GP, false, false, true>
@@ -1632,7 +1716,7 @@ cudaError_t launch_kp(const Params& P_in, bool backward, cudaStream_t st) {
         cfg.dynamicSmemBytes = smem1;
         // the pre-pass overlaps the K_q chain of the per-pair kernel (programmatic dependent launch)
         cfg.numAttrs = pdl_enabled() ? 1 : 0;
-        e = cudaLaunchKernelEx(&cfg, sk, P, 0);
+        e = cudaLaunchKernelEx(&cfg, sk, P, rec64 ? 4 : 0);
         note_launch();
         if (e != cudaSuccess) return e;
       }

@@ -59,6 +59,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 template <int KERNEL>
 __global__ void __launch_bounds__(NT, 1) prior_inv64_kernel(Params P) {
   extern __shared__ __align__(16) double smd[];
+  griddep_launch_dependents();  // a per-pair kernel launched as programmatic dependent may start; it reads the records after its griddep_wait()
   if (*P.prior_flag == 0) return;  // ell_p differs between latent dims: the per-pair kernels take their per-pair path
   const GpklDesc& d = P.d;
   const int TP = p64_tp(d.T_max), ldw = p64_ldw(TP);
