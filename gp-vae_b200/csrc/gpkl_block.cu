@@ -1231,6 +1231,8 @@ __global__ void __launch_bounds__(256, SLOT ? 1 : 2) fwd_block(Params P, int use
     if (POST == GPKL_POST_GP && shared) {
       // ---- shared-prior path: only K_q is factored here (all threads); L_p^-1 and diag L_p come from the record
       if (gm) chol_gemm<KERNEL, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.wide, s.stg, s.dgq, s.rdq, &bad);
+      else if (SH && (use_slot & 4))  // (float64-record path: no product, so no row-major copy of the factor either)
+        chol_block<KERNEL, false, false, true>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.dgq, s.rdq, &bad, G.all, s.pan2);
       else chol_block<KERNEL, false, true, !SLOT>(s.B2, L, T, false, s.ts, s.mm, P.ell_q[dd], sig, noise, s.pan, s.dgq, s.rdq, &bad, G.all,
                                            SH ? s.pan2 : nullptr);
       phase_mark(P, 3);
