@@ -110,7 +110,19 @@ __global__ void offsets_kernel(const int32_t* __restrict__ lengths, int B, int64
 __global__ void sum_pairs_kernel(const float* __restrict__ x, int n, double* __restrict__ out) {
   __shared__ double red[32];
   double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)x[i];
+  if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {  // 128-bit loads, two in flight per thread (the loop is a latency chain)
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+    const int n4 = n >> 2, bd = blockDim.x;
+    for (int i = threadIdx.x; i < n4; i += 2 * bd) {
+      const float4 a = x4[i];
+      const float4 b = i + bd < n4 ? x4[i + bd] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      acc += ((double)a.x + (double)a.y) + ((double)a.z + (double)a.w);
+      acc += ((double)b.x + (double)b.y) + ((double)b.z + (double)b.w);
+    }
+    for (int i = 4 * n4 + threadIdx.x; i < n; i += bd) acc += (double)x[i];
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)x[i];
+  }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) *out = acc;
 }

@@ -284,9 +284,11 @@ __device__ __forceinline__ void small_sweep(double (&x)[Q], const int (&rr)[Q], 
 // offset f32_off (PriorRec::KI), identity on the padding.
 // Several CTAs per SM; the per-pair kernel launched behind it (programmatic dependent launch) starts at once and waits where
 // it first reads a record.
-template <int KERNEL>
-__global__ void __launch_bounds__(NT) prior_inv64_small_kernel(Params P, int f32_off, int f32_tm) {
-  constexpr int TP = 64, Q = (TP * (TP + 1) / 2 + NT - 1) / NT;
+// NTH threads per sequence for sequences of at most NMAX points (64 / 16, 128 / 32, 256 / 64): the pivot chain is the same,
+// but barriers, the final reduction and the idle lanes of a short sequence are cheaper with fewer warps.
+template <int KERNEL, int NTH, int NMAX>
+__global__ void __launch_bounds__(NTH) prior_inv64_small_kernel(Params P, int f32_off, int f32_tm) {
+  constexpr int TP = 64, NT = NTH, Q = (NMAX * (NMAX + 1) / 2 + NT - 1) / NT;
   __shared__ double pc[2][TP + 2];
   __shared__ double piv[TP];
   __shared__ double red[32];
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(NT) prior_inv64_small_kernel(Params P, int f32
   const int tid = threadIdx.x;
   const float noise = d.noise, sig = (float)(1.0 - (double)noise);
   const KernC<KERNEL> kc(P.ell_p[0], sig);
-  if (tid < 2 * (TP + 2)) (&pc[0][0])[tid] = 0.0;
+  for (int i = tid; i < 2 * (TP + 2); i += NT) (&pc[0][0])[i] = 0.0;
   for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
     const int n = P.lengths[b];
     float* rec = P.prior + (size_t)b * P.prior_stride;
@@ -336,17 +338,16 @@ __global__ void __launch_bounds__(NT) prior_inv64_small_kernel(Params P, int f32
         x[q] = (double)(kc.val(ts[rr[q]] - ts[cc[q]]) + (rr[q] == cc[q] ? noise : 0.0f));
       }
     }
-    switch (qn) {  // (compile-time entry counts: no branch between the entries of a pivot step, their latencies overlap)
-      case 1: small_sweep<1, Q, TP>(x, rr, cc, n, pc, piv); break;
-      case 2: small_sweep<2, Q, TP>(x, rr, cc, n, pc, piv); break;
-      case 3: small_sweep<3, Q, TP>(x, rr, cc, n, pc, piv); break;
-      case 4: small_sweep<4, Q, TP>(x, rr, cc, n, pc, piv); break;
-      case 5: small_sweep<5, Q, TP>(x, rr, cc, n, pc, piv); break;
-      case 6: small_sweep<6, Q, TP>(x, rr, cc, n, pc, piv); break;
-      case 7: small_sweep<7, Q, TP>(x, rr, cc, n, pc, piv); break;
-      case 8: small_sweep<8, Q, TP>(x, rr, cc, n, pc, piv); break;
-      default: small_sweep<9, Q, TP>(x, rr, cc, n, pc, piv); break;
-    }
+    // (compile-time entry counts: no branch between the entries of a pivot step, their latencies overlap)
+    if (qn <= 1) small_sweep<1, Q, TP>(x, rr, cc, n, pc, piv);
+    else if (qn == 2) small_sweep<(Q < 2 ? Q : 2), Q, TP>(x, rr, cc, n, pc, piv);
+    else if (qn == 3) small_sweep<(Q < 3 ? Q : 3), Q, TP>(x, rr, cc, n, pc, piv);
+    else if (qn == 4) small_sweep<(Q < 4 ? Q : 4), Q, TP>(x, rr, cc, n, pc, piv);
+    else if (qn == 5) small_sweep<(Q < 5 ? Q : 5), Q, TP>(x, rr, cc, n, pc, piv);
+    else if (qn == 6) small_sweep<(Q < 6 ? Q : 6), Q, TP>(x, rr, cc, n, pc, piv);
+    else if (qn == 7) small_sweep<(Q < 7 ? Q : 7), Q, TP>(x, rr, cc, n, pc, piv);
+    else if (qn == 8) small_sweep<(Q < 8 ? Q : 8), Q, TP>(x, rr, cc, n, pc, piv);
+    else small_sweep<Q, Q, TP>(x, rr, cc, n, pc, piv);
     if (!f32_tm) {
 #pragma unroll
       for (int q = 0; q < Q; ++q)
@@ -388,10 +389,21 @@ cudaError_t launch_prior_inv64_small(const Params& P, cudaStream_t st, int f32_o
   if (P.d.T_max > 64 || f32_tm > 64) return cudaErrorInvalidValue;
   const size_t need = f32_tm ? (size_t)f32_off + (size_t)f32_tm * f32_tm : prior64_record_floats(P.d.T_max);
   if (P.prior_stride < need) return cudaErrorInvalidValue;
-  void (*ks)(Params, int, int) =
-      P.d.kernel == GPKL_KERNEL_RBF ? prior_inv64_small_kernel<GPKL_KERNEL_RBF> : prior_inv64_small_kernel<GPKL_KERNEL_CAUCHY>;
-  const int cap = 4 * kNumSMs;
-  ks<<<P.d.B < cap ? P.d.B : cap, NT, 0, st>>>(P, f32_off, f32_tm);
+  const bool rbf = P.d.kernel == GPKL_KERNEL_RBF;
+  void (*ks)(Params, int, int);
+  int nth;
+  if (P.d.T_max <= 16) {
+    nth = 64;
+    ks = rbf ? prior_inv64_small_kernel<GPKL_KERNEL_RBF, 64, 16> : prior_inv64_small_kernel<GPKL_KERNEL_CAUCHY, 64, 16>;
+  } else if (P.d.T_max <= 32) {
+    nth = 128;
+    ks = rbf ? prior_inv64_small_kernel<GPKL_KERNEL_RBF, 128, 32> : prior_inv64_small_kernel<GPKL_KERNEL_CAUCHY, 128, 32>;
+  } else {
+    nth = 256;
+    ks = rbf ? prior_inv64_small_kernel<GPKL_KERNEL_RBF, 256, 64> : prior_inv64_small_kernel<GPKL_KERNEL_CAUCHY, 256, 64>;
+  }
+  const int cap = (1024 / nth) * kNumSMs;
+  ks<<<P.d.B < cap ? P.d.B : cap, nth, 0, st>>>(P, f32_off, f32_tm);
   note_launch();
   return cudaGetLastError();
 }
