@@ -19,11 +19,17 @@ bool pdl_enabled();  // programmatic dependent launch of the per-pair kernels be
 
 // Shared-prior records (Params::prior): floats per sequence, an upper bound over the tiers' layouts
 // (warp tier: packed L_p^-1 rows + diag + K_p^-1, gpkl_warp.cuh PriorRec; block tier: gpkl_block.cu).
+// float64 forward records (gpkl_prior64.cu): column pitch in doubles.  Register tier (T_max <= 64): T_max rounded up to 8;
+// beyond: T_max rounded up to the 64 x 64 tiles.
+__host__ __device__ inline int prior64_pitch(int T_max) {
+  const int t = T_max < 1 ? 1 : T_max;
+  return t <= 64 ? (t + 7) / 8 * 8 : (t + 63) / 64 * 64;
+}
 inline size_t prior_record_floats(int T_max) {
   const size_t al = T_max > 208 ? 64 : 16;  // as Lay (gpkl_block.cu): 64 x 64 tiles beyond the resident sizes
   const size_t TP = ((size_t)(T_max < 1 ? 1 : T_max) + al - 1) / al * al;
-  const size_t tp64 = ((size_t)(T_max < 1 ? 1 : T_max) + 63) / 64 * 64;  // float64 forward records (gpkl_prior64.cu): pitch 64 k
-  const size_t f32 = 2 * (TP + 1) * (TP + 4), f64 = 2 * (tp64 * tp64 + 2);
+  const size_t p64 = (size_t)prior64_pitch(T_max);
+  const size_t f32 = 2 * (TP + 1) * (TP + 4), f64 = 2 * (p64 * p64 + 2);
   return f32 > f64 ? f32 : f64;
 }
 

@@ -278,8 +278,8 @@ __device__ __forceinline__ void small_sweep(double (&x)[Q], const int (&rr)[Q], 
 // coalesced), and one scalar symmetric sweep per pivot needs only the pivot column sym(., s), which its owners publish through
 // a double-buffered shared vector: ONE barrier per pivot, 2 FP64 operations per entry and pivot, the pivot's reciprocal by
 // MUFU.RCP + two Newton steps.
-// Forward record (f32_tm == 0): -(sweep result) = K_p^-1 in float64, lower triangle column-major with pitch 64, THE DIAGONAL
-// HALVED (the consumer's trace is 2 * sum_{k <= r}), log|K_p| at [64 * 64].
+// Forward record (f32_tm == 0): -(sweep result) = K_p^-1 in float64, lower triangle column-major, THE DIAGONAL
+// HALVED (the consumer's trace is 2 * sum_{k <= r}), log|K_p| at [pitch * pitch]; pitch = prior64_pitch(T_max) (T_max rounded up to 8).
 // Backward record (f32_tm = TM of the consumer's lane geometry): K_p^-1 rounded to float32, full symmetric TM x TM at float
 // offset f32_off (PriorRec::KI), identity on the padding.
 // Several CTAs per SM; the per-pair kernel launched behind it (programmatic dependent launch) starts at once and waits where
@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(NTH) prior_inv64_small_kernel(Params P, int f3
     const int n = P.lengths[b];
     float* rec = P.prior + (size_t)b * P.prior_stride;
     double* A = reinterpret_cast<double*>(rec);
+    const int ldk = prior64_pitch(d.T_max);  // column pitch of the float64 record
     __syncthreads();
     if (f32_tm) {  // padding of the float32 record: identity
       for (int e = tid; e < f32_tm * f32_tm; e += NT) {
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(NTH) prior_inv64_small_kernel(Params P, int f3
       }
     }
     if (n <= 0) {
-      if (tid == 0 && !f32_tm) A[(size_t)TP * TP] = 0.0;
+      if (tid == 0 && !f32_tm) A[(size_t)ldk * ldk] = 0.0;
       continue;
     }
     if (tid < n) ts[tid] = P.times[(size_t)b * d.T_max + tid];
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(NTH) prior_inv64_small_kernel(Params P, int f3
     if (!f32_tm) {
 #pragma unroll
       for (int q = 0; q < Q; ++q)
-        if (rr[q] < TP) A[(size_t)cc[q] * TP + rr[q]] = (rr[q] == cc[q] ? -0.5 : -1.0) * x[q];
+        if (rr[q] < TP) A[(size_t)cc[q] * ldk + rr[q]] = (rr[q] == cc[q] ? -0.5 : -1.0) * x[q];
     } else {
 #pragma unroll
       for (int q = 0; q < Q; ++q)
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(NTH) prior_inv64_small_kernel(Params P, int f3
     ld = block_sum(ld, red);
     bad = __syncthreads_or(bad);
     if (tid == 0) {
-      if (!f32_tm) A[(size_t)TP * TP] = ld;
+      if (!f32_tm) A[(size_t)ldk * ldk] = ld;
       if (bad && P.status) atomicAdd(P.status, 1);
     }
   }
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(NTH) prior_inv64_small_kernel(Params P, int f3
 }  // namespace
 
 size_t prior64_record_floats(int T_max) {
-  const size_t TP = p64_tp(T_max);
+  const size_t TP = T_max <= 64 ? (size_t)prior64_pitch(T_max) : (size_t)p64_tp(T_max);
   return 2 * (TP * TP + 2);
 }
 

@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
     build_rows<LP, R, KERNEL>(a, trow, sm.ts, lig, T, Tw, lq, sig, noise);
     double tr0 = 0.0, tr1 = 0.0, tr2 = 0.0, tr3 = 0.0, ldp_rec = 0.0;
     if (shared) {
-      // Shared prior: the record of this sequence is K_p^-1 in FLOAT64 (lower triangle, column-major, pitch 64, diagonal
+      // Shared prior: the record of this sequence is K_p^-1 in FLOAT64 (lower triangle, column-major, pitch prior64_pitch(T_max), diagonal
       // halved) + log|K_p| (prior_inv64_small_kernel, gpkl_prior64.cu), and the KL is the reference's own formula
       // (Full_GP_VAE_dynamic_time.py:250-259)
       //     KL = 1/2 [ tr(K_p^-1 (K_q + m m^T)) - T + log|K_p| - log|K_q| ],   tr = 2 sum_{k<=r} Kinv'_rk (K_q,rk + m_r m_k),
@@ -559,6 +559,7 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
       const double* __restrict__ kinv = reinterpret_cast<const double*>(P.prior + (size_t)pi.b * P.prior_stride);
       double* m64 = reinterpret_cast<double*>(sm.bufA);  // the mean as doubles (bufA is idle on this path)
       constexpr int TRB = LP < 16 ? LP : 16;
+      const int ldk = prior64_pitch(d.T_max);
 #pragma unroll
       for (int j = 0; j < R; ++j) m64[lig + LP * j] = (double)mrow[j];
       __syncwarp();
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
             // one batch of record entries in flight per trip (no branch between the loads: the L2 round trips overlap)
             double kd[TRB];
 #pragma unroll
-            for (int e = 0; e < TRB; ++e) kd[e] = (kb + e <= r && rin) ? __ldg(kinv + (size_t)(kb + e) * 64 + r) : 0.0;
+            for (int e = 0; e < TRB; ++e) kd[e] = (kb + e <= r && rin) ? __ldg(kinv + (size_t)(kb + e) * ldk + r) : 0.0;
 #pragma unroll
             for (int e = 0; e < TRB; e += 4) {
               tr0 = fma(kd[e], fma(mr, m64[kb + e], (double)a[j][kb + e]), tr0);
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(WPC * 32) fwd_warp(Params P, int group_floats)
           }
         }
       }
-      ldp_rec = __ldg(kinv + 64 * 64);
+      ldp_rec = __ldg(kinv + ldk * ldk);
     }
     chol_rows<LP, R>(a, lig, T, Tw, sm.col, sm.dgq, bad);
     // z_s = m + L_q eps_s from the register rows
