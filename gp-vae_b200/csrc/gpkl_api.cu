@@ -152,8 +152,10 @@ struct Workspace {
 // The shared-prior fast path applies to the GP posterior when no d/d ell_p is requested (that goes to the generic
 // tier) and the caller did not force the per-pair factorisation.
 bool prior_sharing_eligible(const GpklDesc& d) {
-  return d.posterior == GPKL_POST_GP && !(d.flags & (GPKL_FLAG_GRAD_ELL_P | GPKL_FLAG_PER_PAIR_PRIOR)) &&
-         d.tier != GPKL_TIER_GENERIC && d.B > 0;
+  if (d.flags & (GPKL_FLAG_GRAD_ELL_P | GPKL_FLAG_PER_PAIR_PRIOR)) return false;
+  if (d.tier == GPKL_TIER_GENERIC || d.B <= 0) return false;
+  if (d.posterior == GPKL_POST_BIDIAG) return d.tier != GPKL_TIER_BLOCK && bidiag_tier_supports(d);  // V3 hot tier (T <= 64)
+  return d.posterior == GPKL_POST_GP;
 }
 
 Workspace plan(const GpklDesc& d, void* base) {
@@ -207,7 +209,17 @@ int dispatch(const Params& P, bool backward, cudaStream_t st) {
   // shared memory up to T ~ 144, in an L2-backed workspace slot beyond), generic tier for the combinations
   // the specialised tiers do not implement (d/d ell_p).  Explicit requests are honoured or refused, never silently rerouted.
   cudaError_t e;
-  if (P.d.tier == GPKL_TIER_WARP) {
+  if (P.d.posterior == GPKL_POST_BIDIAG && P.prior != nullptr &&
+      (P.d.tier == GPKL_TIER_AUTO || P.d.tier == GPKL_TIER_WARP)) {
+    // V3 hot tier (T <= 64, one warp per pair, O(T^2)); if the device finds ell_p non-uniform it returns at once and the
+    // generic tier launched behind it does the work (and returns at once otherwise)
+    e = launch_bidiag(P, backward, st);
+    if (e == cudaSuccess) {
+      Params Q = P;
+      Q.skip_if_shared = 1;
+      e = launch_generic(Q, backward, st);
+    }
+  } else if (P.d.tier == GPKL_TIER_WARP) {
     if (!warp_tier_supports(P.d, backward)) return GPKL_ERR_UNSUPPORTED;
     e = launch_warp(P, backward, st);
   } else if (P.d.tier == GPKL_TIER_BLOCK) {

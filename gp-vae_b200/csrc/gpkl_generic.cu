@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(NT) fwd_generic(Params P, int Tcap, int ld_cap
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int bad;
   const GpklDesc& d = P.d;
+  if (P.skip_if_shared && P.prior_flag && *P.prior_flag != 0) return;  // fallback launch behind the V3 hot tier (gpkl_bidiag.cu)
   const int npairs = d.B * d.D;
   const int S = d.S;
   const float noise = d.noise;
@@ -335,6 +336,7 @@ __global__ void __launch_bounds__(NT) bwd_generic(Params P, int Tcap, int ld_cap
   const float noise = d.noise;
   const float sig = (float)(1.0 - (double)noise);
   const bool want_lp = (d.flags & GPKL_FLAG_GRAD_ELL_P) != 0;
+  if (P.skip_if_shared && P.prior_flag && *P.prior_flag != 0) return;  // fallback launch behind the V3 hot tier
   float* slot = mats_in_smem ? nullptr : (P.scratch ? P.scratch + (size_t)blockIdx.x * P.scratch_stride : nullptr);
   const double g_sum = P.g_kl_sum ? *P.g_kl_sum : 1.0;
   for (int p = blockIdx.x; p < npairs; p += gridDim.x) {

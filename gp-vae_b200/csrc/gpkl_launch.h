@@ -63,6 +63,11 @@ size_t prior64_record_floats(int T_max);
 cudaError_t launch_prior_inv64(const Params& P, cudaStream_t st);
 cudaError_t launch_prior_inv64_small(const Params& P, cudaStream_t st, int f32_off, int f32_tm);
 
+// V3 hot tier (gpkl_bidiag.cu): bidiagonal-precision posterior, T <= 64, shared prior; launches the register tier's float64
+// pre-pass itself.  The caller launches the generic tier behind it with skip_if_shared (non-uniform ell_p).
+bool bidiag_tier_supports(const GpklDesc& d);
+cudaError_t launch_bidiag(const Params& P, bool backward, cudaStream_t st);
+
 // reconstruction term (gpkl_recon.cu), SURVEY.md S8(f) row 1
 int recon_grid(long long rows);
 cudaError_t launch_recon_fwd(const float* x, const float* xd, const long long* off, int B, int F, int S, long long rows,

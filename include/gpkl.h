@@ -46,6 +46,10 @@ extern "C" {
 #define GPKL_VERSION 1
 
 enum { GPKL_KERNEL_RBF = 0, GPKL_KERNEL_CAUCHY = 1 };
+/* GPKL_POST_BIDIAG (V3, bidiagonal-precision posterior q = N(m, (B^T B)^-1); an extension named by north_star, not in the
+ * reference): T_max <= 64 and S <= 8 under GPKL_TIER_AUTO / GPKL_TIER_WARP run the V3 hot tier (gpkl_bidiag.cu: one warp per
+ * pair, bidiagonal solves + semiseparable recurrences against the per-sequence float64 K_p^-1, O(T^2) per pair); longer
+ * sequences, a non-uniform ell_p (decided on the device) and GPKL_FLAG_PER_PAIR_PRIOR run the dense generic tier. */
 enum { GPKL_POST_GP = 0, GPKL_POST_DIAG = 1, GPKL_POST_BIDIAG = 2 };
 enum { GPKL_TIER_AUTO = 0, GPKL_TIER_GENERIC = 1, GPKL_TIER_WARP = 2, GPKL_TIER_BLOCK = 3 };
 enum {

@@ -220,16 +220,40 @@ def test_v2_vs_oracle_irregular_times(cuda_device, B, D, T, S, ragged, kernel, t
     assert_parity(errs, "V2 %s T=%d" % (kernel, T))
 
 
+V3_GRID = [(3, 4, 1, 1, False), (2, 3, 2, 2, False), (4, 5, 7, 1, True), (3, 5, 16, 2, True), (2, 4, 33, 1, True),
+           (2, 6, 48, 1, False), (3, 7, 64, 3, True), (1, 3, 100, 2, True)]
+
+
+@pytest.mark.parametrize("tier", ["auto", "warp", "generic"])
 @pytest.mark.parametrize("kernel", ["rbf", "cauchy"])
 @pytest.mark.parametrize("grid", [True, False])
-@pytest.mark.parametrize("B,D,T,S,ragged", [(3, 4, 1, 1, False), (2, 3, 2, 2, False), (4, 5, 7, 1, True), (3, 5, 16, 2, True),
-                                            (2, 4, 33, 1, True), (2, 6, 48, 1, False), (1, 3, 100, 2, True)])
-def test_v3_bidiag_vs_oracle(cuda_device, B, D, T, S, ragged, grid, kernel):
+@pytest.mark.parametrize("B,D,T,S,ragged", V3_GRID)
+def test_v3_bidiag_vs_oracle(cuda_device, B, D, T, S, ragged, grid, kernel, tier):
     """V3 (bidiagonal-precision posterior, an extension named by north_star; NOT in the reference):
-    checked against the float64 dense oracle only -- parity unpinned by the reference."""
+    checked against the float64 dense oracle only -- parity unpinned by the reference.
+    tier "auto" / "warp": the V3 hot tier (gpkl_bidiag.cu: one warp per pair, O(T^2), float64 prior record) for T <= 64;
+    "generic": the dense correctness-first path (also what "auto" uses beyond T = 64)."""
+    if tier == "warp" and T > 64:
+        pytest.skip("the V3 hot tier serves T <= 64")
     case = orc.synthetic_batch(B, D, T, S, ragged=ragged, seed=300 + T, posterior="bidiag", grid=grid)
-    errs = compare(case, cuda_device, floor=not grid, kernel=kernel, posterior="bidiag", S=S, tier="auto", grad_ell_p=False)
-    assert_parity(errs, "V3 %s T=%d" % (kernel, T))
+    errs = compare(case, cuda_device, floor=not grid, kernel=kernel, posterior="bidiag", S=S, tier=tier, grad_ell_p=False)
+    assert_parity(errs, "V3 %s T=%d tier=%s" % (kernel, T, tier))
+
+
+@pytest.mark.parametrize("T", [5, 20, 48])
+def test_v3_hot_tier_matches_generic_and_falls_back(cuda_device, T):
+    """The V3 hot tier and the generic tier agree (same inputs), and with ell_p differing between latent dims the hot
+    tier's kernels return at once (device flag) and the generic tier launched behind them produces the result."""
+    case = orc.synthetic_batch(3, 5, T, 2, ragged=True, seed=900 + T, posterior="bidiag", grid=True)
+    hf, hb = run_cuda(case, cuda_device, posterior="bidiag", S=2, tier="auto", grad_ell_p=False)
+    gf, gb = run_cuda(case, cuda_device, posterior="bidiag", S=2, tier="generic", grad_ell_p=False)
+    for k in ("kl_pairs", "z"):
+        assert rel_err(hf[k].cpu(), gf[k].cpu()) < 2e-5, (k, rel_err(hf[k].cpu(), gf[k].cpu()))
+    for k in ("g_mean", "g_aux"):
+        assert rel_err(hb[k].cpu(), gb[k].cpu()) < 2e-4, (k, rel_err(hb[k].cpu(), gb[k].cpu()))
+    case["ell_p"] = case["ell_p"] * torch.linspace(0.8, 1.2, case["ell_p"].numel())
+    errs = compare(case, cuda_device, posterior="bidiag", S=2, tier="auto", grad_ell_p=False)
+    assert_parity(errs, "V3 non-uniform ell_p T=%d" % T)
 
 
 @pytest.mark.parametrize("tier,lp", [("generic", True), ("block", False), ("auto", False)])
