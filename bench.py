@@ -56,15 +56,18 @@ def executed_flops(T, B, D, shared_prior):
     if not shared_prior:
         return B * D * f, B * D * 2.0 * f
     if tile_forward(T):
-        # tile tier, forward: the trace tr(K_p^-1 K_q) is evaluated entrywise against a float64 K_p^-1 (O(T^2) per pair), so
-        # the only FP32 O(T^3) work per pair is chol K_q; the float64 per-sequence inverse (T^3 DP flops per sequence, FP64
-        # pipe) is inside the timed launch but not counted as FP32 work
-        return B * D * (1.0 / 3.0) * f, B * D * (4.0 / 3.0) * f + B * f
+        # forward (every shared-prior tier up to T = 512 since round 2: warp, one-buffer block, tile): the trace tr(K_p^-1 K_q) is
+        # evaluated entrywise against a float64 K_p^-1 (O(T^2) per pair), so the only FP32 O(T^3) work per pair is chol K_q; the
+        # float64 per-sequence inverse (T^3 DP flops per sequence, FP64 pipe) is inside the timed launch but not counted as
+        # FP32 work.  Backward: chol K_q, L_q^-1, contraction per pair; the per-sequence float32 K_p^-1 of the block / tile
+        # tiers (T^3) -- the register tier (T <= 64) takes its backward record from the float64 sweep too.
+        return B * D * (1.0 / 3.0) * f, B * D * (4.0 / 3.0) * f + (B * f if T > 64 else 0.0)
     return B * D * (2.0 / 3.0) * f + B * (2.0 / 3.0) * f, B * D * (4.0 / 3.0) * f + B * f
 
 
 def tile_forward(T):
-    return 208 < T <= 512
+    """Forward through the float64 K_p^-1 record (name kept from the round in which only the tile tier had it)."""
+    return T <= 512
 
 
 def algo_bytes_pair(T, S=1):
@@ -366,7 +369,7 @@ def roofline_block(w, B, fwd_ms, bwd_ms, peak, shared_prior, step_ms, hbm_peak, 
         "unit": "TFLOP/s", "frac": ach_bwd / peak if peak > 0 else None, "traffic": traffic,
         "peak_source": "FFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry; "
                        "nominal 148x128x2x1.965GHz = 74.4)",
-        "algorithmic": ("shared prior: %d pairs x 4/3 T^3 + %d sequences x T^3 flops" % (npairs, B)) if shared_prior
+        "algorithmic": ("shared prior: %d pairs x 4/3 T^3 + %d sequences x T^3 flops" % (npairs, B if T > 64 else 0)) if shared_prior
                        else "%d pairs x 2*T^3 flops" % npairs,
         "model_frac": mod_bwd / peak if peak > 0 else None, "shared_prior": bool(shared_prior),
         "launch_ms": bwd_ms,
@@ -462,6 +465,39 @@ def note(msg):
     """Progress line on stderr (the JSON line on stdout stays the only stdout output)."""
     sys.stderr.write("[bench %7.1fs] %s\n" % (time.perf_counter() - _T0, msg))
     sys.stderr.flush()
+
+
+def v3_bench(gpkl, dev, flush):
+    """Forward + backward of the V3 posterior on the c2 shape (T=48, D=35, B=256), median of 20, CUDA events, L2 flushed."""
+    import gp_kl_oracle as orc
+    ws = WORKLOADS["c2"]
+    c = orc.synthetic_batch(ws["B"], ws["D"], ws["T"], 1, ragged=False, seed=77, posterior="bidiag", grid=True)
+    d = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in c.items()}
+    row = {"workload": "V3 bidiagonal-precision posterior on the c2 shape (T=%d D=%d B=%d)" % (ws["T"], ws["D"], ws["B"])}
+    for tier in ("auto", "generic"):
+        def f():
+            gpkl.gp_prior_kl_forward(d["mean"], d["times"], d["lengths"], d["ell_q"], d["ell_p"], d["eps"], aux=d["aux"],
+                                     posterior="bidiag", S=1, tier=tier)
+
+        def g():
+            gpkl.gp_prior_kl_backward(d["mean"], d["times"], d["lengths"], d["ell_q"], d["ell_p"], d["eps"], d["g_z"],
+                                      aux=d["aux"], posterior="bidiag", S=1, tier=tier, grad_ell_p=False)
+        ms = []
+        for fn in (f, g):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(20):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                b.synchronize()
+                ts.append(a.elapsed_time(b))
+            ts.sort()
+            ms.append(ts[10])
+        row["hot_tier" if tier == "auto" else "generic_tier"] = {"fwd_ms": ms[0], "bwd_ms": ms[1], "value": ws["B"] / ((ms[0] + ms[1]) * 1e-3),
+                                                                 "unit": "sequences/s"}
+    return row
 
 
 def main():
@@ -645,6 +681,13 @@ def main():
             sec.append(row)
             note("secondary %s done" % name)
         out["secondary"] = sec
+    # ---- V3 (bidiagonal-precision posterior, north_star (c)) on the c2 shape: hot tier (gpkl_bidiag.cu) next to the generic tier ----
+    if world == 1 and not args.no_secondary:
+        try:
+            out["v3"] = v3_bench(gpkl, dev, flush)
+        except Exception as ex:
+            out["v3"] = {"error": repr(ex)[:200]}
+        note("v3 done")
     # ---- short T-sweep (N=1): FP32 fraction of the forward / backward kernels at T >= 128 --------------------------------
     if world == 1 and not args.no_sweep:
         sweep = []
