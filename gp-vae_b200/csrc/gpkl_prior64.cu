@@ -410,7 +410,8 @@ cudaError_t launch_prior_inv64_small(const Params& P, cudaStream_t st, int f32_o
 }
 
 cudaError_t launch_prior_inv64(const Params& P, cudaStream_t st) {
-  if (P.d.T_max <= 64) return launch_prior_inv64_small(P, st, 0, 0);
+  // (T_max <= 64 is the register tier's: launch_prior_inv64_small, whose record differs -- pitch prior64_pitch(), diagonal halved)
+  if (P.d.T_max <= 64) return cudaErrorInvalidValue;
   const int TP = p64_tp(P.d.T_max);
   const size_t smem = ((size_t)2 * NB * p64_ldw(TP) + NB * (NB + 1) + TP) * sizeof(double) + (size_t)TP * sizeof(float);
   if (smem > kMaxDynSmem || P.prior_stride < prior64_record_floats(P.d.T_max)) return cudaErrorInvalidValue;
