@@ -286,10 +286,13 @@ def measure_device(gpkl, L, w, dev, steps, warmup, cfg, *, world=1, flush=None, 
                 compute(buckets[k])  # warms the workspace cache of the capture stream
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize()
+        graph_nodes = 0
         for k in (0, 1):
             g = torch.cuda.CUDAGraph()
+            n0 = L.gpkl_launch_count()
             with torch.cuda.graph(g, stream=side):
                 compute(buckets[k])
+            graph_nodes = L.gpkl_launch_count() - n0  # the library's kernels captured per step (replays do not pass the counter)
             graphs[k] = g
 
     def step():
@@ -346,6 +349,8 @@ def measure_device(gpkl, L, w, dev, steps, warmup, cfg, *, world=1, flush=None, 
     sampler.sample()
     per_step_launches = None
     lib_launches = L.gpkl_launch_count() - launches0
+    if use_graph:
+        lib_launches = graph_nodes * steps
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     fwd_ms, bwd_ms = ctypes.c_double(0), ctypes.c_double(0)
     nf, nb = ctypes.c_int32(0), ctypes.c_int32(0)
@@ -514,6 +519,9 @@ def main():
     ap.add_argument("--per-pair-prior", action="store_true",
                     help="A/B: force the per-pair prior factorisation (GPKL_FLAG_PER_PAIR_PRIOR) instead of the "
                          "shared-prior fast path")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the step's forward+backward from a CUDA graph (launch-bound workloads, e.g. c3 over 8 GPUs; "
+                         "the all-reduce stays an eager NCCL call behind the replay; no per-kernel times in this mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the short T-sweep of kernel FP32 fractions")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short c2 / c1 / c3 lines (N=1 only)")
@@ -563,7 +571,8 @@ def main():
 
     note("FP32 peak %.1f TFLOP/s; timing %s" % (best_peak, args.workload))
     # ---- device-resident timed region ----------------------------------------------------------------
-    m = measure_device(gpkl, L, w, dev, args.steps, warmup, cfg, world=world, flush=flush, grad_ell_p=args.grad_ell_p)
+    m = measure_device(gpkl, L, w, dev, args.steps, warmup, cfg, world=world, flush=flush, grad_ell_p=args.grad_ell_p,
+                       use_graph=args.graph)
     case = m["case"]
     host = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
     # our launches: the library's own count + per step the KL copy into the bucket (+ the NCCL all-reduce at N>1)
@@ -644,7 +653,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload + ": " + w["desc"], "per_gpu_batch": B, "global_batch": B * world,
                    "parallelism": "dp%d (sequences sharded; async all-reduce of lengthscale grads overlapped with the next step)" % world,
-                   "l2": "256 MiB flush between timed iterations", "tier": args.tier,
+                   "l2": "256 MiB flush between timed iterations", "tier": args.tier, "cuda_graph": bool(args.graph),
                    "grad_ell_p": bool(args.grad_ell_p)},
         "clocks": m["clocks"],
         "e2e": {"value": e2e_val, "unit": "sequences/s", "h2d_bytes_per_step": int(h2d_b),
