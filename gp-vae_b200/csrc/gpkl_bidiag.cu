@@ -27,16 +27,32 @@ namespace {
 
 constexpr int BW = 4;        // warps (pairs) per CTA
 constexpr int TMX = 64;      // longest sequence of this tier
-constexpr int YLD = TMX + 1;  // row pitch of the Y table (odd: lane i reads column i conflict-free)
 
-struct BdSm {  // per-warp shared memory
-  double g[TMX + 1];   // g_i = -c_i / b_i (0 beyond the sequence)
-  double sd[TMX + 1];  // Sigma_ii (sd[T] = 0)
-  double m[TMX];
-  float b[TMX], c[TMX], h[TMX], rb[TMX];  // b_i, c_i, h_i = -c_i / b_{i+1}, 1 / b_i
-  float w[8][TMX];                        // w_s = B^-1 eps_s per sample (S <= 8)
-  float lam[8][TMX];                      // lambda_s = B^-T g_z,s (backward)
+// Per-warp shared memory, sized by the batch (tm = T_max rounded up to 8, S samples): doubles g[tm+1] (g_i = -c_i / b_i, 0 beyond
+// the sequence), sd[tm+1] (Sigma_ii, sd[T] = 0), m[tm]; floats b, c, h (h_i = -c_i / b_{i+1}), rb (1 / b_i), w[S][tm]
+// (w_s = B^-1 eps_s), lam[S][tm] (lambda_s = B^-T g_z,s; backward), Y[tm][tm+1] (backward; odd pitch: lane i reads column i
+// conflict-free).
+struct BdSm {
+  double *g, *sd, *m;
+  float *b, *c, *h, *rb, *w, *lam, *Y;
+  int tm;
+  __host__ __device__ static size_t bytes(int tm, int S, bool backward) {
+    return (size_t)(3 * tm + 2) * sizeof(double) + ((size_t)4 * tm + (size_t)(backward ? 2 : 1) * S * tm + (backward ? (size_t)tm * (tm + 1) : 0) + 2) * sizeof(float);
+  }
+  __device__ BdSm(unsigned char* base, int tm_, int S, bool backward) : tm(tm_) {
+    g = reinterpret_cast<double*>(base);
+    sd = g + tm + 1;
+    m = sd + tm + 1;
+    b = reinterpret_cast<float*>(m + tm);
+    c = b + tm;
+    h = c + tm;
+    rb = h + tm;
+    w = rb + tm;
+    lam = w + (size_t)S * tm;
+    Y = backward ? lam + (size_t)S * tm : nullptr;
+  }
 };
+__host__ __device__ inline size_t bd_warp_bytes(int tm, int S, bool backward) { return (BdSm::bytes(tm, S, backward) + 15) / 16 * 16; }
 
 struct BdPair {
   int p, b, d, T;
@@ -57,10 +73,11 @@ __device__ __forceinline__ BdPair bd_pair(const Params& P) {
 
 // b, c, m of the pair into shared memory; g, h, 1/b; Sigma_ii by the backward recurrence (lane 0); w_s by back substitution
 // (lanes 1..S), eps from the caller's tensor or the in-kernel generator.
-__device__ __forceinline__ void bd_load(const Params& P, const BdPair& q, BdSm& s, int lane) {
+__device__ __forceinline__ void bd_load(const Params& P, const BdPair& q, const BdSm& s, int lane) {
   const GpklDesc& d = P.d;
   const int T = q.T;
-  for (int i = lane; i < TMX; i += 32) {
+  const int tm = s.tm;
+  for (int i = lane; i < tm; i += 32) {
     const bool ok = i < T;
     const float bi = ok ? P.aux[((size_t)(q.r0 + i) * d.D + q.d) * 2] : 1.0f;
     const float ci = (i + 1 < T) ? P.aux[((size_t)(q.r0 + i) * d.D + q.d) * 2 + 1] : 0.0f;
@@ -70,9 +87,9 @@ __device__ __forceinline__ void bd_load(const Params& P, const BdPair& q, BdSm& 
     s.g[i] = -(double)ci / (double)bi;
     s.m[i] = ok ? (double)P.mean[(size_t)(q.r0 + i) * d.D + q.d] : 0.0;
   }
-  if (lane == 0) s.g[TMX] = 0.0;
+  if (lane == 0) s.g[tm] = 0.0;
   __syncwarp();
-  for (int i = lane; i < TMX; i += 32) s.h[i] = (i + 1 < T) ? -s.c[i] / s.b[i + 1] : 0.0f;
+  for (int i = lane; i < tm; i += 32) s.h[i] = (i + 1 < T) ? -s.c[i] / s.b[i + 1] : 0.0f;
   if (lane == 0) {
     double acc = 0.0;
     s.sd[T] = 0.0;
@@ -87,7 +104,7 @@ __device__ __forceinline__ void bd_load(const Params& P, const BdPair& q, BdSm& 
     for (int i = T - 1; i >= 0; --i) {  // w_i = (eps_i - c_i w_{i+1}) / b_i
       const float e = eps_value(P, ((size_t)q.p * d.S + sx) * d.T_max + i);
       wv = (e - s.c[i] * wv) * s.rb[i];
-      s.w[sx][i] = wv;
+      s.w[sx * tm + i] = wv;
     }
   }
   __syncwarp();
@@ -98,7 +115,8 @@ __global__ void __launch_bounds__(BW * 32) fwd_bidiag(Params P) {
   if (*P.prior_flag == 0) return;  // ell_p differs between latent dims: the generic tier launched behind does the work
   const GpklDesc& d = P.d;
   const int lane = threadIdx.x & 31;
-  BdSm& s = reinterpret_cast<BdSm*>(bd_raw)[threadIdx.x >> 5];
+  const int tm = prior64_pitch(d.T_max);
+  const BdSm s(bd_raw + (size_t)(threadIdx.x >> 5) * bd_warp_bytes(tm, d.S, false), tm, d.S, false);
   const BdPair q = bd_pair(P);
   const int T = q.T;
   if (!q.active) return;
@@ -112,7 +130,7 @@ __global__ void __launch_bounds__(BW * 32) fwd_bidiag(Params P) {
   bd_load(P, q, s, lane);
   for (int sx = 0; sx < d.S; ++sx)
     for (int i = lane; i < T; i += 32)
-      P.z[((size_t)d.S * q.r0 + (size_t)sx * T + i) * d.D + q.d] = (float)s.m[i] + s.w[sx][i];
+      P.z[((size_t)d.S * q.r0 + (size_t)sx * T + i) * d.D + q.d] = (float)s.m[i] + s.w[sx * tm + i];
   // tr(K_p^-1 (Sigma + m m^T)) = 2 sum_{k <= r} Kinv'_rk (Sigma_rk + m_r m_k)   (record: diagonal halved, gpkl_prior64.cu)
   const int ldk = prior64_pitch(d.T_max);
   const double* __restrict__ kinv = reinterpret_cast<const double*>(P.prior + (size_t)q.b * P.prior_stride);
@@ -167,8 +185,9 @@ __global__ void __launch_bounds__(BW * 32) bwd_bidiag(Params P) {
   if (*P.prior_flag == 0) return;
   const GpklDesc& d = P.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  BdSm& s = reinterpret_cast<BdSm*>(bd_raw)[warp];
-  float* Y = reinterpret_cast<float*>(bd_raw + BW * sizeof(BdSm)) + (size_t)warp * TMX * YLD;  // Y[k * YLD + r]
+  const int tm = prior64_pitch(d.T_max), YLD = tm + 1;
+  const BdSm s(bd_raw + (size_t)warp * bd_warp_bytes(tm, d.S, true), tm, d.S, true);
+  float* Y = s.Y;  // Y[k * YLD + r]
   const BdPair q = bd_pair(P);
   const int T = q.T, S = d.S;
   if (!q.active || T <= 0) return;
@@ -180,19 +199,26 @@ __global__ void __launch_bounds__(BW * 32) bwd_bidiag(Params P) {
     for (int i = 0; i < T; ++i) {
       const float gz = P.g_z ? P.g_z[((size_t)S * q.r0 + (size_t)lane * T + i) * d.D + q.d] : 0.0f;
       lv = (gz - (i > 0 ? s.c[i - 1] : 0.0f) * lv) * s.rb[i];
-      s.lam[lane][i] = lv;
+      s.lam[lane * tm + i] = lv;
     }
   }
-  const int tm = prior64_pitch(d.T_max);
   const float* __restrict__ kinv = P.prior + (size_t)q.b * P.prior_stride;  // kinv[k * tm + r], symmetric
   // row r of Y = K_p^-1 W along k, and alpha_r = (K_p^-1 m)_r in the same pass
   for (int r = lane; r < T; r += 32) {
     float y = 0.0f, al = 0.0f;
-    for (int k = 0; k < T; ++k) {
-      const float kv = __ldg(kinv + (size_t)k * tm + r);
-      y = fmaf(k > 0 ? s.h[k - 1] : 0.0f, y, kv * s.rb[k]);
-      al = fmaf(kv, (float)s.m[k], al);
-      Y[k * YLD + r] = y;
+    for (int kb = 0; kb < T; kb += 8) {  // eight record entries in flight (tm is a multiple of 8: the padding reads are in bounds)
+      float kv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) kv[e] = __ldg(kinv + (size_t)(kb + e) * tm + r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = kb + e;
+        if (k < T) {
+          y = fmaf(k > 0 ? s.h[k - 1] : 0.0f, y, kv[e] * s.rb[k]);
+          al = fmaf(kv[e], (float)s.m[k], al);
+          Y[k * YLD + r] = y;
+        }
+      }
     }
     float gzs = 0.0f;
     if (P.g_z)
@@ -219,8 +245,8 @@ __global__ void __launch_bounds__(BW * 32) bwd_bidiag(Params P) {
     const float d2 = fmaf(gi * (float)s.sd[i + 1], A, Bq);
     float gb = g * (s.rb[i] - d1), gc = -g * d2;
     for (int sx = 0; sx < S; ++sx) {  // sample path: -lambda_i w_i, -lambda_i w_{i+1}
-      gb = fmaf(-s.lam[sx][i], s.w[sx][i], gb);
-      if (i + 1 < T) gc = fmaf(-s.lam[sx][i], s.w[sx][i + 1], gc);
+      gb = fmaf(-s.lam[sx * tm + i], s.w[sx * tm + i], gb);
+      if (i + 1 < T) gc = fmaf(-s.lam[sx * tm + i], s.w[sx * tm + i + 1], gc);
     }
     float* ga = P.g_aux + ((size_t)(q.r0 + i) * d.D + q.d) * 2;
     ga[0] = gb;
@@ -240,7 +266,7 @@ cudaError_t launch_bidiag(const Params& P, bool backward, cudaStream_t st) {
   if (e != cudaSuccess) return e;
   const int npairs = P.d.B * P.d.D;
   const int grid = (npairs + BW - 1) / BW;
-  const size_t smem = BW * sizeof(BdSm) + (backward ? (size_t)BW * TMX * YLD * sizeof(float) : 0);
+  const size_t smem = BW * bd_warp_bytes(prior64_pitch(P.d.T_max), P.d.S, backward);
   void (*kern)(Params) = backward ? bwd_bidiag : fwd_bidiag;  // (the kernel kind only enters through the pre-pass)
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
