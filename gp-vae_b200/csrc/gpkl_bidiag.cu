@@ -103,7 +103,7 @@ __device__ __forceinline__ void bd_load(const Params& P, const BdPair& q, const 
     float wv = 0.0f;
     for (int i = T - 1; i >= 0; --i) {  // w_i = (eps_i - c_i w_{i+1}) / b_i
       const float e = eps_value(P, ((size_t)q.p * d.S + sx) * d.T_max + i);
-      wv = (e - s.c[i] * wv) * s.rb[i];
+      wv = __fmul_rn(__fmaf_rn(-s.c[i], wv, e), s.rb[i]);  // (explicit: no contraction with the inlined noise generator)
       s.w[sx * tm + i] = wv;
     }
   }

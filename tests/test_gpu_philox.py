@@ -63,3 +63,24 @@ def test_autograd_op_draws_in_kernel(cuda_device):
                                        case["g_z"])
     assert rel_err(z1, out["z"]) < 1e-5 and rel_err(mean.grad, grads["mean"]) < 1e-4
     assert rel_err(lq.grad, grads["ell_q"]) < 1e-4
+
+
+@pytest.mark.parametrize("T,S", [(9, 3), (48, 1), (64, 2)])
+def test_seeded_op_equals_explicit_eps_v3_hot_tier(cuda_device, T, S):
+    """The V3 hot tier (gpkl_bidiag.cu) draws its noise in the kernel too: seed == materialised stream, bit for bit."""
+    import gpkl
+    dev = cuda_device
+    B, D = 3, 4
+    case = orc.synthetic_batch(B, D, T, S, ragged=True, seed=850 + T, posterior="bidiag", grid=True)
+    c = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in case.items()}
+    seed = torch.tensor([13579 + T], dtype=torch.int64, device=dev)
+    eps = gpkl.philox_normal(seed, B * D * S * T, device=dev).reshape(B, D, S, T)
+    a = (c["mean"], c["times"], c["lengths"], c["ell_q"], c["ell_p"])
+    kw = dict(aux=c["aux"], posterior="bidiag", S=S, tier="auto")
+    f0 = gpkl.gp_prior_kl_forward(*a, eps, **kw)
+    f1 = gpkl.gp_prior_kl_forward(*a, seed, **kw)
+    b0 = gpkl.gp_prior_kl_backward(*a, eps, c["g_z"], **kw)
+    b1 = gpkl.gp_prior_kl_backward(*a, seed, c["g_z"], **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(f0["z"], f1["z"]) and torch.equal(f0["kl_pairs"], f1["kl_pairs"])
+    assert torch.equal(b0["g_mean"], b1["g_mean"]) and torch.equal(b0["g_aux"], b1["g_aux"])
