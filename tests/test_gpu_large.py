@@ -173,3 +173,25 @@ def test_full_size_c3_sampled_pairs_vs_oracle(cuda_device):
 def test_full_size_c4_sampled_pairs_vs_oracle(cuda_device):
     """BASELINE config C4 at full size (T=512, D=64, B=1024, Cauchy): 8 x 8 sampled pairs against the oracle."""
     _sample_pairs_check(cuda_device, 1024, 64, 512, "cauchy", 8, 8, 7300, "C4 full size")
+
+
+def test_full_size_c2_shape_v3_hot_tier_sampled_sequences_vs_oracle(cuda_device):
+    """V3 (bidiagonal-precision posterior) on the C2 shape at full size (T=48, D=35, B=256) through the V3 hot tier
+    (gpkl_bidiag.cu): six sampled sequences, all latent dims, against the float64 dense oracle (pairs are independent)."""
+    B, D, T = 256, 35, 48
+    case = orc.synthetic_batch(B, D, T, 1, ragged=True, seed=7400, posterior="bidiag", grid=True)
+    fwd, bwd = run_cuda(case, cuda_device, posterior="bidiag", tier="auto", grad_ell_p=False)
+    assert int(fwd["status"]) == 0
+    off = torch.zeros(B + 1, dtype=torch.int64)
+    off[1:] = case["lengths"].to(torch.int64).cumsum(0)
+    seqs = torch.randperm(B, generator=torch.Generator().manual_seed(7401))[:6].sort().values
+    rows = torch.cat([torch.arange(int(off[b]), int(off[b + 1])) for b in seqs.tolist()])
+    sub = dict(mean=case["mean"][rows], times=case["times"][seqs], lengths=case["lengths"][seqs], ell_q=case["ell_q"],
+               ell_p=case["ell_p"], eps=case["eps"][seqs], g_z=case["g_z"][rows], aux=case["aux"][rows])
+    out, grads = orc.gp_prior_kl_grads(sub["mean"], sub["times"], sub["lengths"], sub["ell_q"], sub["ell_p"], sub["eps"],
+                                       sub["g_z"], aux=sub["aux"], posterior="bidiag")
+    kl = fwd["kl_pairs"].cpu().reshape(B, D)[seqs].reshape(-1)
+    errs = {"kl": rel_err(kl, out["kl_pairs"]), "z": rel_err(fwd["z"].cpu()[rows], out["z"]),
+            "g_mean": rel_err(bwd["g_mean"].cpu()[rows], grads["mean"]), "g_aux": rel_err(bwd["g_aux"].cpu()[rows], grads["aux"])}
+    print("V3 hot tier, C2 shape, sampled sequences: %s" % errs)
+    assert errs["kl"] < TOL_KL and errs["z"] < TOL_Z and errs["g_mean"] < TOL_GRAD and errs["g_aux"] < TOL_GRAD, errs
