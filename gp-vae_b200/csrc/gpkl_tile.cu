@@ -430,7 +430,12 @@ __device__ __forceinline__ void diag_block64(float* __restrict__ D, float* __res
 // all threads pre-filled with the generated kernel matrix, in part order (flush_begin / flush_end).
 // The diagonal tile is updated first, by all warps; then warps 6-7 factor and invert it (the serial chain of the panel,
 // ~20 K cycles) WHILE the other warps update the tiles below it, and join them for a smaller share when they are done.
-constexpr int kDiagChunks = 4;  // the team's factor + invert + publish, in units of one warp's chunk time (~2.3 K cycles)
+// The team's factor + invert + publish in units of one worker warp's chunk time (~2.3-2.6 K cycles).  The routine measures 17 K
+// cycles stand-alone but ~30 K next to six streaming workers, i.e. 10-13 chunks: with the first estimate (4) the team was dealt
+// more of the panel update than it could finish in time and the workers waited for it.  Measured on C4 (sequences/s):
+// 4 -> 1743, 6 -> 1762, 8 -> 1788, 10 -> 1802, 11 -> 1801, 13 -> 1799, 16 -> 1793  (GPKL_DIAG_CHUNKS overrides: experiments).
+constexpr int kDiagChunks = 10;
+__device__ int g_diag_chunks = kDiagChunks;
 
 // kinv (forward only, else NULL): this sequence's K_p^-1 in float64 (lower triangle, column-major, pitch ldk; gpkl_prior64.cu);
 // the pass that generates K_q also accumulates  tr(K_p^-1 (K_q + m m^T)) = sum_ij Kinv_ij (K_q,ij + m_i m_j)  into tr (per
@@ -545,7 +550,8 @@ __device__ __forceinline__ void chol_panels_tile(const Pair<KERNEL>& pr, float* 
       __syncthreads();
     } else {
       const int U = (m - 1) * n;  // chunks of the tiles below the diagonal one
-      int st = (U + 2 * kDiagChunks) / NW - kDiagChunks;  // the team's share once it has finished the diagonal block
+      const int kdc = g_diag_chunks;
+      int st = (U + 2 * kdc) / NW - kdc;  // the team's share once it has finished the diagonal block
       if (st < 0) st = 0;
       if (W.w >= 6) {
         float* mine = s.stg + (size_t)6 * WSTG_F;  // the team's own stage areas (one tile) as scratch; panel tile 0 is free (J > 0)
@@ -1059,6 +1065,8 @@ cudaError_t launch_tile(const Params& P_in, bool backward, cudaStream_t st) {
     const cudaError_t pe = launch_prior_inv64(P, st);
     if (pe != cudaSuccess) return pe;
   }
+  static const int env_dc = [] { const char* e = getenv("GPKL_DIAG_CHUNKS"); return e ? atoi(e) : 0; }();
+  if (env_dc > 0) cudaMemcpyToSymbolAsync(g_diag_chunks, &env_dc, sizeof(int), 0, cudaMemcpyHostToDevice, st);
   void (*kern)(Params);
   if (P.d.kernel == GPKL_KERNEL_RBF) kern = backward ? bwd_tile<GPKL_KERNEL_RBF> : fwd_tile<GPKL_KERNEL_RBF>;
   else kern = backward ? bwd_tile<GPKL_KERNEL_CAUCHY> : fwd_tile<GPKL_KERNEL_CAUCHY>;
