@@ -417,3 +417,12 @@ def test_grad_ell_p_warp_tier(cuda_device, T, S, kernel):
     _, bg = run_cuda(case, cuda_device, kernel=kernel, S=S, tier="generic", grad_ell_p=True)
     assert rel_err(bw["g_ell_p"], bg["g_ell_p"]) < 2e-4
     assert rel_err(bw["g_ell_q"], bg["g_ell_q"]) < 2e-4
+
+
+@pytest.mark.parametrize("posterior", ["gp", "bidiag"])
+def test_more_sequences_than_prepass_ctas(cuda_device, posterior):
+    """B larger than the grid cap of the per-sequence float64 pre-pass (gpkl_prior64.cu: 4 x 148 CTAs of 256 threads, more
+    for shorter sequences): its grid-stride loop over the sequences, for the register tier and the V3 hot tier."""
+    case = orc.synthetic_batch(1300, 2, 40, 1, ragged=True, seed=4242, posterior=posterior, grid=True)
+    errs = compare(case, cuda_device, posterior=posterior, S=1, tier="auto", grad_ell_p=False)
+    assert_parity(errs, "B=1300 %s" % posterior)
