@@ -687,6 +687,8 @@ def main():
                     row["roofline"] = {k: rf[k] for k in ("frac", "model_frac", "hbm_frac", "kernel_share_of_step", "launch_ms")}
                     row["roofline"]["forward_frac"] = rf["forward"]["frac"]
                     row["roofline"]["forward_launch_ms"] = rf["forward"]["launch_ms"]
+            # the same kernels under graph replay (kernel times from the eager pass: replays carry no per-kernel events)
+            row["graph"]["kernel_share_of_step"] = row["roofline"]["kernel_share_of_step"] * row["eager"]["ms_per_step"] / row["graph"]["ms_per_step"]
             sec.append(row)
             note("secondary %s done" % name)
         out["secondary"] = sec
